@@ -1,0 +1,745 @@
+"""CPU oracle: numpy restatement of the PDEControlGym hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file restates, from scratch, the algorithms of the reference's environment dynamics
+(`/root/reference/pde_control_gym/src/...`, citations below are relative to that tree) so that
+the CUDA kernels in `pdecontrolgym_b200/csrc` can be checked on machines where the reference
+tree does not exist (the GPU box).  It is the *checker*: only `tests/`, `__graft_entry__.smoke()`
+and `bench.py`'s CPU-baseline / `--impl reference` legs may import it.  The product package
+never does (and raises if its CUDA library is missing rather than falling back to this).
+
+Pinning: every class here is compared (a) bit-for-bit with the live reference in
+`tests/test_oracle_vs_reference.py` (runs only where `/root/reference` exists) and (b) with the
+golden vectors committed under `tests/golden/` that `tests/golden/gen_golden.py` produced by
+running the unmodified reference (numpy 2.3.5).  NormReward and Traffic-ARZ have no published
+golden in the reference -- their pins are reference *runs* only.
+
+Differences from the reference, all deliberate:
+  * a leading batch axis B (B independent envs in lockstep); with B=1 the per-substep numpy call
+    pattern (and therefore the CPU cost profile) is that of the reference;
+  * no `u[nt, nx]` trajectory buffer: the rewards that index into history
+    (`tuned_reward_1d.py:36-40`, `norm_reward.py:57-72`) get what they need from a 101-row ring and a
+    boundary-value history, which produces the same numbers;
+  * precision mode "fp64" keeps the state in float64 (the reference always stores float32 for
+    Transport / ReactionDiffusion: `hyperbolic.py:214-216`, `parabolic.py:208-210`).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+LOOKBACK = 100  # tuned_reward_1d.py:25,40 -> int(1/0.01); control_sample_rate is never passed
+
+
+# --------------------------------------------------------------------------------------------
+# rewards for the 1-D hyperbolic / parabolic envs
+# --------------------------------------------------------------------------------------------
+class TunedReward1DSpec:
+    """Parameters of `TunedReward1D` (tuned_reward_1d.py:17-23)."""
+
+    kind = "tuned"
+
+    def __init__(self, nt, truncate_penalty=-1e-4, terminate_reward=1e2):
+        if nt is None:
+            raise Exception("Number of simulation steps must be specified in the NormReward class.")
+        self.nt = nt
+        self.truncate_penalty = truncate_penalty
+        self.terminate_reward = terminate_reward
+
+
+class NormRewardSpec:
+    """Parameters of `NormReward` with the repaired semantics of SURVEY A.6 (norm_reward.py:19-73)."""
+
+    kind = "norm"
+
+    def __init__(self, nt=None, norm="2", horizon="temporal", truncate_penalty=-1e-4,
+                 terminate_reward=1e2, t_horizon_length=5, norm_coeff=1.0):
+        if nt is None:
+            raise Exception("Number of simulation steps must be specified in the NormReward class.")
+        self.nt = nt
+        self.ord = {"1": 1, "2": 2, "inf": np.inf, 1: 1, 2: 2, np.inf: np.inf}[norm]
+        self.horizon = horizon
+        self.truncate_penalty = truncate_penalty
+        self.terminate_reward = terminate_reward
+        self.t_horizon_length = t_horizon_length
+        self.norm_coeff = norm_coeff
+
+
+def _norm_rows(rows, ord=2):
+    # one np.linalg.norm call per env row: the same routine (and bits) as the reference's scalar env
+    return np.array([np.linalg.norm(r, ord) for r in rows])
+
+
+# --------------------------------------------------------------------------------------------
+# shared machinery of TransportPDE1D / ReactionDiffusionPDE1D
+# --------------------------------------------------------------------------------------------
+class _BoundaryControl1D:
+    """base_env_1d.py:20-45 + the ctor / step / terminate / truncate / reset skeleton shared by
+    hyperbolic.py:25-227 and parabolic.py:25-221."""
+
+    npts_extra = 0  # RD carries one ghost point (parabolic.py:124)
+
+    def __init__(self, B, T, dt, X, dx, reward, normalize=False, sensing_loc="full",
+                 control_type="Dirchilet", sensing_type="Dirchilet", limit_pde_state_size=False,
+                 max_state_value=1e10, max_control_value=20, control_sample_rate=0.1,
+                 precision="ref"):
+        self.B = B
+        self.T, self.dt, self.X, self.dx = T, dt, X, dx
+        self.nt = int(round(T / dt) + 1)           # base_env_1d.py:23
+        self.nx = int(round(X / dx))               # base_env_1d.py:24
+        self.npts = self.nx + self.npts_extra
+        self.reward = reward
+        self.normalize = bool(normalize)
+        if sensing_loc not in ("full", "collocated", "opposite"):
+            raise Exception("Invalid sensing_loc parameter. Please use 'full', 'collocated', or 'opposite'. See documentation for details.")
+        if control_type not in ("Neumann", "Dirchilet"):
+            raise Exception("Invalid control_type parameter. Please use 'Neumann' or 'Dirchilet'. See documentation for details.")
+        if sensing_loc == "opposite" and sensing_type not in ("Neumann", "Dirchilet"):
+            raise Exception("Invalid sensing_type parameter. Please use 'Neumann' or 'Dirchilet'. See documentation for details.")
+        self.sensing_loc, self.control_type, self.sensing_type = sensing_loc, control_type, sensing_type
+        self.limit_pde_state_size = limit_pde_state_size
+        self.max_state_value = max_state_value
+        self.max_control_value = max_control_value
+        self.control_sample_rate = control_sample_rate
+        self.substeps = int(round(control_sample_rate / dt))   # hyperbolic.py:137 / parabolic.py:137
+        assert precision in ("ref", "fp64")
+        self.sdtype = np.float32 if precision == "ref" else np.float64
+        if self.nt <= LOOKBACK:
+            raise ValueError("oracle assumes nt > 100 (TunedReward1D negative-index wrap lands on an unwritten row)")
+
+    # -- helpers -------------------------------------------------------------------------
+    def _normalize(self, a):
+        # base_env_1d.py:36-39: evaluated as written, in the dtype of `a`
+        if self.normalize:
+            return (a + 1) * self.max_control_value - self.max_control_value
+        return a
+
+    def _sense(self, row):
+        """hyperbolic.py:69-120 / parabolic.py:69-118 (noise function applied by the caller)."""
+        if self.sensing_loc == "full":
+            return row.copy()
+        if self.sensing_loc == "collocated":
+            if self.control_type == "Neumann":
+                return row[:, -1].copy()
+            return (row[:, -1] - row[:, -2]) / self.dx
+        if self.sensing_type == "Neumann":
+            return (row[:, 1] - row[:, 0]) / self.dx
+        return row[:, 0].copy()
+
+    def reset(self, init_condition, beta):
+        """hyperbolic.py:198-227 / parabolic.py:192-221.  `init_condition`: (npts,) or (B,npts);
+        `beta`: (npts,) or (B,npts); beta's dtype is kept (it selects the arithmetic)."""
+        B, P = self.B, self.npts
+        self.u = np.zeros((B, P), dtype=self.sdtype)
+        self.u[:] = np.broadcast_to(np.asarray(init_condition), (B, P))   # cast on assignment
+        beta = np.asarray(beta)
+        if self.sdtype == np.float64:
+            beta = beta.astype(np.float64)
+        self.beta = np.broadcast_to(beta, (B, P))
+        self.t = np.zeros(B, dtype=np.int64)
+        # replacements for the history buffer
+        self._ring = np.zeros((LOOKBACK + 1, B, P), dtype=self.sdtype)
+        self._ring_t = np.full((LOOKBACK + 1, B), -1, dtype=np.int64)
+        self._bhist = np.zeros((B, self.nt), dtype=self.sdtype)       # uVec[:, -1] column
+        self._push()
+        return self._sense(self.u)
+
+    def _push(self):
+        """Record the current row (ring of the last 101 rows + boundary-value column)."""
+        t0 = int(self.t[0])
+        if self.B == 1 or (self.t == t0).all():        # lockstep fast path
+            s = t0 % (LOOKBACK + 1)
+            self._ring[s] = self.u
+            self._ring_t[s] = t0
+            self._bhist[:, t0] = self.u[:, -1]
+            return
+        self._push_live(np.ones(self.B, dtype=bool))
+
+    def _row_at(self, b, t):
+        """uVec[t] for env b with the reference's negative-index wrap (tuned_reward_1d.py:40)."""
+        if t < 0:
+            return np.zeros(self.npts, dtype=self.sdtype)   # row nt+t: not yet written (nt > 100)
+        s = t % (LOOKBACK + 1)
+        assert self._ring_t[s, b] == t, "history ring does not hold the requested row"
+        return self._ring[s, b]
+
+    def terminate(self):
+        return self.t >= self.nt - 1                                   # hyperbolic.py:171-180
+
+    def truncate(self):
+        if not self.limit_pde_state_size:                             # hyperbolic.py:182-194
+            return np.zeros(self.B, dtype=bool)
+        return _norm_rows(self.u, 2) >= self.max_state_value
+
+    def _reward(self, term, trunc):
+        rw = self.reward
+        out = []
+        for b in range(self.B):
+            t = int(self.t[b])
+            row = self.u[b]
+            if rw.kind == "tuned":
+                # tuned_reward_1d.py:25-40 (order of the three branches matters)
+                if term[b] and np.linalg.norm(row) < 20:
+                    r = (rw.terminate_reward - np.sum(abs(self._bhist[b])) / 1000 - np.linalg.norm(row))
+                elif trunc[b]:
+                    r = rw.truncate_penalty * (rw.nt - t)
+                else:
+                    r = np.linalg.norm(self._row_at(b, t - LOOKBACK)) - np.linalg.norm(row)
+            else:
+                # norm_reward.py:29-73, repaired
+                if term[b]:
+                    r = rw.terminate_reward
+                elif trunc[b]:
+                    r = rw.truncate_penalty * (rw.nt - t)
+                elif rw.horizon == "temporal":
+                    r = -np.linalg.norm(row, ord=rw.ord) / rw.norm_coeff
+                elif rw.horizon == "differential":
+                    if t > 0:
+                        r = np.linalg.norm(row - self._row_at(b, t - 1), ord=rw.ord) / rw.norm_coeff
+                    else:
+                        r = -np.linalg.norm(row, ord=rw.ord) / rw.norm_coeff
+                elif rw.horizon == "t-horizon":
+                    m = rw.t_horizon_length if t > rw.t_horizon_length else t
+                    acc = 0
+                    for i in range(m):
+                        acc += np.linalg.norm(self._row_at(b, t - i), ord=rw.ord)   # `t-1 * i` == t - i
+                    acc /= m
+                    r = -acc / rw.norm_coeff
+                else:
+                    raise ValueError(rw.horizon)
+            out.append(r)
+        return np.array(out)
+
+    def step(self, action):
+        """One control step for all B envs.  `action`: array (B,) of dtype float32 or float64
+        (its dtype drives the actuation arithmetic exactly as a numpy action does in the reference)."""
+        a = np.asarray(action).reshape(self.B)
+        for _ in range(self.substeps):
+            live = self.t < self.nt - 1          # hyperbolic.py:140: per-env loop guard
+            if not live.any():
+                break
+            new = self._substep(a)
+            if live.all():
+                self.u = new
+                self.t = self.t + 1
+                self._push()
+            else:
+                self.u = np.where(live[:, None], new, self.u)
+                self.t = self.t + live
+                self._push_live(live)
+        term, trunc = self.terminate(), self.truncate()
+        return self._sense(self.u), self._reward(term, trunc), term, trunc
+
+    def _push_live(self, live):
+        for b in np.nonzero(live)[0]:
+            s = self.t[b] % (LOOKBACK + 1)
+            self._ring[s, b] = self.u[b]
+            self._ring_t[s, b] = self.t[b]
+            self._bhist[b, self.t[b]] = self.u[b, -1]
+
+
+class TransportOracle(_BoundaryControl1D):
+    """`TransportPDE1D` (hyperbolic.py:126-169): u_t = u_x + beta(x) u(0,t), first-order upwind."""
+
+    npts_extra = 0
+
+    def _substep(self, a):
+        p = self.u
+        n = np.zeros_like(p)                      # the freshly zeroed history row of the reference
+        # hyperbolic.py:143-145 -- Neumann reads n[nx-2] of the NEW row, still zero
+        if self.control_type == "Neumann":
+            g = a * self.dx + n[:, -2]
+        else:
+            g = a
+        n[:, -1] = self._normalize(g)
+        # hyperbolic.py:146-155
+        n[:, :-1] = p[:, :-1] + self.dt * ((p[:, 1:] - p[:, :-1]) / self.dx + (p[:, 0:1] * self.beta)[:, :-1])
+        return n
+
+
+class ReactionDiffusionOracle(_BoundaryControl1D):
+    """`ReactionDiffusionPDE1D` (parabolic.py:126-164): u_t = u_xx + lambda(x) u, explicit FTCS,
+    u(0,t)=0, ghost/actuated point at index nx."""
+
+    npts_extra = 1
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        if self.sensing_loc == "opposite" and self.sensing_type == "Dirchilet":
+            raise Exception("In the parabolic PDE system, u(0, t)=0 and so Dirchilet sensing at u(0, t) is not viable. See documentation for details.")
+        self.F = self.dt / (self.dx ** 2)          # parabolic.py:138
+
+    def _substep(self, a):
+        p = self.u
+        nx = self.nx
+        n = np.zeros_like(p)
+        # parabolic.py:143-144
+        n[:, 1:nx] = p[:, 1:nx] + self.F * (p[:, 0:nx - 1] - 2 * p[:, 1:nx] + p[:, 2:nx + 1]) \
+            + self.dt * self.beta[:, 1:nx] * p[:, 1:nx]
+        n[:, 0] = 0                                # parabolic.py:146
+        # parabolic.py:148-150 -- Neumann uses the PREVIOUS row's u[nx-1]
+        if self.control_type == "Neumann":
+            g = a * self.dx + p[:, -2]
+        else:
+            g = a
+        n[:, -1] = self._normalize(g)
+        return n
+
+
+# --------------------------------------------------------------------------------------------
+# Traffic ARZ (all float64)
+# --------------------------------------------------------------------------------------------
+class TrafficARZOracle:
+    """`TrafficPDE1D` (traffic_arz_env.py:23-280) + `TrafficARZReward` (traffic_arz_reward.py:12-22).
+
+    Aw-Rascle-Zhang 2x2 system in (rho, y) with the two-step Richtmyer / Lax-Wendroff scheme and a
+    relaxation source.  Time bookkeeping quirks are kept: `time_index` is a float
+    time advanced by dt per *step*, the integrator only runs while `time_index < T`, `terminate()`
+    compares it with T/dt and zeroes it.  `rs` may be a per-env array (the reference draws it with
+    Python's global `random` for the '*-train' types, traffic_arz_env.py:66-70,251-256)."""
+
+    def __init__(self, B, T, dt, X, dx, simulation_type="inlet", v_steady=10, ro_steady=0.12,
+                 v_max=40, ro_max=0.16, tau=60, limit_pde_state_size=False, control_freq=1):
+        assert isinstance(control_freq, int) and control_freq >= 1
+        if simulation_type not in ("inlet", "outlet", "both", "outlet-train"):
+            raise ValueError("Invalid simulation type")     # 'inlet-train' crashes in the reference
+        self.B = B
+        self.T, self.dt, self.X, self.dx = T, dt, X, dx
+        self.nt = int(round(T / dt) + 1)
+        self.nx = int(round(X / dx))
+        self.simulation_type = simulation_type
+        self.vm, self.rm, self.tau = v_max, ro_max, tau
+        self.limit_pde_state_size = limit_pde_state_size
+        self.control_freq = control_freq
+        if simulation_type != "outlet-train":
+            if v_steady != self.Veq(ro_steady):
+                raise ValueError("The steady state velocity and density do not satisfy the equilibrium condition.")
+            self.set_steady(np.full(B, float(ro_steady)), vs=np.full(B, float(v_steady)))
+        else:
+            self.set_steady(np.full(B, 0.12))
+        self.x = np.arange(0, X + dx, dx)            # traffic_arz_env.py:74
+        self.M = len(self.x)
+        self.L = X
+        self.time_index = np.zeros(B)
+        self.reset()
+
+    def Veq(self, rho):
+        return self.vm * (1 - rho / self.rm)          # traffic_arz_env.py:271-272
+
+    def F_r(self, rho, y):
+        return y + rho * self.Veq(rho)                # :275-276
+
+    def F_y(self, rho, y):
+        return y * (y / rho + self.Veq(rho))          # :279-280
+
+    def set_steady(self, rs, vs=None):
+        self.rs = np.asarray(rs, dtype=np.float64)
+        self.vs = self.Veq(self.rs) if vs is None else np.asarray(vs, dtype=np.float64)
+        if self.simulation_type == "outlet-train":
+            self.qs = self.rs * self.vs               # :70,256
+        else:
+            self.qs = self.vs * self.rs               # :63
+        self.act_low, self.act_high = self.qs * 0.8, 1.2 * self.qs   # :98-100
+
+    def reset(self, rs=None):
+        """traffic_arz_env.py:237-267 (does NOT reset time_index -- that is terminate()'s side effect)."""
+        if rs is not None:
+            self.set_steady(rs)
+        rs, qs = self.rs[:, None], self.qs[:, None]
+        self.r = rs * (np.sin(3 * self.x / self.L * np.pi) * 0.1 + np.ones(self.M))[None, :]
+        self.y = qs * np.ones((self.B, self.M)) - self.vm * self.r + self.vm / self.rm * (self.r) ** (2)
+        self.v = self.y / self.r + self.Veq(self.r)
+        return np.concatenate((self.r, self.v), axis=1)
+
+    def step(self, action):
+        """traffic_arz_env.py:131-233.  `action`: (B,1) or (B,2) float64."""
+        dt, dx, M = self.dt, self.dx, self.M
+        self.time_index = self.time_index + dt
+        a = np.asarray(action, dtype=np.float64).reshape(self.B, -1)
+        a = np.clip(a, self.act_low[:, None], self.act_high[:, None])
+        st = self.simulation_type
+        q_in = a[:, 0] if st in ("inlet", "both") else self.qs
+        q_out = a[:, 0] if st in ("outlet", "outlet-train") else (a[:, 1] if st == "both" else self.qs)
+        r, y = self.r.copy(), self.y.copy()
+        c1, c3 = dt / (2 * dx), dt / dx
+        count = 0
+        while count < self.control_freq:
+            live = self.time_index < self.T           # :173 (per env)
+            if not live.any():
+                break
+            rn, yn = r.copy(), y.copy()
+            rn[:, 0] = rn[:, 1]
+            yn[:, 0] = q_in - rn[:, 0] * self.Veq(rn[:, 0])
+            rn[:, M - 1] = rn[:, M - 2]
+            yn[:, M - 1] = q_out - rn[:, M - 1] * self.Veq(rn[:, M - 1])
+            r_jm1, r_j, r_jp1 = rn[:, 0:M - 2], rn[:, 1:M - 1], rn[:, 2:M]
+            y_jm1, y_j, y_jp1 = yn[:, 0:M - 2], yn[:, 1:M - 1], yn[:, 2:M]
+            r_pm = 0.5 * (r_jp1 + r_j) - c1 * (self.F_r(r_jp1, y_jp1) - self.F_r(r_j, y_j))
+            r_mm = 0.5 * (r_jm1 + r_j) - c1 * (self.F_r(r_j, y_j) - self.F_r(r_jm1, y_jm1))
+            y_pm = (0.5 * (y_jp1 + y_j) - c1 * (self.F_y(r_jp1, y_jp1) - self.F_y(r_j, y_j))
+                    - 0.25 * dt / self.tau * (y_jp1 + y_j))
+            y_mm = (0.5 * (y_jm1 + y_j) - c1 * (self.F_y(r_j, y_j) - self.F_y(r_jm1, y_jm1))
+                    - 0.25 * dt / self.tau * (y_jm1 + y_j))
+            r_new = r_j - c3 * (self.F_r(r_pm, y_pm) - self.F_r(r_mm, y_mm))
+            y_new = y_j - (c3 * (self.F_y(r_pm, y_pm) - self.F_y(r_mm, y_mm)) + 0.5 * dt / self.tau * (y_pm + y_mm))
+            rn[:, 1:M - 1] = r_new
+            yn[:, 1:M - 1] = y_new
+            r = np.where(live[:, None], rn, r)
+            y = np.where(live[:, None], yn, y)
+            count += 1
+        self.r, self.y = r, y
+        self.v = self.y / self.r + self.Veq(self.r)
+        rs, vs = self.rs, self.vs
+        reward = -(np.array([np.linalg.norm(self.v[b] - vs[b]) for b in range(self.B)]) / vs
+                   + np.array([np.linalg.norm(self.r[b] - rs[b]) for b in range(self.B)]) / rs)   # traffic_arz_reward.py:22
+        # terminate(): :103-113 (resets the float time as a side effect)
+        term = self.time_index >= self.T / self.dt
+        self.time_index = np.where(term, 0.0, self.time_index)
+        # truncate(): :116-127
+        trunc = np.zeros(self.B, dtype=bool)
+        if self.limit_pde_state_size:
+            trunc |= (self.v > self.vm).any(axis=1) | (self.r > self.rm).any(axis=1)
+        trunc |= ((self.r - rs[:, None]) == 0).all(axis=1) & ((self.v - vs[:, None]) == 0).all(axis=1)
+        if st == "outlet-train":
+            obs = np.concatenate(((self.r - rs[:, None]) / rs[:, None], (self.v - vs[:, None]) / vs[:, None]), axis=1)
+            return obs, reward, term, trunc
+        obs = np.concatenate((self.r, self.v), axis=1)
+        return obs, reward, term | (reward > -0.00023), trunc
+
+
+# --------------------------------------------------------------------------------------------
+# BrainTumor1D (all float64) + TherapyWrapper
+# --------------------------------------------------------------------------------------------
+GROWTH, THERAPY, POST = 0, 1, 2
+
+
+class BrainTumorOracle:
+    """`BrainTumor1D` (brain_tumor_env.py:33-384) + `BrainTumorReward` (brain_tumor_reward.py:31-73).
+
+    Per-env stage machine Growth -> Therapy -> Post-Therapy; one explicit diffusion-proliferation
+    (-radiation) step per call; T1/T2 radii = right-most index with c >= theta*k."""
+
+    def __init__(self, B, T, dt, X, dx, total_dosage, t1_detection_threshold=0.8,
+                 t2_detection_threshold=0.16, dosage_termination_threshold=0.1, D=0.2, rho=0.03,
+                 alpha=0.04, alpha_beta_ratio=10, k=1e5, t1_detection_radius=15, t1_death_radius=35):
+        self.B = B
+        self.T, self.dt, self.X, self.dx = T, dt, X, dx
+        self.nt = int(round(T / dt) + 1)
+        self.nx = int(round(X / dx) + 1)              # brain_tumor_env.py:52
+        self.xScale = np.linspace(0, X, self.nx)      # :57
+        self.th1, self.th2 = t1_detection_threshold, t2_detection_threshold
+        self.dose_stop = dosage_termination_threshold
+        bc = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), (B,)).copy()
+        self.D, self.rho = bc(D), bc(rho)             # per-env jitter allowed
+        self.alpha, self.abr, self.k = alpha, alpha_beta_ratio, k
+        self.r_detect, self.r_death = t1_detection_radius, t1_death_radius
+        self.total_dosage = float(total_dosage)
+        self.t_benchmark = None                       # None or (B,) ints
+
+    def reset(self, init_condition):
+        B = self.B
+        self.u = np.zeros((B, self.nx))
+        self.u[:] = np.broadcast_to(np.asarray(init_condition, dtype=np.float64), (B, self.nx))
+        self.t = np.zeros(B, dtype=np.int64)
+        self.stage = np.full(B, GROWTH)
+        self.remaining = np.full(B, self.total_dosage)
+        self.growthDays = np.zeros(B, dtype=np.int64)
+        self.therapyDays = np.zeros(B, dtype=np.int64)
+        self.postTherapyDays = np.zeros(B, dtype=np.int64)
+        self.simulationDays = np.zeros(B, dtype=np.int64)
+        self.firstTherapyDay = np.full(B, -1)
+        self.firstPostTherapyDay = np.full(B, -1)
+        self.cDeathDay = np.full(B, -1)
+        return self.u.copy()
+
+    def radius(self, c, theta):
+        """getTumorRadius (:104-121): right-most index with c >= theta*k, times dx; NaN if none."""
+        mask = c >= theta * self.k
+        out = np.full(c.shape[0], np.nan)
+        for b in range(c.shape[0]):
+            if mask[b].any():
+                out[b] = (mask[b].size - 1 - np.argmax(mask[b][::-1])) * self.dx
+        return out
+
+    def _fd(self, c, R=None):
+        """_update_fd (:221-245)."""
+        u_c, u_l, u_r = c[:, 1:-1], c[:, :-2], c[:, 2:]
+        diffusion = self.D[:, None] * ((u_r - 2.0 * u_c + u_l) / (self.dx ** 2))
+        proliferation = self.rho[:, None] * u_c * (1.0 - (u_c / self.k))
+        radiation = 0.0 if R is None else (R[:, 1:-1] * u_c * (1.0 - (u_c / self.k)))
+        n = np.empty_like(c)
+        n[:, 1:-1] = u_c + self.dt * (diffusion + proliferation - radiation)
+        n[:, 0] = n[:, 1]
+        n[:, -1] = n[:, -2]
+        return np.clip(n, 0, self.k)
+
+    def step(self, control):
+        """brain_tumor_env.py:123-218 for B envs.  Returns obs, reward, term, trunc, valid where
+        `valid[b]` is False when the reference would have returned None (t >= nt-1 at entry, :135)."""
+        B = self.B
+        ctl = np.asarray(control, dtype=np.float64).reshape(B)
+        valid = self.t < self.nt - 1
+        reward = np.zeros(B)
+        term = np.zeros(B, dtype=bool)
+        trunc = np.zeros(B, dtype=bool)
+        for b in np.nonzero(valid)[0]:
+            self.t[b] += 1
+            t = int(self.t[b])
+            cur = self.u[b:b + 1]
+            sl = slice(b, b + 1)
+            nxt = self._fd_b(cur, sl, None)
+            stage0 = self.stage[b]
+            if stage0 == GROWTH:
+                self.u[b] = nxt[0]
+                T1 = self.radius(self.u[sl], self.th1)[0]
+                self.growthDays[b] = t
+                if not np.isnan(T1) and T1 >= self.r_detect:
+                    self.firstTherapyDay[b] = t + 1
+                    self.stage[b] = THERAPY
+            elif stage0 == THERAPY:
+                c = float(ctl[b])
+                applied = min(c * self.total_dosage, self.remaining[b])
+                self.remaining[b] -= applied
+                # _compute_radiation_field (:247-265): previous day's T2 radius
+                T2 = self.radius(cur, self.th2)[0]
+                treatR = 0.0 if np.isnan(T2) else (T2 + 25)
+                d = np.zeros((1, self.nx))
+                d[0, self.xScale <= treatR] = applied
+                BED = d + ((d ** 2) / (self.abr))
+                R = 1.0 - np.exp(-self.alpha * BED)
+                nxt = self._fd_b(cur, sl, R)
+                self.u[b] = nxt[0]
+                if self.remaining[b] < self.dose_stop:
+                    self.therapyDays[b] = t - self.growthDays[b]
+                    self.firstPostTherapyDay[b] = t + 1
+                    self.stage[b] = POST
+                term[b] = self._terminate(b)
+                trunc[b] = self._truncate(b)
+                reward[b] = self._reward(b, term[b], trunc[b], treatR, applied)
+                continue
+            else:
+                self.u[b] = nxt[0]
+            term[b] = self._terminate(b)
+            trunc[b] = self._truncate(b)
+            if self.stage[b] == POST and (term[b] or trunc[b]):
+                reward[b] = self._reward(b, term[b], trunc[b], None, None)
+            else:
+                reward[b] = 0.0
+        return self.u.copy(), reward, term, trunc, valid
+
+    def _fd_b(self, cur, sl, R):
+        D, rho = self.D, self.rho
+        self.D, self.rho = D[sl], rho[sl]
+        try:
+            return self._fd(cur, R)
+        finally:
+            self.D, self.rho = D, rho
+
+    def _terminate(self, b):
+        """terminate() (:285-311)."""
+        t = int(self.t[b])
+        if t < self.nt - 1:
+            return False
+        self._book(b, t)
+        return True
+
+    def _book(self, b, t):
+        if self.stage[b] == THERAPY:
+            self.therapyDays[b] = t - self.growthDays[b]
+            self.simulationDays[b] = self.growthDays[b] + self.therapyDays[b]
+        elif self.stage[b] == POST:
+            self.postTherapyDays[b] = t - self.therapyDays[b] - self.growthDays[b]
+            self.simulationDays[b] = self.growthDays[b] + self.therapyDays[b] + self.postTherapyDays[b]
+
+    def _truncate(self, b):
+        """truncate() (:313-345)."""
+        T1 = self.radius(self.u[b:b + 1], self.th1)[0]
+        if np.isnan(T1) or not (T1 >= self.r_death):
+            return False
+        if self.cDeathDay[b] < 0:
+            self.cDeathDay[b] = self.t[b]
+            self._book(b, int(self.t[b]))
+        return True
+
+    def _reward(self, b, term, trunc, treatR, applied):
+        """BrainTumorReward.reward (brain_tumor_reward.py:46-73)."""
+        if self.t_benchmark is None:
+            return 0
+        if term or trunc:
+            return int(self.t[b]) - int(self.t_benchmark[b])
+        maxsafe = 116 * (np.float64(treatR) ** -0.685)
+        ratio = (applied - maxsafe) / (self.total_dosage - maxsafe)
+        r_toxic = (min(max(ratio, 0.0), 1.0)) ** (1 / 3)
+        return -50 * r_toxic
+
+
+class TherapyWrapperOracle:
+    """`TherapyWrapper` (brain_tumor_env.py:386-505) over a B=1 `BrainTumorOracle`."""
+
+    def __init__(self, env: BrainTumorOracle, init_condition, weekends=False):
+        assert env.B == 1
+        self.env, self.ic, self.weekends = env, init_condition, weekends
+        self.treatment_calls = 0
+        self.soft_constraint_violations = 0
+        self.consecutive_treatment_days = 0
+
+    def reset(self):
+        self.consecutive_treatment_days = 0
+        obs = self.env.reset(self.ic)
+        while self.env.stage[0] == GROWTH:
+            obs, _, term, trunc, _ = self.env.step(np.zeros(1))
+            if term[0] or trunc[0]:
+                break
+        return obs
+
+    def step(self, control):
+        env = self.env
+        if env.stage[0] == POST:
+            term = trunc = np.zeros(1, dtype=bool)
+            while not (term[0] or trunc[0]):
+                obs, reward, term, trunc, _ = env.step(np.zeros(1))
+            return obs, reward, term, trunc
+        obs, reward, term, trunc, _ = env.step(np.array([control], dtype=np.float64))
+        self.treatment_calls += 1
+        if reward[0] < 0.0:
+            self.soft_constraint_violations += 1
+        if self.weekends:
+            if control > 0:
+                self.consecutive_treatment_days += 1
+            else:
+                self.consecutive_treatment_days = 0
+        if self.weekends and self.consecutive_treatment_days >= 5:
+            self.consecutive_treatment_days = 0
+            for _ in range(2):
+                env.step(np.zeros(1))         # results discarded; stale flags tested (:470-473)
+                if term[0] or trunc[0]:
+                    return obs, reward, term, trunc
+        return obs, reward, term, trunc
+
+    def benchmark(self):
+        env = self.env
+        env.reset(self.ic)
+        term = trunc = np.zeros(1, dtype=bool)
+        while not (term[0] or trunc[0]):
+            _, _, term, trunc, _ = env.step(np.zeros(1))
+        tb = env.simulationDays.copy()
+        env.t_benchmark = tb
+        env.reset(self.ic)
+        return int(tb[0])
+
+
+# --------------------------------------------------------------------------------------------
+# NavierStokes2D (all float64)
+# --------------------------------------------------------------------------------------------
+def _cd_x(f, step):
+    """central_difference(f, "x") (navier_stokes2D.py:9-15); arrays are [B, row(y), col(x)]."""
+    d = np.zeros_like(f)
+    d[:, 1:-1, 1:-1] = (f[:, 1:-1, 2:] - f[:, 1:-1, 0:-2]) / (2 * step)
+    return d
+
+
+def _cd_y(f, step):
+    d = np.zeros_like(f)
+    d[:, 1:-1, 1:-1] = (f[:, 2:, 1:-1] - f[:, 0:-2, 1:-1]) / (2 * step)
+    return d
+
+
+def _lap(f, dx, dy):
+    """laplace (navier_stokes2D.py:17-22)."""
+    d = np.zeros_like(f)
+    d[:, 1:-1, 1:-1] = (f[:, 1:-1, 0:-2] + f[:, 0:-2, 1:-1] - 4 * f[:, 1:-1, 1:-1] + f[:, 1:-1, 2:] + f[:, 2:, 1:-1]) / (dx * dy)
+    return d
+
+
+class NavierStokesOracle:
+    """`NavierStokes2D` (navier_stokes2D.py:38-194) + `NSReward` (ns_reward.py:18-28): Chorin
+    projection, fixed-count Jacobi pressure solve warm-started from the previous pressure."""
+
+    SIDES = ("lower", "upper", "left", "right")
+
+    def __init__(self, B, T, dt, X, dx, Y, dy, boundary_condition, U_ref, action_ref, viscosity=0.1,
+                 density=1.0, maximum_pressure_iteration=2000, stable_factor=0.5, gamma=0.1):
+        self.B = B
+        self.nt = int(round(T / dt))                  # base_env_2d.py:27
+        self.nx = int(round(X / dx + 1))
+        self.ny = int(round(Y / dy + 1))
+        self.dx, self.dy, self.dt = dx, dy, dt
+        self.x = np.linspace(0, X, self.nx)
+        self.y = np.linspace(0, Y, self.ny)
+        self.X, self.Y = np.meshgrid(self.x, self.y)
+        self.nu, self.rho_f, self.n_iter = viscosity, density, int(maximum_pressure_iteration)
+        if dt > stable_factor * (0.5 * min(dx, dy) ** 2 / viscosity):
+            raise RuntimeError("Stability is not guarenteed")
+        self.bc = boundary_condition
+        self.U_ref = np.asarray(U_ref)
+        self.action_ref = np.asarray(action_ref)
+        self.gamma = gamma
+
+    def apply_boundary(self, u, v, a):
+        """navier_stokes2D.py:68-91; `a` is (B,) (one scalar action per env)."""
+        for pos in self.SIDES:
+            for i, f in enumerate((u, v)):
+                cond = self.bc[pos][i]
+                if pos == "lower":
+                    dst, src = (slice(None), 0, slice(None)), (slice(None), 1, slice(None))
+                elif pos == "upper":
+                    dst, src = (slice(None), -1, slice(None)), (slice(None), -2, slice(None))
+                elif pos == "left":
+                    dst, src = (slice(None), slice(None), 0), (slice(None), slice(None), 1)
+                else:
+                    dst, src = (slice(None), slice(None), -1), (slice(None), slice(None), -2)
+                if cond == "Neumann":
+                    f[dst] = f[src]
+                elif cond == "Dirchilet":
+                    f[dst] = 0
+                elif cond == "Controllable":
+                    f[dst] = a[:, None]
+        return u, v
+
+    def solve_pressure(self, u, v, p_prev):
+        """navier_stokes2D.py:94-116."""
+        dx, dy, dt = self.dx, self.dy, self.dt
+        rhs = self.rho_f / dt * (_cd_x(u, dx) + _cd_y(v, dy))
+        for _ in range(self.n_iter):
+            p_next = p_prev.copy()
+            p_next[:, 1:-1, 1:-1] = 1 / 4 * (p_prev[:, 1:-1, 0:-2] + p_prev[:, 0:-2, 1:-1] + p_prev[:, 1:-1, 2:] + p_prev[:, 2:, 1:-1]
+                                             - dx * dy * rhs[:, 1:-1, 1:-1])
+            p_next[:, :, -1] = p_next[:, :, -2]
+            p_next[:, 0, :] = p_next[:, 1, :]
+            p_next[:, :, 0] = p_next[:, :, 1]
+            p_next[:, -1, :] = p_next[:, -2, :]
+            p_prev = p_next
+        return p_prev
+
+    def reset(self, u, v, p):
+        B = self.B
+        shp = (B, self.ny, self.nx)
+        self.u = np.broadcast_to(np.asarray(u, dtype=np.float64), shp).copy()
+        self.v = np.broadcast_to(np.asarray(v, dtype=np.float64), shp).copy()
+        self.p = np.broadcast_to(np.asarray(p, dtype=np.float64), shp).copy()
+        self.t = 0
+        return np.stack((self.u, self.v), axis=-1)
+
+    def step(self, action):
+        """navier_stokes2D.py:118-157."""
+        a = np.asarray(action, dtype=np.float64).reshape(self.B)
+        dx, dy, dt = self.dx, self.dy, self.dt
+        u0, v0 = self.u, self.v
+        u_pred = u0 + dt * (-u0 * _cd_x(u0, dx) - v0 * _cd_y(u0, dy) + self.nu * _lap(u0, dx, dy))
+        v_pred = v0 + dt * (-u0 * _cd_x(v0, dx) - v0 * _cd_y(v0, dy) + self.nu * _lap(v0, dx, dy))
+        u_pred, v_pred = self.apply_boundary(u_pred, v_pred, a)
+        p = self.solve_pressure(u_pred, v_pred, self.p)
+        self.p = p
+        u_next = u_pred - dt / self.rho_f * _cd_x(p, dx)
+        v_next = v_pred - dt / self.rho_f * _cd_y(p, dy)
+        u_next, v_next = self.apply_boundary(u_next, v_next, a)
+        self.t += 1
+        self.u, self.v = u_next, v_next
+        U = np.stack((u_next, v_next), axis=-1)
+        term = np.full(self.B, self.t >= self.nt - 1)
+        # ns_reward.py:28 -- np.linalg.norm of the (ny,nx,2) difference = Frobenius over all entries
+        rew = np.array([
+            -1 / 2 * np.linalg.norm(U[b] - self.U_ref[self.t]) ** 2 / U.shape[1] / U.shape[2]
+            - self.gamma / 2 * np.linalg.norm(a[b] - self.action_ref[self.t]) ** 2
+            for b in range(self.B)])
+        return U, rew, term, np.zeros(self.B, dtype=bool)
