@@ -1,0 +1,154 @@
+/*
+ * pdecg.h -- C ABI of libpdecg.so: B200-native (sm_100a) batched PDE-control environment dynamics.
+ *
+ * This is the drop-in boundary for the hot path of lukebhan/PDEControlGym (per-step PDE
+ * integration + boundary actuation + observation sensing + reward / termination evaluation of
+ * N independent, lock-stepped environment instances).  The reference has no FFI layer of its
+ * own -- the path sits behind the gymnasium `Env.reset/step` contract and the `BaseReward.reward`
+ * protocol (reference: pde_control_gym/src/environments1d/base_env_1d.py:20-68,
+ * environments2d/base_env_2d.py:24-63, rewards/base_reward.py:14) -- so each entry point below
+ * cites the reference method(s) whose work it performs for a whole batch of environments.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, PODs.  No C++ / torch types cross this boundary.
+ *   - every `void*` buffer is DEVICE memory owned by the caller (e.g. a torch tensor's
+ *     data_ptr()); the library allocates nothing that outlives a call.  The `*_host` entry points
+ *     are the exception: they take HOST buffers and do the H2D/D2H copies themselves.
+ *   - all work is enqueued on the caller's stream (`pdecg_stream_t` == cudaStream_t) and returns
+ *     asynchronously, except the `*_host` variants which synchronise that stream before returning.
+ *   - return value: 0 on success, a negative pdecg_status otherwise; `pdecg_last_error()` gives a
+ *     thread-local message.  No exceptions, no aborts, no CPU fallback: without a CUDA device every
+ *     compute entry point returns PDECG_ERR_CUDA.
+ *   - layouts are env-major and dense: state `[n_envs, npts]`, one row per environment.
+ */
+#ifndef PDECG_H
+#define PDECG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDECG_ABI_VERSION 1
+
+typedef void* pdecg_stream_t; /* cudaStream_t */
+
+typedef enum {
+    PDECG_OK = 0,
+    PDECG_ERR_INVALID = -1,     /* bad argument / inconsistent configuration            */
+    PDECG_ERR_UNSUPPORTED = -2, /* valid in the reference but not implemented by a kernel */
+    PDECG_ERR_CUDA = -3         /* CUDA runtime error (message has the cudaError string) */
+} pdecg_status;
+
+/* Precision modes.
+ *   REF : what the reference stores/computes -- float32 state for Transport / ReactionDiffusion with
+ *         float32 or float64 intermediates depending on beta's dtype (hyperbolic.py:146-155,214-216),
+ *         float64 for Traffic-ARZ / BrainTumor / NavierStokes.  No FMA contraction, IEEE division:
+ *         states are bit-identical to numpy.
+ *   FP64: float64 state and arithmetic everywhere, same operation order, no FMA.
+ *   FP32: float32 state, FMA contraction allowed (fast, tolerance documented in DESIGN.md).      */
+typedef enum { PDECG_PREC_REF = 0, PDECG_PREC_FP64 = 1, PDECG_PREC_FP32 = 2 } pdecg_precision;
+typedef enum { PDECG_F32 = 0, PDECG_F64 = 1 } pdecg_dtype;
+
+/* ------------------------------------------------------------------------------------------
+ * Family 1: boundary-controlled 1-D envs -- TransportPDE1D and ReactionDiffusionPDE1D
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { PDECG_ENV_TRANSPORT = 0, PDECG_ENV_REACTION_DIFFUSION = 1 } pdecg_bc1d_env;
+typedef enum { PDECG_CONTROL_DIRICHLET = 0, PDECG_CONTROL_NEUMANN = 1 } pdecg_control_type;
+typedef enum { PDECG_SENSE_FULL = 0, PDECG_SENSE_COLLOCATED = 1, PDECG_SENSE_OPPOSITE = 2 } pdecg_sensing_loc;
+typedef enum { PDECG_SENSETYPE_DIRICHLET = 0, PDECG_SENSETYPE_NEUMANN = 1 } pdecg_sensing_type;
+typedef enum { PDECG_REWARD_TUNED1D = 0, PDECG_REWARD_NORM = 1 } pdecg_bc1d_reward;
+typedef enum { PDECG_NORM_L1 = 1, PDECG_NORM_L2 = 2, PDECG_NORM_LINF = 3 } pdecg_norm_ord;
+typedef enum { PDECG_HORIZON_TEMPORAL = 0, PDECG_HORIZON_DIFFERENTIAL = 1, PDECG_HORIZON_T = 2 } pdecg_horizon;
+
+/* Everything the reference keeps as constructor kwargs (hyperbolic.py:25-35, parabolic.py:25-35,
+ * base_env_1d.py:20) plus the reward descriptor (tuned_reward_1d.py:17, norm_reward.py:19). */
+typedef struct {
+    int32_t abi_version;          /* PDECG_ABI_VERSION                                            */
+    int32_t env;                  /* pdecg_bc1d_env                                               */
+    int32_t precision;            /* pdecg_precision                                              */
+    int32_t beta_dtype;           /* pdecg_dtype of `beta`; REF mode only (selects the arithmetic) */
+    int32_t action_dtype;         /* pdecg_dtype of `action` (actuation is evaluated in this type) */
+    int32_t nx;                   /* int(round(X/dx))            base_env_1d.py:24                 */
+    int32_t nt;                   /* int(round(T/dt)+1)          base_env_1d.py:23                 */
+    int32_t substeps;             /* int(round(control_sample_rate/dt))  hyperbolic.py:137          */
+    double dt, dx;
+    int32_t control_type;         /* pdecg_control_type  ("Dirchilet"/"Neumann")                   */
+    int32_t sensing_loc;          /* pdecg_sensing_loc                                            */
+    int32_t sensing_type;         /* pdecg_sensing_type (only for OPPOSITE)                        */
+    int32_t normalize;            /* base_env_1d.py:36-39                                          */
+    double max_control_value;
+    int32_t limit_pde_state_size; /* hyperbolic.py:182-194                                         */
+    int32_t reward_kind;          /* pdecg_bc1d_reward                                            */
+    double max_state_value;
+    int32_t reward_nt;            /* the reward object's own `nt` ctor argument                    */
+    int32_t norm_ord;             /* pdecg_norm_ord      (NormReward)                              */
+    int32_t horizon;              /* pdecg_horizon       (NormReward)                              */
+    int32_t t_horizon_length;     /* NormReward                                                   */
+    double truncate_penalty, terminate_reward, norm_coeff;
+} pdecg_bc1d_cfg;
+
+/* Device buffers of one batch.  npts = nx (Transport) or nx+1 (ReactionDiffusion, ghost point).
+ * State element type S: float for PREC_REF / PREC_FP32, double for PREC_FP64. */
+typedef struct {
+    int64_t n_envs;
+    void* u;                 /* [n_envs, npts] S   -- state; with FULL sensing this IS the observation    */
+    const void* beta;        /* [n_envs or 1, npts] -- beta(x) / lambda(x); dtype cfg.beta_dtype (REF) or S */
+    int64_t beta_env_stride; /* elements between envs' beta rows; 0 = one row shared by all envs          */
+    const void* action;      /* [n_envs] cfg.action_dtype                                               */
+    void* obs;               /* [n_envs] S -- scalar observation (COLLOCATED / OPPOSITE); unused for FULL */
+    double* reward;          /* [n_envs]                                                                */
+    uint8_t* terminated;     /* [n_envs]                                                                */
+    uint8_t* truncated;      /* [n_envs]                                                                */
+    int32_t* time_index;     /* [n_envs] -- substeps done this episode (the reference's self.time_index) */
+    double* carry;           /* [n_envs, pdecg_bc1d_carry_len(cfg)] -- O(1) replacement of the u[nt,nx]
+                                history the reference rewards index into                    */
+} pdecg_bc1d_buffers;
+
+/* Number of doubles of reward carry per env for this configuration. */
+int32_t pdecg_bc1d_carry_len(const pdecg_bc1d_cfg* cfg);
+/* Number of state points per env (nx or nx+1). */
+int32_t pdecg_bc1d_npts(const pdecg_bc1d_cfg* cfg);
+
+/* Replaces TransportPDE1D.reset / ReactionDiffusionPDE1D.reset (hyperbolic.py:198-227,
+ * parabolic.py:192-221) for every env whose mask byte is non-zero (mask == NULL: all envs).
+ * `init` is [n_envs or 1, npts] of dtype `init_dtype` (cast to S on store, like `u[0] = init`). */
+int pdecg_bc1d_reset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* init,
+                     int32_t init_dtype, int64_t init_env_stride, const uint8_t* mask,
+                     pdecg_stream_t stream);
+
+/* Replaces TransportPDE1D.step / ReactionDiffusionPDE1D.step incl. terminate(), truncate(), the
+ * sensing closure and reward_class.reward(...) (hyperbolic.py:126-194, parabolic.py:126-189,
+ * tuned_reward_1d.py:25-40, norm_reward.py:29-73) for all n_envs in one launch. */
+int pdecg_bc1d_step(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, pdecg_stream_t stream);
+
+/* Same step, but `action_host` ([n_envs], cfg.action_dtype) and the outputs are HOST buffers:
+ * H2D(actions) -> kernel -> D2H(obs, reward, flags), all on `stream`, then stream-synchronised.
+ * obs_host is [n_envs, npts] S for FULL sensing, [n_envs] S otherwise; any output pointer may be
+ * NULL to skip that copy.  Device buffers in `buf` are still the caller's (buf->action is the
+ * device staging buffer for the actions). */
+int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
+                         const void* action_host, void* obs_host, double* reward_host,
+                         uint8_t* terminated_host, uint8_t* truncated_host, pdecg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Misc
+ * ------------------------------------------------------------------------------------------ */
+const char* pdecg_last_error(void);
+int32_t pdecg_abi_version(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+int64_t pdecg_launch_count(void);
+
+/* Peak-probe kernels for the roofline denominators that MEASURED_PEAKS.json does not carry
+ * (non-FMA FP64 / FP32 issue rate).  `iters` dependent-chain iterations per thread over `n_chains`
+ * independent chains; returns elapsed milliseconds in *ms (measured with CUDA events on `stream`) and
+ * the number of floating-point instructions executed per thread in *ops_per_thread. */
+int pdecg_probe_fp_issue(int32_t dtype, int32_t blocks, int32_t threads, int32_t iters, float* ms,
+                         double* total_ops, pdecg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDECG_H */

@@ -24,6 +24,7 @@ Differences from the reference, all deliberate:
 """
 from __future__ import annotations
 
+import collections
 import math
 
 import numpy as np
@@ -128,7 +129,8 @@ class _BoundaryControl1D:
 
     def reset(self, init_condition, beta):
         """hyperbolic.py:198-227 / parabolic.py:192-221.  `init_condition`: (npts,) or (B,npts);
-        `beta`: (npts,) or (B,npts); beta's dtype is kept (it selects the arithmetic)."""
+        `beta`: (npts,) or (B,npts); beta's dtype is kept (it selects the arithmetic).
+        All B envs of one oracle instance share the time index (lockstep)."""
         B, P = self.B, self.npts
         self.u = np.zeros((B, P), dtype=self.sdtype)
         self.u[:] = np.broadcast_to(np.asarray(init_condition), (B, P))   # cast on assignment
@@ -136,35 +138,28 @@ class _BoundaryControl1D:
         if self.sdtype == np.float64:
             beta = beta.astype(np.float64)
         self.beta = np.broadcast_to(beta, (B, P))
-        self.t = np.zeros(B, dtype=np.int64)
-        # replacements for the history buffer
-        self._ring = np.zeros((LOOKBACK + 1, B, P), dtype=self.sdtype)
-        self._ring_t = np.full((LOOKBACK + 1, B), -1, dtype=np.int64)
-        self._bhist = np.zeros((B, self.nt), dtype=self.sdtype)       # uVec[:, -1] column
-        self._push()
+        self.t = 0
+        # replacements for the u[nt, nx] history buffer: references to the last 101 rows (no copies)
+        # and, only for TunedReward1D, the boundary-value column uVec[:, -1]
+        self._rows = collections.deque(maxlen=LOOKBACK + 1)
+        self._rows.append((0, self.u))
+        self._need_bhist = self.reward.kind == "tuned"
+        if self._need_bhist:
+            self._bhist = np.zeros((B, self.nt), dtype=self.sdtype)
+            self._bhist[:, 0] = self.u[:, -1]
         return self._sense(self.u)
-
-    def _push(self):
-        """Record the current row (ring of the last 101 rows + boundary-value column)."""
-        t0 = int(self.t[0])
-        if self.B == 1 or (self.t == t0).all():        # lockstep fast path
-            s = t0 % (LOOKBACK + 1)
-            self._ring[s] = self.u
-            self._ring_t[s] = t0
-            self._bhist[:, t0] = self.u[:, -1]
-            return
-        self._push_live(np.ones(self.B, dtype=bool))
 
     def _row_at(self, b, t):
         """uVec[t] for env b with the reference's negative-index wrap (tuned_reward_1d.py:40)."""
         if t < 0:
             return np.zeros(self.npts, dtype=self.sdtype)   # row nt+t: not yet written (nt > 100)
-        s = t % (LOOKBACK + 1)
-        assert self._ring_t[s, b] == t, "history ring does not hold the requested row"
-        return self._ring[s, b]
+        t_new = self._rows[-1][0]
+        tt, rows = self._rows[len(self._rows) - 1 - (t_new - t)]
+        assert tt == t, "history ring does not hold the requested row"
+        return rows[b]
 
     def terminate(self):
-        return self.t >= self.nt - 1                                   # hyperbolic.py:171-180
+        return np.full(self.B, self.t >= self.nt - 1)                  # hyperbolic.py:171-180
 
     def truncate(self):
         if not self.limit_pde_state_size:                             # hyperbolic.py:182-194
@@ -173,9 +168,9 @@ class _BoundaryControl1D:
 
     def _reward(self, term, trunc):
         rw = self.reward
+        t = self.t
         out = []
         for b in range(self.B):
-            t = int(self.t[b])
             row = self.u[b]
             if rw.kind == "tuned":
                 # tuned_reward_1d.py:25-40 (order of the three branches matters)
@@ -214,28 +209,16 @@ class _BoundaryControl1D:
         """One control step for all B envs.  `action`: array (B,) of dtype float32 or float64
         (its dtype drives the actuation arithmetic exactly as a numpy action does in the reference)."""
         a = np.asarray(action).reshape(self.B)
-        for _ in range(self.substeps):
-            live = self.t < self.nt - 1          # hyperbolic.py:140: per-env loop guard
-            if not live.any():
-                break
-            new = self._substep(a)
-            if live.all():
-                self.u = new
-                self.t = self.t + 1
-                self._push()
-            else:
-                self.u = np.where(live[:, None], new, self.u)
-                self.t = self.t + live
-                self._push_live(live)
+        i = 0
+        while i < self.substeps and self.t < self.nt - 1:      # hyperbolic.py:140
+            self.u = self._substep(a)
+            self.t += 1
+            self._rows.append((self.t, self.u))
+            if self._need_bhist:
+                self._bhist[:, self.t] = self.u[:, -1]
+            i += 1
         term, trunc = self.terminate(), self.truncate()
         return self._sense(self.u), self._reward(term, trunc), term, trunc
-
-    def _push_live(self, live):
-        for b in np.nonzero(live)[0]:
-            s = self.t[b] % (LOOKBACK + 1)
-            self._ring[s, b] = self.u[b]
-            self._ring_t[s, b] = self.t[b]
-            self._bhist[b, self.t[b]] = self.u[b, -1]
 
 
 class TransportOracle(_BoundaryControl1D):

@@ -1,0 +1,94 @@
+"""ctypes binding of libpdecg.so (the C ABI declared in include/pdecg.h).
+
+There is deliberately no fallback: if the shared library is missing or was not built for this
+machine, importing an env raises.  Build it with `python -c "import __graft_entry__ as g; g.build()"`
+or `make -C pdecontrolgym_b200/csrc`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpdecg.so")
+
+ABI_VERSION = 1
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
+PREC = {"ref": 0, "fp64": 1, "fp32": 2}
+F32, F64 = 0, 1
+
+
+class PdecgError(RuntimeError):
+    """A libpdecg entry point returned a negative status."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"libpdecg error {code}: {msg}")
+        self.code = code
+
+
+class Bc1dCfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("env", C.c_int32), ("precision", C.c_int32),
+        ("beta_dtype", C.c_int32), ("action_dtype", C.c_int32), ("nx", C.c_int32),
+        ("nt", C.c_int32), ("substeps", C.c_int32), ("dt", C.c_double), ("dx", C.c_double),
+        ("control_type", C.c_int32), ("sensing_loc", C.c_int32), ("sensing_type", C.c_int32),
+        ("normalize", C.c_int32), ("max_control_value", C.c_double),
+        ("limit_pde_state_size", C.c_int32), ("reward_kind", C.c_int32),
+        ("max_state_value", C.c_double), ("reward_nt", C.c_int32), ("norm_ord", C.c_int32),
+        ("horizon", C.c_int32), ("t_horizon_length", C.c_int32),
+        ("truncate_penalty", C.c_double), ("terminate_reward", C.c_double), ("norm_coeff", C.c_double),
+    ]
+
+
+class Bc1dBuffers(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("u", C.c_void_p), ("beta", C.c_void_p), ("beta_env_stride", C.c_int64),
+        ("action", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
+        ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("time_index", C.c_void_p),
+        ("carry", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle of libpdecg.so; raise loudly if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built. "
+            "Run `make -C pdecontrolgym_b200/csrc` (needs nvcc; no GPU required). "
+            "pdecontrolgym_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.pdecg_last_error.restype = C.c_char_p
+    L.pdecg_abi_version.restype = C.c_int32
+    L.pdecg_launch_count.restype = C.c_int64
+    L.pdecg_bc1d_npts.argtypes = [C.POINTER(Bc1dCfg)]
+    L.pdecg_bc1d_npts.restype = C.c_int32
+    L.pdecg_bc1d_carry_len.argtypes = [C.POINTER(Bc1dCfg)]
+    L.pdecg_bc1d_carry_len.restype = C.c_int32
+    L.pdecg_bc1d_step.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.c_void_p]
+    L.pdecg_bc1d_step.restype = C.c_int
+    L.pdecg_bc1d_reset.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.c_void_p, C.c_int32,
+                                   C.c_int64, C.c_void_p, C.c_void_p]
+    L.pdecg_bc1d_reset.restype = C.c_int
+    L.pdecg_bc1d_step_host.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdecg_bc1d_step_host.restype = C.c_int
+    L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_double), C.c_void_p]
+    L.pdecg_probe_fp_issue.restype = C.c_int
+    if L.pdecg_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libpdecg ABI {L.pdecg_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        raise PdecgError(rc, lib().pdecg_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().pdecg_launch_count())

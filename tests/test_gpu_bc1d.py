@@ -1,0 +1,153 @@
+"""CUDA parity: TransportPDE1D / ReactionDiffusionPDE1D kernels vs the numpy oracle, through the
+public vector-env API (which calls the C ABI).  States / observations must be BIT-IDENTICAL in the
+`ref` and `fp64` modes; rewards (norm reductions) within a stated tolerance."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+from tests.helpers import (TOL_F32_REDUCTION, TOL_F64_REDUCTION, assert_rewards_close, bc1d_case,
+                           make_ics, reward_pair)
+
+pytestmark = pytest.mark.gpu
+
+
+def run_pair(cuda_device, env, precision, control_type, sensing, normalize, beta_dtype, act_dtype,
+             reward_kind, nx=None, B=5, steps=12, limit=False, seed=0):
+    import torch
+    import pdecontrolgym_b200 as pcg
+    kw, npts, beta, nt = bc1d_case(env, nx, steps)
+    sensing_loc, sensing_type = sensing
+    nt_r = nt - 1
+    ospec, prew = reward_pair(reward_kind, nt_r)
+    common = dict(normalize=normalize, sensing_loc=sensing_loc, control_type=control_type,
+                  sensing_type=sensing_type, limit_pde_state_size=limit, max_state_value=30.0,
+                  max_control_value=20, **kw)
+    rng = np.random.default_rng(seed)
+    ics = make_ics(rng, B, npts)
+    beta = beta.astype(beta_dtype)
+    Orc = O.ReactionDiffusionOracle if env == "rd" else O.TransportOracle
+    oracle_prec = "fp64" if precision == "fp64" else "ref"
+    oenv = Orc(B, reward=ospec, precision=oracle_prec, **common)
+    o_ref = oenv.reset(ics, beta)
+    eid = "PDEControlGym-ReactionDiffusionPDE1D" if env == "rd" else "PDEControlGym-TransportPDE1D"
+    genv = pcg.make(eid, num_envs=B, device=cuda_device, precision=precision, reward_class=prew,
+                    sensing_noise_func=None, reset_init_condition_func=None,
+                    reset_recirculation_func=None, **common)
+    o_gpu, _ = genv.reset(options={"init_condition": ics, "beta": beta})
+    assert np.array_equal(o_gpu.cpu().numpy(), o_ref), "reset observation"
+    tol = TOL_F64_REDUCTION if precision == "fp64" else TOL_F32_REDUCTION
+    for k in range(steps + 1):          # one extra call on finished envs
+        a = (rng.uniform(-1, 1, B) if normalize else rng.uniform(-3, 3, B)).astype(act_dtype)
+        o_ref, r_ref, te_ref, tr_ref = oenv.step(a)
+        o_gpu, r_gpu, te_gpu, tr_gpu, _ = genv.step(torch.from_numpy(a))
+        og = o_gpu.cpu().numpy()
+        assert og.dtype == o_ref.dtype
+        if precision == "fp32":
+            np.testing.assert_allclose(og, o_ref, rtol=2e-3, atol=2e-3)
+        else:
+            assert np.array_equal(og, o_ref, equal_nan=True), f"step {k}: state/obs not bit-identical (max |d|={np.nanmax(np.abs(og - o_ref))})"
+            assert np.array_equal(te_gpu.cpu().numpy(), te_ref) and np.array_equal(tr_gpu.cpu().numpy(), tr_ref), f"step {k}: flags"
+        if k < steps:
+            scale = 2 * np.sqrt((oenv.u.astype(np.float64) ** 2).sum(axis=1)) + np.abs(r_ref)
+            if precision == "fp32":
+                assert_rewards_close(r_gpu.cpu().numpy(), r_ref, scale + 1.0, 5e-3, f"step {k}")
+            else:
+                assert_rewards_close(r_gpu.cpu().numpy(), r_ref, scale, tol, f"step {k}")
+    assert te_ref.all()
+
+
+SENSINGS = [("full", None), ("collocated", None), ("opposite", "Neumann"), ("opposite", "Dirchilet")]
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("precision,beta_dtype", [("ref", np.float32), ("ref", np.float64), ("fp64", np.float64)])
+def test_default_grid_all_variants(cuda_device, env, precision, beta_dtype):
+    for control_type, sensing, normalize, act_dtype, rk in itertools.product(
+            ("Dirchilet", "Neumann"), SENSINGS, (False, True), (np.float32, np.float64),
+            ("tuned", ("temporal", 2))):
+        if env == "rd" and sensing == ("opposite", "Dirchilet"):
+            continue
+        if env == "rd" and control_type == "Neumann" and normalize:
+            steps = 3   # reference quirk Q4: blows up to inf/nan within a few steps; still compared
+        else:
+            steps = 12
+        run_pair(cuda_device, env, precision, control_type, sensing, normalize, beta_dtype, act_dtype, rk,
+                 steps=steps)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("rk", ["tuned", ("temporal", 1), ("temporal", np.inf), ("differential", 2),
+                                ("differential", 1), ("t-horizon", 2)])
+def test_reward_kinds(cuda_device, env, rk):
+    for precision, bd in (("ref", np.float32), ("fp64", np.float64)):
+        run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), True, bd, np.float32, rk)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("nx", [8, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 160, 191, 192, 200, 223, 224, 255])
+def test_grid_sizes(cuda_device, env, nx):
+    """Every points-per-lane instantiation (K = 1..8), incl. sizes that are not multiples of 32."""
+    if env == "rd" and nx + 1 > 256:
+        pytest.skip("exceeds register-resident limit")
+    for precision, bd in (("ref", np.float32), ("ref", np.float64), ("fp64", np.float64)):
+        run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), False, bd, np.float32, "tuned",
+                 nx=nx, B=3, steps=4)
+        run_pair(cuda_device, env, precision, "Neumann", ("collocated", None), False, bd, np.float64, ("temporal", 2),
+                 nx=nx, B=3, steps=4)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+def test_truncation(cuda_device, env):
+    run_pair(cuda_device, env, "ref", "Dirchilet", ("full", None), False, np.float32, np.float32, "tuned", limit=True)
+    run_pair(cuda_device, env, "fp64", "Dirchilet", ("full", None), False, np.float64, np.float32, ("temporal", 2), limit=True)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+def test_fp32_fast_mode(cuda_device, env):
+    run_pair(cuda_device, env, "fp32", "Dirchilet", ("full", None), True, np.float32, np.float32, "tuned", steps=6)
+
+
+def test_batch_sizes_and_independence(cuda_device):
+    """Ragged batch sizes (not multiples of the 4-env CTA) and batch-composition invariance."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    kw, npts, beta, nt = bc1d_case("rd", None, 3)
+    rng = np.random.default_rng(3)
+    ics = make_ics(rng, 37, npts)
+    acts = rng.uniform(-1, 1, (3, 37)).astype(np.float32)
+    outs = {}
+    for B in (1, 2, 3, 5, 37):
+        env = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=B, device=cuda_device, precision="fp64",
+                       reward_class=pcg.NormReward(nt - 1), normalize=True, **kw)
+        env.reset(options={"init_condition": ics[:B], "beta": beta})
+        for k in range(3):
+            o, r, te, tr, _ = env.step(torch.from_numpy(acts[k, :B]))
+        outs[B] = (o.cpu().numpy(), r.cpu().numpy())
+    for B in (1, 2, 3, 5):
+        assert np.array_equal(outs[B][0], outs[37][0][:B])
+        assert np.array_equal(outs[B][1], outs[37][1][:B])
+
+
+def test_empty_batch_and_errors(cuda_device):
+    import pdecontrolgym_b200 as pcg
+    from pdecontrolgym_b200._lib import PdecgError
+    kw, npts, beta, nt = bc1d_case("tr", None, 3)
+    env = pcg.make("PDEControlGym-TransportPDE1D", num_envs=0, device=cuda_device,
+                   reward_class=pcg.TunedReward1D(nt - 1), **kw)
+    o, _ = env.reset(options={"init_condition": np.zeros(npts), "beta": beta})
+    o, r, te, tr, _ = env.step(np.zeros(0, dtype=np.float32))
+    assert o.shape == (0, npts) and r.shape == (0,)
+    with pytest.raises(Exception, match="Invalid sensing_loc"):
+        pcg.make("PDEControlGym-TransportPDE1D", num_envs=1, device=cuda_device, sensing_loc="middle",
+                 reward_class=pcg.TunedReward1D(nt - 1), **kw)
+    with pytest.raises(Exception, match="not viable"):
+        pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=1, device=cuda_device, sensing_loc="opposite",
+                 sensing_type="Dirchilet", reward_class=pcg.TunedReward1D(nt - 1), **kw)
+    kw2 = dict(kw)
+    kw2["dx"] = 1.0 / 400
+    big = pcg.make("PDEControlGym-TransportPDE1D", num_envs=1, device=cuda_device,
+                   reward_class=pcg.NormReward(nt - 1), **kw2)
+    with pytest.raises(PdecgError, match="register-resident"):
+        big.reset(options={"init_condition": np.zeros(400), "beta": np.zeros(400)})
