@@ -134,6 +134,69 @@ int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* bu
                          uint8_t* terminated_host, uint8_t* truncated_host, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Family 2: BrainTumor1D (+ TherapyWrapper semantics)           -- all float64
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { PDECG_BT_GROWTH = 0, PDECG_BT_THERAPY = 1, PDECG_BT_POST = 2 } pdecg_bt_stage;
+
+/* What one launch does per env (brain_tumor_env.py):
+ *   RAW_STEP      BrainTumor1D.step(action)                      (:123-218)  -- one day
+ *   WRAP_RESET    TherapyWrapper.reset() after the env reset: run the whole Growth stage  (:408-427)
+ *   WRAP_STEP     TherapyWrapper.step(action): one therapy day (+ forced weekend), or the whole
+ *                 Post-Therapy stage until termination / truncation            (:429-478)
+ *   RUN_TO_END    TherapyWrapper.benchmark(): zero-dose days until the episode ends, then
+ *                 t_benchmark <- simulationDays                               (:480-505)          */
+typedef enum { PDECG_BT_RAW_STEP = 0, PDECG_BT_WRAP_RESET = 1, PDECG_BT_WRAP_STEP = 2, PDECG_BT_RUN_TO_END = 3 } pdecg_bt_mode;
+
+/* Per-env integer bookkeeping, int32 [n_envs, PDECG_BT_NINT] (the reference's attributes). */
+enum {
+    PDECG_BT_I_T = 0, PDECG_BT_I_STAGE = 1, PDECG_BT_I_GROWTH_DAYS = 2, PDECG_BT_I_THERAPY_DAYS = 3,
+    PDECG_BT_I_POST_DAYS = 4, PDECG_BT_I_SIM_DAYS = 5, PDECG_BT_I_FIRST_THERAPY = 6 /* -1 = None */,
+    PDECG_BT_I_FIRST_POST = 7 /* -1 = None */, PDECG_BT_I_DEATH_DAY = 8 /* -1 = None */,
+    PDECG_BT_I_T_BENCHMARK = 9 /* -1 = None */, PDECG_BT_I_CONSECUTIVE = 10, PDECG_BT_I_TREATMENT_CALLS = 11,
+    PDECG_BT_I_VIOLATIONS = 12, PDECG_BT_NINT = 16
+};
+/* Per-env float64 values, [n_envs, PDECG_BT_NF64]. */
+enum { PDECG_BT_F_REMAINING = 0, PDECG_BT_F_D = 1, PDECG_BT_F_RHO = 2, PDECG_BT_F_LAST_DOSE = 3, PDECG_BT_NF64 = 4 };
+
+/* Constructor kwargs of BrainTumor1D (brain_tumor_env.py:33-101). */
+typedef struct {
+    int32_t abi_version;
+    int32_t nx;                  /* int(round(X/dx)+1)     :52 */
+    int32_t nt;                  /* int(round(T/dt)+1)     base_env_1d.py:23 */
+    int32_t weekends;            /* TherapyWrapper(weekends=...) */
+    double dt, dx;
+    double k;                    /* carrying capacity */
+    double t1_threshold_k;       /* t1_detection_threshold * k   (:114) */
+    double t2_threshold_k;       /* t2_detection_threshold * k */
+    double dosage_termination_threshold;
+    double alpha, alpha_beta_ratio;
+    double t1_detection_radius, t1_death_radius;
+    double total_dosage;
+} pdecg_bt_cfg;
+
+typedef struct {
+    int64_t n_envs;
+    double* u;              /* [n_envs, nx] state = cell density c(x)                                     */
+    double* obs;            /* [n_envs, nx] observation returned by the wrapper modes (may be NULL for RAW_STEP,
+                               where the observation is the state itself)                              */
+    const double* x_scale;  /* [nx] np.linspace(0, X, nx)   (:57)                                        */
+    const double* action;   /* [n_envs] proportion of total_dosage (unused by WRAP_RESET / RUN_TO_END)   */
+    int32_t* ienv;          /* [n_envs, PDECG_BT_NINT]                                                  */
+    double* fenv;           /* [n_envs, PDECG_BT_NF64]                                                  */
+    double* reward;         /* [n_envs]                                                                 */
+    uint8_t* terminated;    /* [n_envs]                                                                 */
+    uint8_t* truncated;     /* [n_envs]                                                                 */
+    uint8_t* valid;         /* [n_envs] 0 where the reference's step() would have returned None (:135)  */
+} pdecg_bt_buffers;
+
+/* BrainTumor1D.reset (:347-384): u <- init ([n_envs or 1, nx] float64), stage <- Growth, counters <- 0;
+ * D, rho and t_benchmark are kept.  mask == NULL resets every env. */
+int pdecg_bt_reset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const double* init,
+                   int64_t init_env_stride, const uint8_t* mask, pdecg_stream_t stream);
+/* One launch of `mode` (pdecg_bt_mode) for all envs. */
+int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t mode, pdecg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Misc
  * ------------------------------------------------------------------------------------------ */
 const char* pdecg_last_error(void);

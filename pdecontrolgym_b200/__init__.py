@@ -14,6 +14,7 @@ instances whose state lives on the GPU and is advanced by hand-written sm_100a k
 from .rewards import (BaseReward, BrainTumorReward, NormReward, NSReward, TrafficARZReward,
                       TunedReward1D)
 from .envs_bc1d import ReactionDiffusionPDE1D, TransportPDE1D
+from .envs_brain_tumor import BrainTumor1D, TherapyWrapper
 
 __version__ = "0.1.0"
 
@@ -22,6 +23,7 @@ __version__ = "0.1.0"
 REGISTRY = {
     "PDEControlGym-TransportPDE1D": TransportPDE1D,
     "PDEControlGym-ReactionDiffusionPDE1D": ReactionDiffusionPDE1D,
+    "PDEControlGym-BrainTumor1D": BrainTumor1D,
 }
 
 
@@ -34,5 +36,5 @@ def make(id: str, num_envs: int = 1, device="cuda", precision: str = "ref", **kw
 
 make_vec = make
 
-__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BaseReward",
+__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "BaseReward",
            "NormReward", "TunedReward1D", "NSReward", "TrafficARZReward", "BrainTumorReward"]

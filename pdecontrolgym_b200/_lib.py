@@ -47,6 +47,24 @@ class Bc1dBuffers(C.Structure):
     ]
 
 
+class BtCfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("nx", C.c_int32), ("nt", C.c_int32), ("weekends", C.c_int32),
+        ("dt", C.c_double), ("dx", C.c_double), ("k", C.c_double), ("t1_threshold_k", C.c_double),
+        ("t2_threshold_k", C.c_double), ("dosage_termination_threshold", C.c_double),
+        ("alpha", C.c_double), ("alpha_beta_ratio", C.c_double), ("t1_detection_radius", C.c_double),
+        ("t1_death_radius", C.c_double), ("total_dosage", C.c_double),
+    ]
+
+
+class BtBuffers(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("u", C.c_void_p), ("obs", C.c_void_p), ("x_scale", C.c_void_p),
+        ("action", C.c_void_p), ("ienv", C.c_void_p), ("fenv", C.c_void_p), ("reward", C.c_void_p),
+        ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("valid", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -76,6 +94,10 @@ def lib():
     L.pdecg_bc1d_step_host.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_bc1d_step_host.restype = C.c_int
+    L.pdecg_bt_reset.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.pdecg_bt_reset.restype = C.c_int
+    L.pdecg_bt_run.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers), C.c_int32, C.c_void_p]
+    L.pdecg_bt_run.restype = C.c_int
     L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double), C.c_void_p]
     L.pdecg_probe_fp_issue.restype = C.c_int

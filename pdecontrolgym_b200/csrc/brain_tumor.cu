@@ -1,0 +1,379 @@
+// brain_tumor.cu -- BrainTumor1D (+ TherapyWrapper semantics): kernels + C ABI (sm_100a, float64).
+//
+// Reference behaviour restated here (no code shared): brain_tumor_env.py:33-505 and
+// rewards/brain_tumor_reward.py:31-73 of lukebhan/PDEControlGym.
+//
+// One warp = one patient.  The density row c(x) stays in registers; the wrapper-level loops of the
+// reference (whole Growth stage inside reset(), whole Post-Therapy stage inside one step(), forced
+// weekend days, the benchmark episode) run INSIDE one launch with a per-env (warp-uniform) trip count,
+// so a multi-day advance costs one HBM round trip of the row instead of one per day.
+#include "pdecg_internal.h"
+
+namespace pdecg {
+
+struct BtArgs {
+    pdecg_bt_cfg cfg;
+    pdecg_bt_buffers buf;
+    int mode;
+};
+
+struct BtEnv {   // the reference's per-env attributes (brain_tumor_env.py:89-101)
+    int t, stage, growthDays, therapyDays, postTherapyDays, simulationDays;
+    int firstTherapyDay, firstPostTherapyDay, cDeathDay, t_benchmark;
+    int consecutive, treatment_calls, violations;
+    double remaining, D, rho, last_dose;
+};
+
+// right-most index j with c_j >= thr (getTumorRadius, :104-121); -1 when the tumour is invisible
+template <int K>
+__device__ __forceinline__ int rightmost_ge(const double (&c)[K], int j0, int nx, double thr) {
+    int best = -1;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = j0 + k;
+        if (j < nx && c[k] >= thr) best = j;      // ascending k -> keeps the largest
+    }
+    return warp_max_i(best);
+}
+
+// _update_fd (:221-245).  rin < 0 encodes "R is None"; treat_to = number of leading points with
+// xScale <= treatmentRadius (they receive R = rin, the others R = 1 - exp(-alpha*0) = 0).
+template <int K>
+__device__ __forceinline__ void bt_fd(const pdecg_bt_cfg& cfg, const double (&c)[K], double (&n)[K], int lane, int j0,
+                                       double D, double rho, bool has_r, double rin, int treat_to) {
+    const int nx = cfg.nx;
+    const double dx2 = __dmul_rn(cfg.dx, cfg.dx);          // self.dx ** 2
+    const double hl = __shfl_up_sync(kFull, c[K - 1], 1);
+    const double hr = __shfl_down_sync(kFull, c[0], 1);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double cl = (k == 0) ? hl : c[k > 0 ? k - 1 : 0];
+        const double cr = (k == K - 1) ? hr : c[k < K - 1 ? k + 1 : K - 1];
+        const double cc = c[k];
+        // diffusion = D * (((u_r - 2.0*u_c) + u_l) / dx**2)
+        const double lap = __ddiv_rn(__dadd_rn(__dsub_rn(cr, __dmul_rn(2.0, cc)), cl), dx2);
+        const double diff = __dmul_rn(D, lap);
+        // proliferation = (rho*u_c) * (1.0 - u_c/k)
+        const double om = __dsub_rn(1.0, __ddiv_rn(cc, cfg.k));
+        const double pro = __dmul_rn(__dmul_rn(rho, cc), om);
+        double acc = __dadd_rn(diff, pro);
+        if (has_r) {
+            const double rj = (j0 + k < treat_to) ? rin : 0.0;
+            acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(rj, cc), om));
+        } else {
+            acc = __dsub_rn(acc, 0.0);                      // `- radiation` with radiation = 0.0
+        }
+        n[k] = __dadd_rn(cc, __dmul_rn(cfg.dt, acc));
+    }
+    // nextU[0] = nextU[1]; nextU[-1] = nextU[-2]  (mirrored ends), then clip to [0, k]
+    const double from_left = __shfl_up_sync(kFull, n[K - 1], 1);
+    const double from_right = __shfl_down_sync(kFull, n[0], 1);
+    double m[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = j0 + k;
+        double v = n[k];
+        if (j == 0) v = (K > 1) ? n[K > 1 ? 1 : 0] : from_right;
+        if (j == nx - 1) v = (k > 0) ? n[k > 0 ? k - 1 : 0] : from_left;
+        v = (v < 0.0) ? 0.0 : ((v > cfg.k) ? cfg.k : v);   // np.clip keeps NaN
+        m[k] = (j < nx) ? v : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) n[k] = m[k];
+}
+
+__device__ __forceinline__ void bt_book(BtEnv& e) {
+    if (e.stage == PDECG_BT_THERAPY) {
+        e.therapyDays = e.t - e.growthDays;
+        e.simulationDays = e.growthDays + e.therapyDays;
+    } else if (e.stage == PDECG_BT_POST) {
+        e.postTherapyDays = e.t - e.therapyDays - e.growthDays;
+        e.simulationDays = e.growthDays + e.therapyDays + e.postTherapyDays;
+    }
+}
+
+// One call of BrainTumor1D.step (:123-218) for an env with t < nt-1.
+template <int K>
+__device__ __forceinline__ void bt_day(const BtArgs& a, BtEnv& e, double (&u)[K], int lane, int j0, double control,
+                                        double& reward, bool& term, bool& trunc) {
+    const pdecg_bt_cfg& cfg = a.cfg;
+    const int nx = cfg.nx;
+    e.t += 1;
+    double n[K];
+    double treat_r = 0.0, applied = 0.0;
+    const int stage0 = e.stage;
+    if (stage0 == PDECG_BT_THERAPY) {
+        // :158-166
+        const double want = __dmul_rn(control, cfg.total_dosage);
+        applied = (e.remaining < want) ? e.remaining : want;          // python min(a, b)
+        e.remaining = __dsub_rn(e.remaining, applied);
+        e.last_dose = applied;
+        // _compute_radiation_field (:247-265) uses the PREVIOUS day's T2 radius
+        const int t2 = rightmost_ge<K>(u, j0, nx, cfg.t2_threshold_k);
+        treat_r = (t2 < 0) ? 0.0 : __dadd_rn(__dmul_rn(static_cast<double>(t2), cfg.dx), 25.0);
+        // number of leading grid points with xScale <= treat_r (xScale is increasing)
+        int cnt = 0;
+        for (int j = lane; j < nx; j += 32) cnt += (a.buf.x_scale[j] <= treat_r) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+        const double bed = __dadd_rn(applied, __ddiv_rn(__dmul_rn(applied, applied), cfg.alpha_beta_ratio));
+        const double rin = __dsub_rn(1.0, exp(__dmul_rn(-cfg.alpha, bed)));
+        bt_fd<K>(cfg, u, n, lane, j0, e.D, e.rho, true, rin, cnt);
+    } else {
+        bt_fd<K>(cfg, u, n, lane, j0, e.D, e.rho, false, 0.0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) u[k] = n[k];
+
+    const int t1 = rightmost_ge<K>(u, j0, nx, cfg.t1_threshold_k);
+    const double t1_radius = __dmul_rn(static_cast<double>(t1), cfg.dx);
+    if (stage0 == PDECG_BT_GROWTH) {
+        e.growthDays = e.t;
+        if (t1 >= 0 && t1_radius >= cfg.t1_detection_radius) {       // :151-155
+            e.firstTherapyDay = e.t + 1;
+            e.stage = PDECG_BT_THERAPY;
+        }
+    } else if (stage0 == PDECG_BT_THERAPY) {
+        if (e.remaining < cfg.dosage_termination_threshold) {        // :171-176
+            e.therapyDays = e.t - e.growthDays;
+            e.firstPostTherapyDay = e.t + 1;
+            e.stage = PDECG_BT_POST;
+        }
+    }
+    // terminate() (:285-311) then truncate() (:313-345)
+    term = e.t >= cfg.nt - 1;
+    if (term) bt_book(e);
+    trunc = (t1 >= 0) && (t1_radius >= cfg.t1_death_radius);
+    if (trunc && e.cDeathDay < 0) {
+        e.cDeathDay = e.t;
+        bt_book(e);
+    }
+    // rewards (brain_tumor_reward.py:46-73)
+    const bool ended = term || trunc;
+    if (stage0 == PDECG_BT_THERAPY) {
+        if (e.t_benchmark < 0) reward = 0.0;
+        else if (ended) reward = static_cast<double>(e.t - e.t_benchmark);
+        else {
+            const double maxsafe = __dmul_rn(116.0, pow(treat_r, -0.685));
+            const double ratio = __ddiv_rn(__dsub_rn(applied, maxsafe), __dsub_rn(cfg.total_dosage, maxsafe));
+            double cl = (0.0 > ratio) ? 0.0 : ratio;       // python max(ratio, 0.0)
+            cl = (1.0 < cl) ? 1.0 : cl;                    // python min(., 1.0)
+            reward = __dmul_rn(-50.0, pow(cl, 1.0 / 3.0));
+        }
+    } else if (e.stage == PDECG_BT_POST && ended) {
+        reward = (e.t_benchmark < 0) ? 0.0 : static_cast<double>(e.t - e.t_benchmark);
+    } else {
+        reward = 0.0;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) bt_run_kernel(const BtArgs a) {
+    __shared__ double sm_all[kWarpsPerBlock][32 * K];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
+    if (env >= a.buf.n_envs) return;
+    double* sm = sm_all[wib];
+    const pdecg_bt_cfg& cfg = a.cfg;
+    const int nx = cfg.nx;
+    const int j0 = lane * K;
+
+    // per-env scalars: one coalesced read, broadcast by shuffle
+    int* irow = a.buf.ienv + env * PDECG_BT_NINT;
+    double* frow = a.buf.fenv + env * PDECG_BT_NF64;
+    const int iv = (lane < PDECG_BT_NINT) ? irow[lane] : 0;
+    const double fv = (lane < PDECG_BT_NF64) ? frow[lane] : 0.0;
+    BtEnv e;
+    e.t = __shfl_sync(kFull, iv, PDECG_BT_I_T);
+    e.stage = __shfl_sync(kFull, iv, PDECG_BT_I_STAGE);
+    e.growthDays = __shfl_sync(kFull, iv, PDECG_BT_I_GROWTH_DAYS);
+    e.therapyDays = __shfl_sync(kFull, iv, PDECG_BT_I_THERAPY_DAYS);
+    e.postTherapyDays = __shfl_sync(kFull, iv, PDECG_BT_I_POST_DAYS);
+    e.simulationDays = __shfl_sync(kFull, iv, PDECG_BT_I_SIM_DAYS);
+    e.firstTherapyDay = __shfl_sync(kFull, iv, PDECG_BT_I_FIRST_THERAPY);
+    e.firstPostTherapyDay = __shfl_sync(kFull, iv, PDECG_BT_I_FIRST_POST);
+    e.cDeathDay = __shfl_sync(kFull, iv, PDECG_BT_I_DEATH_DAY);
+    e.t_benchmark = __shfl_sync(kFull, iv, PDECG_BT_I_T_BENCHMARK);
+    e.consecutive = __shfl_sync(kFull, iv, PDECG_BT_I_CONSECUTIVE);
+    e.treatment_calls = __shfl_sync(kFull, iv, PDECG_BT_I_TREATMENT_CALLS);
+    e.violations = __shfl_sync(kFull, iv, PDECG_BT_I_VIOLATIONS);
+    e.remaining = __shfl_sync(kFull, fv, PDECG_BT_F_REMAINING);
+    e.D = __shfl_sync(kFull, fv, PDECG_BT_F_D);
+    e.rho = __shfl_sync(kFull, fv, PDECG_BT_F_RHO);
+    e.last_dose = __shfl_sync(kFull, fv, PDECG_BT_F_LAST_DOSE);
+
+    double* urow = a.buf.u + env * nx;
+    double u[K];
+    load_row_chunk<double, double, K>(u, urow, nx, sm, lane);
+
+    double reward = 0.0;
+    bool term = false, trunc = false, valid = true, wrote_obs = false;
+    const int last = cfg.nt - 1;
+
+    if (a.mode == PDECG_BT_RAW_STEP) {
+        if (e.t < last) {
+            bt_day<K>(a, e, u, lane, j0, a.buf.action[env], reward, term, trunc);
+        } else {
+            valid = false;                       // the reference returns None here (:135)
+            term = true;
+        }
+    } else if (a.mode == PDECG_BT_WRAP_RESET) {
+        // TherapyWrapper.reset (:408-427)
+        e.consecutive = 0;
+        while (e.stage == PDECG_BT_GROWTH && e.t < last) {
+            bt_day<K>(a, e, u, lane, j0, 0.0, reward, term, trunc);
+            if (term || trunc) break;
+        }
+    } else if (a.mode == PDECG_BT_RUN_TO_END) {
+        // TherapyWrapper.benchmark (:480-505): zero-dose episode, then t_benchmark <- simulationDays
+        while (!(term || trunc) && e.t < last) bt_day<K>(a, e, u, lane, j0, 0.0, reward, term, trunc);
+        e.t_benchmark = e.simulationDays;
+    } else {
+        // TherapyWrapper.step (:429-478)
+        if (e.stage == PDECG_BT_POST) {
+            while (!(term || trunc) && e.t < last) bt_day<K>(a, e, u, lane, j0, 0.0, reward, term, trunc);
+            if (e.t >= last && !(term || trunc)) { valid = false; term = true; }
+        } else if (e.t < last) {
+            const double control = a.buf.action[env];
+            bt_day<K>(a, e, u, lane, j0, control, reward, term, trunc);
+            e.treatment_calls += 1;
+            if (reward < 0.0) e.violations += 1;
+            if (cfg.weekends) {
+                e.consecutive = (control > 0.0) ? e.consecutive + 1 : 0;
+                if (e.consecutive >= 5) {
+                    e.consecutive = 0;
+                    // the observation returned is the therapy day's row; the two rest days' results are
+                    // discarded and the loop tests the STALE flags (:470-473)
+                    if (a.buf.obs != nullptr) {
+                        store_row_chunk<double, K>(u, a.buf.obs + env * nx, nx, sm, lane);
+                        wrote_obs = true;
+                    }
+                    for (int i = 0; i < 2; ++i) {
+                        if (e.t < last) {
+                            double r2;
+                            bool te2, tr2;
+                            bt_day<K>(a, e, u, lane, j0, 0.0, r2, te2, tr2);
+                        }
+                        if (term || trunc) break;
+                    }
+                }
+            }
+        } else {
+            valid = false;
+            term = true;
+        }
+    }
+
+    store_row_chunk<double, K>(u, urow, nx, sm, lane);
+    if (a.buf.obs != nullptr && !wrote_obs) store_row_chunk<double, K>(u, a.buf.obs + env * nx, nx, sm, lane);
+
+    // write back scalars (coalesced)
+    int ov = iv;
+    ov = (lane == PDECG_BT_I_T) ? e.t : ov;
+    ov = (lane == PDECG_BT_I_STAGE) ? e.stage : ov;
+    ov = (lane == PDECG_BT_I_GROWTH_DAYS) ? e.growthDays : ov;
+    ov = (lane == PDECG_BT_I_THERAPY_DAYS) ? e.therapyDays : ov;
+    ov = (lane == PDECG_BT_I_POST_DAYS) ? e.postTherapyDays : ov;
+    ov = (lane == PDECG_BT_I_SIM_DAYS) ? e.simulationDays : ov;
+    ov = (lane == PDECG_BT_I_FIRST_THERAPY) ? e.firstTherapyDay : ov;
+    ov = (lane == PDECG_BT_I_FIRST_POST) ? e.firstPostTherapyDay : ov;
+    ov = (lane == PDECG_BT_I_DEATH_DAY) ? e.cDeathDay : ov;
+    ov = (lane == PDECG_BT_I_T_BENCHMARK) ? e.t_benchmark : ov;
+    ov = (lane == PDECG_BT_I_CONSECUTIVE) ? e.consecutive : ov;
+    ov = (lane == PDECG_BT_I_TREATMENT_CALLS) ? e.treatment_calls : ov;
+    ov = (lane == PDECG_BT_I_VIOLATIONS) ? e.violations : ov;
+    if (lane < PDECG_BT_NINT) irow[lane] = ov;
+    double of = fv;
+    of = (lane == PDECG_BT_F_REMAINING) ? e.remaining : of;
+    of = (lane == PDECG_BT_F_LAST_DOSE) ? e.last_dose : of;
+    if (lane < PDECG_BT_NF64) frow[lane] = of;
+    if (lane == 0) {
+        a.buf.reward[env] = reward;
+        a.buf.terminated[env] = term ? 1 : 0;
+        a.buf.truncated[env] = trunc ? 1 : 0;
+        if (a.buf.valid) a.buf.valid[env] = valid ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bt_reset_kernel(const BtArgs a, const double* __restrict__ init, int64_t init_stride,
+                                                            const uint8_t* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (env >= a.buf.n_envs) return;
+    if (mask != nullptr && mask[env] == 0) return;
+    const int nx = a.cfg.nx;
+    const double* irow = init + env * init_stride;
+    double* urow = a.buf.u + env * nx;
+    for (int j = lane; j < nx; j += 32) {
+        const double v = irow[j];
+        urow[j] = v;
+        if (a.buf.obs) a.buf.obs[env * nx + j] = v;
+    }
+    // brain_tumor_env.py:363-379; t_benchmark, D, rho survive a reset
+    int* ir = a.buf.ienv + env * PDECG_BT_NINT;
+    if (lane < PDECG_BT_NINT) {
+        int v = 0;
+        if (lane == PDECG_BT_I_FIRST_THERAPY || lane == PDECG_BT_I_FIRST_POST || lane == PDECG_BT_I_DEATH_DAY) v = -1;
+        if (lane == PDECG_BT_I_T_BENCHMARK || lane == PDECG_BT_I_TREATMENT_CALLS || lane == PDECG_BT_I_VIOLATIONS) v = ir[lane];
+        ir[lane] = v;
+    }
+    if (lane == 0) {
+        double* fr = a.buf.fenv + env * PDECG_BT_NF64;
+        fr[PDECG_BT_F_REMAINING] = a.cfg.total_dosage;
+        fr[PDECG_BT_F_LAST_DOSE] = 0.0;
+        a.buf.reward[env] = 0.0;
+        a.buf.terminated[env] = 0;
+        a.buf.truncated[env] = 0;
+        if (a.buf.valid) a.buf.valid[env] = 1;
+    }
+}
+
+static int bt_validate(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf) {
+    if (!cfg || !buf) return fail(PDECG_ERR_INVALID, "null cfg/buffers");
+    if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
+    if (cfg->nx < 4 || cfg->nt < 2) return fail(PDECG_ERR_INVALID, "need nx >= 4 and nt >= 2");
+    if (cfg->nx > 256) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", cfg->nx);
+    if (!(cfg->dt > 0) || !(cfg->dx > 0) || !(cfg->k > 0)) return fail(PDECG_ERR_INVALID, "dt, dx, k must be positive");
+    if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
+    if (buf->n_envs > 0 && (!buf->u || !buf->ienv || !buf->fenv || !buf->reward || !buf->terminated || !buf->truncated || !buf->x_scale))
+        return fail(PDECG_ERR_INVALID, "null device buffer");
+    return PDECG_OK;
+}
+
+}  // namespace pdecg
+
+using namespace pdecg;
+
+extern "C" int pdecg_bt_reset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const double* init,
+                              int64_t init_env_stride, const uint8_t* mask, pdecg_stream_t stream) {
+    int rc = bt_validate(cfg, buf);
+    if (rc != PDECG_OK) return rc;
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!init) return fail(PDECG_ERR_INVALID, "null init buffer");
+    BtArgs a{*cfg, *buf, 0};
+    const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    bt_reset_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init, init_env_stride, mask);
+    count_launch();
+    return check_launch("bt_reset_kernel");
+}
+
+extern "C" int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t mode, pdecg_stream_t stream) {
+    int rc = bt_validate(cfg, buf);
+    if (rc != PDECG_OK) return rc;
+    if (mode < PDECG_BT_RAW_STEP || mode > PDECG_BT_RUN_TO_END) return fail(PDECG_ERR_INVALID, "bad mode %d", mode);
+    if (buf->n_envs == 0) return PDECG_OK;
+    if ((mode == PDECG_BT_RAW_STEP || mode == PDECG_BT_WRAP_STEP) && !buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
+    BtArgs a{*cfg, *buf, mode};
+    const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K = (cfg->nx + 31) / 32;
+    switch (K) {
+#define PDECG_CASE(KK) case KK: bt_run_kernel<KK><<<grid, kThreads, 0, st>>>(a); break;
+        PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
+#undef PDECG_CASE
+        default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
+    }
+    count_launch();
+    return check_launch("bt_run_kernel");
+}

@@ -1,0 +1,244 @@
+"""BrainTumor1D and TherapyWrapper as batched environments (brain_tumor_env.py:33-505 of the reference).
+
+Same constructor keywords as the reference plus `num_envs`, `device`.  `D` and `rho` may be arrays of
+shape (num_envs,) (per-patient parameters).  All arithmetic is float64 and runs in
+`libpdecg.so` (csrc/brain_tumor.cu); the TherapyWrapper loops (whole Growth stage inside `reset`,
+whole Post-Therapy stage inside one `step`, forced weekends, `benchmark`) run inside ONE kernel
+launch per call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .rewards import BrainTumorReward
+from .spaces import Box
+
+STAGE_NAMES = ("Growth", "Therapy", "Post-Therapy")
+RAW_STEP, WRAP_RESET, WRAP_STEP, RUN_TO_END = 0, 1, 2, 3
+(I_T, I_STAGE, I_GROWTH, I_THERAPY, I_POST, I_SIM, I_FIRST_THERAPY, I_FIRST_POST, I_DEATH, I_TBENCH,
+ I_CONSEC, I_CALLS, I_VIOL) = range(13)
+NINT, NF64 = 16, 4
+F_REMAINING, F_D, F_RHO, F_LAST_DOSE = range(4)
+
+
+class BrainTumor1D:
+    """Batched `BrainTumor1D`: diffusion-proliferation-radiation PDE with the Growth -> Therapy ->
+    Post-Therapy stage machine.  `step(action)` advances every env by one day."""
+
+    def __init__(self,
+                 t1_detection_threshold: float = 0.8,
+                 t2_detection_threshold: float = 0.16,
+                 dosage_termination_threshold: float = 0.1,
+                 D=0.2, rho=0.03, alpha: float = 0.04, alpha_beta_ratio: int = 10, k: float = 1e5,
+                 t1_detection_radius: int = 15, t1_death_radius: int = 35,
+                 reset_init_condition_func=None, total_dosage=None, verbose=False,
+                 *, T, dt, X, dx, reward_class=None, normalize=False,
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True):
+        if precision not in ("ref", "fp64"):
+            raise ValueError("BrainTumor1D is float64 in the reference; precision must be 'ref' or 'fp64'")
+        if reward_class is not None and not isinstance(reward_class, BrainTumorReward):
+            raise TypeError("reward_class must be a pdecontrolgym_b200.BrainTumorReward (evaluated inside the kernel)")
+        self.num_envs = N = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("pdecontrolgym_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.T, self.dt, self.X, self.dx = T, dt, X, dx
+        self.nt = int(round(T / dt) + 1)                 # base_env_1d.py:23
+        self.nx = int(round(X / dx) + 1)                 # brain_tumor_env.py:52
+        self.reward_class = reward_class
+        self.verbose = verbose
+        self.copy_obs = copy_obs
+        self.reset_init_condition_func = reset_init_condition_func
+        self.total_dosage = float(total_dosage)          # :89 (TypeError on None, like the reference)
+        self.k = k
+        self.single_action_space = Box(np.full(1, 0, dtype="float32"), np.full(1, 1, dtype="float32"))
+        self.action_space = Box(np.full((N, 1), 0, dtype="float32"), np.full((N, 1), 1, dtype="float32"))
+        self.single_observation_space = Box(np.full(self.nx, 0, dtype="float64"), np.full(self.nx, k, dtype="float64"), dtype=np.float64)
+        self.observation_space = Box(np.full((N, self.nx), 0, dtype="float64"), np.full((N, self.nx), k, dtype="float64"), dtype=np.float64)
+
+        cfg = _lib.BtCfg()
+        cfg.abi_version = _lib.ABI_VERSION
+        cfg.nx, cfg.nt, cfg.weekends = self.nx, self.nt, 0
+        cfg.dt, cfg.dx, cfg.k = float(dt), float(dx), float(k)
+        cfg.t1_threshold_k = t1_detection_threshold * k          # :114 detectionRatio * self.k
+        cfg.t2_threshold_k = t2_detection_threshold * k
+        cfg.dosage_termination_threshold = float(dosage_termination_threshold)
+        cfg.alpha, cfg.alpha_beta_ratio = float(alpha), float(alpha_beta_ratio)
+        cfg.t1_detection_radius, cfg.t1_death_radius = float(t1_detection_radius), float(t1_death_radius)
+        cfg.total_dosage = self.total_dosage
+        self._cfg = cfg
+        self._L = _lib.lib()
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.u = torch.zeros((N, self.nx), dtype=torch.float64, device=dev)
+            self._obs = torch.zeros((N, self.nx), dtype=torch.float64, device=dev)
+            self.xScale = torch.from_numpy(np.linspace(0, X, self.nx)).to(dev)      # :57
+            self._ienv = torch.zeros((N, NINT), dtype=torch.int32, device=dev)
+            self._ienv[:, [I_FIRST_THERAPY, I_FIRST_POST, I_DEATH, I_TBENCH]] = -1
+            self._fenv = torch.zeros((N, NF64), dtype=torch.float64, device=dev)
+            self._fenv[:, F_REMAINING] = self.total_dosage
+            self._fenv[:, F_D] = torch.as_tensor(np.broadcast_to(np.asarray(D, dtype=np.float64), (N,)).copy(), device=dev)
+            self._fenv[:, F_RHO] = torch.as_tensor(np.broadcast_to(np.asarray(rho, dtype=np.float64), (N,)).copy(), device=dev)
+            self._reward = torch.zeros((N,), dtype=torch.float64, device=dev)
+            self._terminated = torch.zeros((N,), dtype=torch.uint8, device=dev)
+            self._truncated = torch.zeros((N,), dtype=torch.uint8, device=dev)
+            self._valid = torch.ones((N,), dtype=torch.uint8, device=dev)
+            self._zero_action = torch.zeros((N,), dtype=torch.float64, device=dev)
+        buf = _lib.BtBuffers()
+        buf.n_envs = N
+        buf.u, buf.obs, buf.x_scale = self.u.data_ptr(), self._obs.data_ptr(), self.xScale.data_ptr()
+        buf.action = self._zero_action.data_ptr()
+        buf.ienv, buf.fenv = self._ienv.data_ptr(), self._fenv.data_ptr()
+        buf.reward = self._reward.data_ptr()
+        buf.terminated, buf.truncated, buf.valid = self._terminated.data_ptr(), self._truncated.data_ptr(), self._valid.data_ptr()
+        self._buf = buf
+        self._ic = None
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _run(self, mode, action=None):
+        a = self._zero_action if action is None else action
+        self._buf.action = a.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pdecg_bt_run(C.byref(self._cfg), C.byref(self._buf), mode, self._stream()))
+
+    def _prep_action(self, action):
+        if isinstance(action, torch.Tensor):
+            a = action.to(self.device, torch.float64)
+        else:
+            a = torch.from_numpy(np.ascontiguousarray(np.asarray(action, dtype=np.float64))).to(self.device)
+        a = a.reshape(-1)
+        if a.numel() == 1 and self.num_envs > 1:
+            a = a.expand(self.num_envs)
+        if a.numel() != self.num_envs:
+            raise ValueError(f"action must have {self.num_envs} elements (got {a.numel()})")
+        return a.contiguous()
+
+    def _outputs(self, obs_src):
+        obs = obs_src.clone() if self.copy_obs else obs_src
+        return (obs, self._reward.clone(), self._terminated.bool(), self._truncated.bool(),
+                {"stage": self._ienv[:, I_STAGE].clone(), "valid": self._valid.bool()})
+
+    # -- gym API -------------------------------------------------------------------------------
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        """brain_tumor_env.py:347-384.  options["init_condition"]: (nx,) or (num_envs, nx) replaces the
+        `reset_init_condition_func(X, nx)` callback; options["mask"]: reset only those envs."""
+        options = options or {}
+        ic = options.get("init_condition")
+        if ic is None:
+            if self.reset_init_condition_func is None:
+                raise Exception("Please pass an initial condition function")
+            try:
+                ic = self.reset_init_condition_func(self.X, self.nx, self.num_envs)
+            except TypeError:
+                rows = [np.asarray(self.reset_init_condition_func(self.X, self.nx)) for _ in range(self.num_envs)]
+                ic = rows[0] if all(np.array_equal(r, rows[0]) for r in rows[1:]) else np.stack(rows)
+        t = ic.to(self.device, torch.float64) if isinstance(ic, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(ic, dtype=np.float64))).to(self.device)
+        if t.dim() == 1:
+            t = t.unsqueeze(0)
+        if t.shape[-1] != self.nx or t.shape[0] not in (1, self.num_envs):
+            raise ValueError(f"init_condition must have shape ({self.nx},) or ({self.num_envs}, {self.nx})")
+        self._ic = t.contiguous()
+        mask = options.get("mask")
+        mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pdecg_bt_reset(C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
+                                              0 if self._ic.shape[0] == 1 else self.nx,
+                                              None if mask_t is None else mask_t.data_ptr(), self._stream()))
+        return (self.u.clone() if self.copy_obs else self.u), {}
+
+    def step(self, control):
+        """One day for every env (brain_tumor_env.py:123-218).  Envs already at t == nt-1 (where the
+        reference returns None) are left unchanged and flagged in info["valid"]."""
+        if self._ic is None:
+            raise RuntimeError("call reset() before step()")
+        self._run(RAW_STEP, self._prep_action(control))
+        return self._outputs(self.u)
+
+    # -- reference attributes, as per-env tensors ------------------------------------------------
+    def _icol(self, i):
+        return self._ienv[:, i]
+
+    time_index = property(lambda s: s._icol(I_T))
+    stage = property(lambda s: s._icol(I_STAGE))
+    growthDays = property(lambda s: s._icol(I_GROWTH))
+    therapyDays = property(lambda s: s._icol(I_THERAPY))
+    postTherapyDays = property(lambda s: s._icol(I_POST))
+    simulationDays = property(lambda s: s._icol(I_SIM))
+    firstTherapyDay = property(lambda s: s._icol(I_FIRST_THERAPY))
+    firstPostTherapyDay = property(lambda s: s._icol(I_FIRST_POST))
+    cDeathDay = property(lambda s: s._icol(I_DEATH))
+    remaining_dosage = property(lambda s: s._fenv[:, F_REMAINING])
+
+    @property
+    def t_benchmark(self):
+        return self._ienv[:, I_TBENCH]
+
+    @t_benchmark.setter
+    def t_benchmark(self, value):
+        if value is None:
+            self._ienv[:, I_TBENCH] = -1
+        else:
+            self._ienv[:, I_TBENCH] = torch.as_tensor(value, device=self.device).to(torch.int32)
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close(self):
+        pass
+
+
+class TherapyWrapper:
+    """Batched `TherapyWrapper` (brain_tumor_env.py:386-505): exposes only the Therapy stage to the
+    agent.  `reset` runs the whole Growth stage, a `step` in Post-Therapy runs to the end of the
+    episode, `weekends=True` forces two rest days after five consecutive treatment days."""
+
+    def __init__(self, env: BrainTumor1D, weekends=False, verbose=False):
+        self.env = env
+        self.verbose = verbose
+        self.weekends = weekends
+        self.num_envs = env.num_envs
+        self.action_space, self.observation_space = env.action_space, env.observation_space
+        self.single_action_space, self.single_observation_space = env.single_action_space, env.single_observation_space
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    treatment_calls = property(lambda s: s.env._ienv[:, I_CALLS])
+    soft_constraint_violations = property(lambda s: s.env._ienv[:, I_VIOL])
+    consecutive_treatment_days = property(lambda s: s.env._ienv[:, I_CONSEC])
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        env = self.env
+        env.reset(seed=seed, options=options)
+        env._cfg.weekends = int(bool(self.weekends))
+        env._run(WRAP_RESET)
+        return (env._obs.clone() if env.copy_obs else env._obs), {"stage": env._ienv[:, I_STAGE].clone()}
+
+    def step(self, control):
+        env = self.env
+        env._cfg.weekends = int(bool(self.weekends))
+        env._run(WRAP_STEP, env._prep_action(control))
+        return env._outputs(env._obs)
+
+    def benchmark(self):
+        """Runs a zero-dose episode per env, stores its length in `env.t_benchmark`, resets.  Returns the
+        per-env t_benchmark tensor (the reference returns one int)."""
+        env = self.env
+        env.reset()
+        env._run(RUN_TO_END)
+        tb = env._ienv[:, I_TBENCH].clone()
+        env.reset()
+        return tb
