@@ -197,6 +197,52 @@ int pdecg_bt_reset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const d
 int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t mode, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Family 3: TrafficPDE1D (Aw-Rascle-Zhang) + TrafficARZReward      -- all float64
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { PDECG_ARZ_INLET = 0, PDECG_ARZ_OUTLET = 1, PDECG_ARZ_BOTH = 2, PDECG_ARZ_OUTLET_TRAIN = 3 } pdecg_arz_type;
+/* Per-env float64 values, [n_envs, PDECG_ARZ_NF64]: the float time (traffic_arz_env.py:148 -- `time_index`
+ * advances by dt per STEP and is compared with T/dt, reference quirk Q9) and the steady state. */
+enum { PDECG_ARZ_F_TIME = 0, PDECG_ARZ_F_RS = 1, PDECG_ARZ_F_VS = 2, PDECG_ARZ_F_QS = 3, PDECG_ARZ_NF64 = 4 };
+
+/* Constructor kwargs of TrafficPDE1D (traffic_arz_env.py:23-100); the dt/dx/tau combinations are
+ * passed as the Python floats the reference forms (:202-222) so the kernel multiplies by the same bits. */
+typedef struct {
+    int32_t abi_version;
+    int32_t simulation_type;      /* pdecg_arz_type */
+    int32_t M;                    /* len(np.arange(0, X+dx, dx))      :74-76 */
+    int32_t control_freq;         /* substeps per step                :43    */
+    int32_t limit_pde_state_size;
+    int32_t action_dim;           /* 1, or 2 for 'both'               :97-100 */
+    double T, dt;
+    double t_over_dt;             /* self.T / self.dt                 :109   */
+    double vm, rm;
+    double c1;                    /* dt / (2*dx)                      :202   */
+    double c2;                    /* 0.25 * dt / tau                  :208   */
+    double c3;                    /* dt / dx                          :218   */
+    double c4;                    /* 0.5 * dt / tau                   :221   */
+    double vm_over_rm;            /* self.vm / self.rm                :84    */
+} pdecg_arz_cfg;
+
+typedef struct {
+    int64_t n_envs;
+    double* ry;              /* [n_envs, 2, M] state: density rho then y = rho*(v - Veq(rho))            */
+    double* obs;             /* [n_envs, 2*M]  concat(rho, v)  (normalised deviations for OUTLET_TRAIN)  */
+    const double* action;    /* [n_envs, action_dim] flow-rate control(s)                               */
+    double* fenv;            /* [n_envs, PDECG_ARZ_NF64]                                                */
+    double* reward;          /* [n_envs]                                                                */
+    uint8_t* terminated;     /* [n_envs]                                                                */
+    uint8_t* truncated;      /* [n_envs]                                                                */
+} pdecg_arz_buffers;
+
+/* TrafficPDE1D.reset (:237-267): rho <- rs*profile, y, v from the fixed sinusoidal initial condition.
+ * `profile` is [M] = sin(3x/L*pi)*0.1 + 1 evaluated by the caller; fenv rows must already hold rs/vs/qs.
+ * Like the reference it does NOT reset the time (terminate() does).  mask == NULL: all envs. */
+int pdecg_arz_reset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* profile,
+                    const uint8_t* mask, pdecg_stream_t stream);
+/* TrafficPDE1D.step (:131-233) + terminate/truncate (:103-127) + TrafficARZReward.reward. */
+int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, pdecg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Misc
  * ------------------------------------------------------------------------------------------ */
 const char* pdecg_last_error(void);

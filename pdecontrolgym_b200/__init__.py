@@ -15,6 +15,7 @@ from .rewards import (BaseReward, BrainTumorReward, NormReward, NSReward, Traffi
                       TunedReward1D)
 from .envs_bc1d import ReactionDiffusionPDE1D, TransportPDE1D
 from .envs_brain_tumor import BrainTumor1D, TherapyWrapper
+from .envs_traffic_arz import TrafficPDE1D
 
 __version__ = "0.1.0"
 
@@ -24,6 +25,7 @@ REGISTRY = {
     "PDEControlGym-TransportPDE1D": TransportPDE1D,
     "PDEControlGym-ReactionDiffusionPDE1D": ReactionDiffusionPDE1D,
     "PDEControlGym-BrainTumor1D": BrainTumor1D,
+    "PDEControlGym-TrafficPDE1D": TrafficPDE1D,
 }
 
 
@@ -36,5 +38,5 @@ def make(id: str, num_envs: int = 1, device="cuda", precision: str = "ref", **kw
 
 make_vec = make
 
-__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "BaseReward",
+__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "BaseReward",
            "NormReward", "TunedReward1D", "NSReward", "TrafficARZReward", "BrainTumorReward"]

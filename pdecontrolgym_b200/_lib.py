@@ -65,6 +65,22 @@ class BtBuffers(C.Structure):
     ]
 
 
+class ArzCfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("simulation_type", C.c_int32), ("M", C.c_int32), ("control_freq", C.c_int32),
+        ("limit_pde_state_size", C.c_int32), ("action_dim", C.c_int32), ("T", C.c_double), ("dt", C.c_double),
+        ("t_over_dt", C.c_double), ("vm", C.c_double), ("rm", C.c_double), ("c1", C.c_double), ("c2", C.c_double),
+        ("c3", C.c_double), ("c4", C.c_double), ("vm_over_rm", C.c_double),
+    ]
+
+
+class ArzBuffers(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("ry", C.c_void_p), ("obs", C.c_void_p), ("action", C.c_void_p),
+        ("fenv", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -98,6 +114,10 @@ def lib():
     L.pdecg_bt_reset.restype = C.c_int
     L.pdecg_bt_run.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers), C.c_int32, C.c_void_p]
     L.pdecg_bt_run.restype = C.c_int
+    L.pdecg_arz_reset.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdecg_arz_reset.restype = C.c_int
+    L.pdecg_arz_step.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p]
+    L.pdecg_arz_step.restype = C.c_int
     L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double), C.c_void_p]
     L.pdecg_probe_fp_issue.restype = C.c_int

@@ -1,0 +1,263 @@
+// traffic_arz.cu -- TrafficPDE1D (Aw-Rascle-Zhang) step / reset kernels + C ABI (sm_100a, float64).
+//
+// Reference behaviour restated here (no code shared): traffic_arz_env.py:23-280 and
+// rewards/traffic_arz_reward.py:12-22 of lukebhan/PDEControlGym.
+//
+// One warp = one freeway.  (rho, y) rows live in registers; per substep the Richtmyer two-step
+// Lax-Wendroff update needs the right neighbour's node state/fluxes (shuffle down) and the left
+// neighbour's midpoint fluxes (shuffle up).  Node and midpoint fluxes are computed once and shared
+// between the two cells that use them -- bit-identical to the reference, which evaluates them twice.
+#include "pdecg_internal.h"
+
+namespace pdecg {
+
+struct ArzArgs {
+    pdecg_arz_cfg cfg;
+    pdecg_arz_buffers buf;
+};
+
+using D = Strict<double>;
+
+__device__ __forceinline__ double veq(const pdecg_arz_cfg& c, double rho) {          // :271-272
+    return D::mul(c.vm, D::sub(1.0, D::div(rho, c.rm)));
+}
+__device__ __forceinline__ double flux_r(const pdecg_arz_cfg& c, double rho, double y) {   // :275-276
+    return D::add(y, D::mul(rho, veq(c, rho)));
+}
+__device__ __forceinline__ double flux_y(const pdecg_arz_cfg& c, double rho, double y) {   // :279-280
+    return D::mul(y, D::add(D::div(y, rho), veq(c, rho)));
+}
+__device__ __forceinline__ double clipd(double v, double lo, double hi) {            // np.clip keeps NaN
+    v = (v < lo) ? lo : v;
+    return (v > hi) ? hi : v;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
+    __shared__ double sm_all[kWarpsPerBlock][32 * K];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
+    if (env >= a.buf.n_envs) return;
+    double* sm = sm_all[wib];
+    const pdecg_arz_cfg& cfg = a.cfg;
+    const int M = cfg.M;
+    const int j0 = lane * K;
+
+    double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
+    const double fv = (lane < PDECG_ARZ_NF64) ? frow[lane] : 0.0;
+    double time = __shfl_sync(kFull, fv, PDECG_ARZ_F_TIME);
+    const double rs = __shfl_sync(kFull, fv, PDECG_ARZ_F_RS);
+    const double vs = __shfl_sync(kFull, fv, PDECG_ARZ_F_VS);
+    const double qs = __shfl_sync(kFull, fv, PDECG_ARZ_F_QS);
+
+    double* rrow = a.buf.ry + env * 2 * M;
+    double* yrow = rrow + M;
+    double r[K], y[K];
+    load_row_chunk<double, double, K>(r, rrow, M, sm, lane);
+    load_row_chunk<double, double, K>(y, yrow, M, sm, lane);
+
+    // :148-170 -- float time advances once per step; actions clipped to the action space
+    time = D::add(time, cfg.dt);
+    const double lo = D::mul(qs, 0.8), hi = D::mul(1.2, qs);                          // :98-100
+    const double* act = a.buf.action + env * cfg.action_dim;
+    const double a0 = clipd(act[0], lo, hi);
+    const double a1 = (cfg.action_dim > 1) ? clipd(act[1], lo, hi) : a0;
+    const int st = cfg.simulation_type;
+    const double q_in = (st == PDECG_ARZ_INLET || st == PDECG_ARZ_BOTH) ? a0 : qs;
+    const double q_out = (st == PDECG_ARZ_OUTLET || st == PDECG_ARZ_OUTLET_TRAIN) ? a0 : ((st == PDECG_ARZ_BOTH) ? a1 : qs);
+
+    for (int count = 0; count < cfg.control_freq && time < cfg.T; ++count) {          // :173
+        // ---- boundary conditions (:175-190) ----
+        {
+            const double r_right = __shfl_down_sync(kFull, r[0], 1);                  // node j0+K
+            const double r_left = __shfl_up_sync(kFull, r[K - 1], 1);                 // node j0-1
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int j = j0 + k;
+                const double rn = (k < K - 1) ? r[k < K - 1 ? k + 1 : 0] : r_right;   // r[j+1]
+                const double rp = (k > 0) ? r[k > 0 ? k - 1 : 0] : r_left;            // r[j-1]
+                if (j == 0) {
+                    r[k] = rn;
+                    y[k] = D::sub(q_in, D::mul(r[k], veq(cfg, r[k])));
+                }
+                if (j == M - 1) {
+                    r[k] = rp;
+                    y[k] = D::sub(q_out, D::mul(r[k], veq(cfg, r[k])));
+                }
+            }
+        }
+        // ---- node fluxes ----
+        double fr[K], fy[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            fr[k] = flux_r(cfg, r[k], y[k]);
+            fy[k] = flux_y(cfg, r[k], y[k]);
+        }
+        const double r_nx = __shfl_down_sync(kFull, r[0], 1), y_nx = __shfl_down_sync(kFull, y[0], 1);
+        const double fr_nx = __shfl_down_sync(kFull, fr[0], 1), fy_nx = __shfl_down_sync(kFull, fy[0], 1);
+        // ---- midpoints j+1/2 (:202-215) and their fluxes ----
+        double ym[K], frm[K], fym[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool lastk = (k == K - 1);
+            const double rb = lastk ? r_nx : r[lastk ? 0 : k + 1], yb = lastk ? y_nx : y[lastk ? 0 : k + 1];
+            const double frb = lastk ? fr_nx : fr[lastk ? 0 : k + 1], fyb = lastk ? fy_nx : fy[lastk ? 0 : k + 1];
+            const double rmid = D::sub(D::mul(0.5, D::add(rb, r[k])), D::mul(cfg.c1, D::sub(frb, fr[k])));
+            const double ysum = D::add(yb, y[k]);
+            const double ymid = D::sub(D::sub(D::mul(0.5, ysum), D::mul(cfg.c1, D::sub(fyb, fy[k]))), D::mul(cfg.c2, ysum));
+            ym[k] = ymid;
+            frm[k] = flux_r(cfg, rmid, ymid);
+            fym[k] = flux_y(cfg, rmid, ymid);
+        }
+        const double ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1);
+        const double frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1);
+        const double fym_pv = __shfl_up_sync(kFull, fym[K - 1], 1);
+        // ---- interior update (:218-222) ----
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = j0 + k;
+            const double yl = (k == 0) ? ym_pv : ym[k > 0 ? k - 1 : 0];
+            const double frl = (k == 0) ? frm_pv : frm[k > 0 ? k - 1 : 0];
+            const double fyl = (k == 0) ? fym_pv : fym[k > 0 ? k - 1 : 0];
+            const double rnew = D::sub(r[k], D::mul(cfg.c3, D::sub(frm[k], frl)));
+            const double ynew = D::sub(y[k], D::add(D::mul(cfg.c3, D::sub(fym[k], fyl)), D::mul(cfg.c4, D::add(ym[k], yl))));
+            const bool interior = (j >= 1) && (j <= M - 2);
+            r[k] = interior ? rnew : r[k];
+            y[k] = interior ? ynew : y[k];
+        }
+    }
+
+    // ---- velocity, reward, flags, observation (:226-233) ----
+    double v[K];
+    double sv = 0.0, sr = 0.0;
+    bool over = false, steady = true;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const bool valid = j0 + k < M;
+        v[k] = valid ? D::add(D::div(y[k], r[k]), veq(cfg, r[k])) : 0.0;
+        const double dv = D::sub(v[k], vs), dr = D::sub(r[k], rs);
+        if (valid) {
+            sv += dv * dv;
+            sr += dr * dr;
+            over = over || (v[k] > cfg.vm) || (r[k] > cfg.rm);
+            steady = steady && (dv == 0.0) && (dr == 0.0);
+        }
+    }
+    sv = warp_sum(sv);
+    sr = warp_sum(sr);
+    const double reward = -D::add(D::div(sqrt(sv), vs), D::div(sqrt(sr), rs));       // traffic_arz_reward.py:22
+    over = __any_sync(kFull, over);
+    steady = __all_sync(kFull, steady);
+    bool term = time >= cfg.t_over_dt;                                                // :109-111
+    if (term) time = 0.0;
+    const bool trunc = (cfg.limit_pde_state_size && over) || steady;                  // :122-127
+    if (st != PDECG_ARZ_OUTLET_TRAIN) term = term || (reward > -0.00023);             // :233
+
+    store_row_chunk<double, K>(r, rrow, M, sm, lane);
+    store_row_chunk<double, K>(y, yrow, M, sm, lane);
+    double* orow = a.buf.obs + env * 2 * M;
+    if (st == PDECG_ARZ_OUTLET_TRAIN) {                                               // :231
+        double rn[K], vn[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            rn[k] = D::div(D::sub(r[k], rs), rs);
+            vn[k] = D::div(D::sub(v[k], vs), vs);
+        }
+        store_row_chunk<double, K>(rn, orow, M, sm, lane);
+        store_row_chunk<double, K>(vn, orow + M, M, sm, lane);
+    } else {
+        store_row_chunk<double, K>(r, orow, M, sm, lane);
+        store_row_chunk<double, K>(v, orow + M, M, sm, lane);
+    }
+    if (lane == 0) {
+        frow[PDECG_ARZ_F_TIME] = time;
+        a.buf.reward[env] = reward;
+        a.buf.terminated[env] = term ? 1 : 0;
+        a.buf.truncated[env] = trunc ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, const double* __restrict__ profile,
+                                                             const uint8_t* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (env >= a.buf.n_envs) return;
+    if (mask != nullptr && mask[env] == 0) return;
+    const pdecg_arz_cfg& cfg = a.cfg;
+    const int M = cfg.M;
+    const double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
+    const double rs = frow[PDECG_ARZ_F_RS], vs = frow[PDECG_ARZ_F_VS], qs = frow[PDECG_ARZ_F_QS];
+    double* rrow = a.buf.ry + env * 2 * M;
+    double* orow = a.buf.obs + env * 2 * M;
+    for (int j = lane; j < M; j += 32) {
+        // :259-261  r = rs*profile ; y = qs*1 - vm*r + (vm/rm)*r**2 ; v = y/r + Veq(r)
+        const double r = D::mul(rs, profile[j]);
+        const double y = D::add(D::sub(D::mul(qs, 1.0), D::mul(cfg.vm, r)), D::mul(cfg.vm_over_rm, D::mul(r, r)));
+        const double v = D::add(D::div(y, r), veq(cfg, r));
+        rrow[j] = r;
+        rrow[M + j] = y;
+        if (cfg.simulation_type == PDECG_ARZ_OUTLET_TRAIN && false) {
+            orow[j] = D::div(D::sub(r, rs), rs);
+            orow[M + j] = D::div(D::sub(v, vs), vs);
+        } else {                                   // reset() always returns concat(r, v)  (:263)
+            orow[j] = r;
+            orow[M + j] = v;
+        }
+    }
+    if (lane == 0) {
+        a.buf.reward[env] = 0.0;
+        a.buf.terminated[env] = 0;
+        a.buf.truncated[env] = 0;
+    }
+}
+
+static int arz_validate(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf) {
+    if (!cfg || !buf) return fail(PDECG_ERR_INVALID, "null cfg/buffers");
+    if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
+    if (cfg->simulation_type < PDECG_ARZ_INLET || cfg->simulation_type > PDECG_ARZ_OUTLET_TRAIN) return fail(PDECG_ERR_INVALID, "Invalid simulation type");
+    if (cfg->M < 4) return fail(PDECG_ERR_INVALID, "need at least 4 grid points");
+    if (cfg->M > 256) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", cfg->M);
+    if (cfg->control_freq < 1) return fail(PDECG_ERR_INVALID, "control_freq must be a positive integer (got %d)", cfg->control_freq);
+    if (cfg->action_dim != ((cfg->simulation_type == PDECG_ARZ_BOTH) ? 2 : 1)) return fail(PDECG_ERR_INVALID, "action_dim must be 2 for 'both', else 1");
+    if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
+    if (buf->n_envs > 0 && (!buf->ry || !buf->obs || !buf->fenv || !buf->reward || !buf->terminated || !buf->truncated))
+        return fail(PDECG_ERR_INVALID, "null device buffer");
+    return PDECG_OK;
+}
+
+}  // namespace pdecg
+
+using namespace pdecg;
+
+extern "C" int pdecg_arz_reset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* profile,
+                               const uint8_t* mask, pdecg_stream_t stream) {
+    int rc = arz_validate(cfg, buf);
+    if (rc != PDECG_OK) return rc;
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!profile) return fail(PDECG_ERR_INVALID, "null profile buffer");
+    ArzArgs a{*cfg, *buf};
+    const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    arz_reset_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, profile, mask);
+    count_launch();
+    return check_launch("arz_reset_kernel");
+}
+
+extern "C" int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, pdecg_stream_t stream) {
+    int rc = arz_validate(cfg, buf);
+    if (rc != PDECG_OK) return rc;
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
+    ArzArgs a{*cfg, *buf};
+    const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K = (cfg->M + 31) / 32;
+    switch (K) {
+#define PDECG_CASE(KK) case KK: arz_step_kernel<KK><<<grid, kThreads, 0, st>>>(a); break;
+        PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
+#undef PDECG_CASE
+        default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
+    }
+    count_launch();
+    return check_launch("arz_step_kernel");
+}

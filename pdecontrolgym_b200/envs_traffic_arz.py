@@ -1,0 +1,204 @@
+"""TrafficPDE1D (Aw-Rascle-Zhang traffic model) as a batched environment
+(traffic_arz_env.py:23-280 of the reference).  float64 throughout, like the reference.
+
+The reference's time bookkeeping is kept as is: `time_index` is a float time that
+advances by dt per *step*, the PDE integrates only while it is < T, `terminated` fires when it reaches
+T/dt (and zeroes it), so with the tutorial defaults an episode has 3,840 steps of which the first 959
+integrate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .rewards import TrafficARZReward
+from .spaces import Box
+
+_TYPES = {"inlet": 0, "outlet": 1, "both": 2, "outlet-train": 3}
+F_TIME, F_RS, F_VS, F_QS, NF64 = 0, 1, 2, 3, 4
+_RS_VALUES = (0.115, 0.12, 0.125)            # traffic_arz_env.py:66-68
+
+
+class TrafficPDE1D:
+    def __init__(self, simulation_type: str = "inlet", v_steady: float = 10, ro_steady: float = 0.12,
+                 v_max: float = 40, ro_max: float = 0.16, tau: float = 60,
+                 limit_pde_state_size: bool = False, control_freq: int = 1,
+                 *, T, dt, X, dx, reward_class=None, normalize=False,
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True):
+        if precision not in ("ref", "fp64"):
+            raise ValueError("TrafficPDE1D is float64 in the reference; precision must be 'ref' or 'fp64'")
+        if reward_class is not None and not isinstance(reward_class, TrafficARZReward):
+            raise TypeError("reward_class must be a pdecontrolgym_b200.TrafficARZReward (evaluated inside the kernel)")
+        assert isinstance(control_freq, int) and control_freq >= 1, \
+            f"control_freq must be a positive integer (got {control_freq} of type {type(control_freq).__name__})"
+        if simulation_type == "inlet-train":
+            raise NotImplementedError("'inlet-train' crashes at the first step in the reference (q_inlet is never set); unsupported")
+        if simulation_type not in _TYPES:
+            raise ValueError("Invalid simulation type")
+        self.num_envs = N = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("pdecontrolgym_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.T, self.dt, self.X, self.dx = T, dt, X, dx
+        self.nt = int(round(T / dt) + 1)
+        self.nx = int(round(X / dx))
+        self.simulation_type = simulation_type
+        self.vm, self.rm, self.tau = v_max, ro_max, tau
+        self.qm = v_max * ro_max / 4
+        self.limit_pde_state_size = limit_pde_state_size
+        self.control_freq = control_freq
+        self.copy_obs = copy_obs
+        self.reward_class = reward_class
+        if simulation_type != "outlet-train":
+            if v_steady != self.Veq(v_max, ro_max, ro_steady):
+                raise ValueError("The steady state velocity and density do not satisfy the equilibrium condition. Check the values of v_steady and ro_steady and ensure that they obey v_steady = v_max(1 - ro_steady/v_max).")
+            rs = np.full(N, float(ro_steady))
+            vs = np.full(N, float(v_steady))
+            qs = vs * rs                                                   # :63
+        else:
+            rs = np.array([_RS_VALUES[random.randint(0, 2)] for _ in range(N)], dtype=np.float64)
+            vs = self.Veq(self.vm, self.rm, rs)
+            qs = rs * vs                                                   # :70
+        x = np.arange(0, X + dx, dx)                                       # :74
+        self.L = X
+        self.M = len(x)
+        self._profile_np = (np.sin(3 * x / self.L * np.pi) * 0.1 + np.ones([1, self.M])).reshape(-1)   # :83
+        nact = 2 if simulation_type == "both" else 1
+        cfg = _lib.ArzCfg()
+        cfg.abi_version = _lib.ABI_VERSION
+        cfg.simulation_type = _TYPES[simulation_type]
+        cfg.M, cfg.control_freq = self.M, control_freq
+        cfg.limit_pde_state_size = int(bool(limit_pde_state_size))
+        cfg.action_dim = nact
+        cfg.T, cfg.dt = float(T), float(dt)
+        cfg.t_over_dt = T / dt                                             # :109
+        cfg.vm, cfg.rm = float(v_max), float(ro_max)
+        cfg.c1 = dt / (2 * dx)                                             # :202
+        cfg.c2 = 0.25 * dt / tau                                           # :208
+        cfg.c3 = dt / dx                                                   # :218
+        cfg.c4 = 0.5 * dt / tau                                            # :221
+        cfg.vm_over_rm = v_max / ro_max                                    # :84
+        self._cfg = cfg
+        self._L = _lib.lib()
+        dev = self.device
+        with torch.cuda.device(dev):
+            self._ry = torch.zeros((N, 2, self.M), dtype=torch.float64, device=dev)
+            self._obs = torch.zeros((N, 2 * self.M), dtype=torch.float64, device=dev)
+            self._fenv = torch.zeros((N, NF64), dtype=torch.float64, device=dev)
+            self._profile = torch.from_numpy(self._profile_np.copy()).to(dev)
+            self._reward = torch.zeros((N,), dtype=torch.float64, device=dev)
+            self._terminated = torch.zeros((N,), dtype=torch.uint8, device=dev)
+            self._truncated = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        buf = _lib.ArzBuffers()
+        buf.n_envs = N
+        buf.ry, buf.obs, buf.fenv = self._ry.data_ptr(), self._obs.data_ptr(), self._fenv.data_ptr()
+        buf.reward = self._reward.data_ptr()
+        buf.terminated, buf.truncated = self._terminated.data_ptr(), self._truncated.data_ptr()
+        self._buf = buf
+        self._set_steady(rs, vs, qs)
+        if simulation_type == "outlet-train":
+            self.single_observation_space = Box(low=-10, high=10, shape=(2 * self.M,), dtype=np.float64)
+        else:
+            self.single_observation_space = Box(low=0, high=40, shape=(2 * self.M,), dtype=np.float64)
+        self.observation_space = Box(low=self.single_observation_space.low[0], high=self.single_observation_space.high[0],
+                                     shape=(N, 2 * self.M), dtype=np.float64)
+        q0 = float(qs[0]) if N else float(v_steady * ro_steady)
+        self.single_action_space = Box(dtype=np.float64, low=q0 * 0.8, high=1.2 * q0, shape=(nact,))
+        self.action_space = Box(dtype=np.float64, low=q0 * 0.8, high=1.2 * q0, shape=(N, nact))
+        # the constructor already holds the initial condition; info['V'] is the INITIAL velocity, always (:87-88)
+        self._reset_kernel(None)
+        self.info = {"V": self._obs[:, self.M:].clone()}
+
+    @staticmethod
+    def Veq(vm, rm, rho):
+        return vm * (1 - rho / rm)                                         # :270-272
+
+    @staticmethod
+    def F_r(vm, rm, rho, y):
+        return y + rho * TrafficPDE1D.Veq(vm, rm, rho)
+
+    @staticmethod
+    def F_y(vm, rm, rho, y):
+        return y * (y / rho + TrafficPDE1D.Veq(vm, rm, rho))
+
+    def _set_steady(self, rs, vs, qs, mask=None):
+        vals = torch.from_numpy(np.stack([np.asarray(rs, np.float64), np.asarray(vs, np.float64), np.asarray(qs, np.float64)], axis=1)).to(self.device)
+        if mask is None:
+            self._fenv[:, F_RS:F_QS + 1] = vals
+        else:
+            self._fenv[mask, F_RS:F_QS + 1] = vals[mask]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _reset_kernel(self, mask_t):
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pdecg_arz_reset(C.byref(self._cfg), C.byref(self._buf), self._profile.data_ptr(),
+                                               None if mask_t is None else mask_t.data_ptr(), self._stream()))
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        """traffic_arz_env.py:237-267.  options["rs"]: per-env steady densities for 'outlet-train' (default:
+        a fresh draw from {0.115, 0.12, 0.125} per env with Python's `random`, like the reference);
+        options["mask"]: reset only those envs.  The float time is NOT reset here (reference quirk)."""
+        options = options or {}
+        mask = options.get("mask")
+        mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        if self.simulation_type == "outlet-train":
+            rs = options.get("rs")
+            if rs is None:
+                rs = np.array([_RS_VALUES[random.randint(0, 2)] for _ in range(self.num_envs)], dtype=np.float64)
+            rs = np.broadcast_to(np.asarray(rs, dtype=np.float64), (self.num_envs,)).copy()
+            vs = self.Veq(self.vm, self.rm, rs)
+            self._set_steady(rs, vs, rs * vs, None if mask_t is None else mask_t.bool())
+        self._reset_kernel(mask_t)
+        return (self._obs.clone() if self.copy_obs else self._obs), {}
+
+    def step(self, action):
+        """traffic_arz_env.py:131-233: clip the flow-rate action(s), `control_freq` Lax-Wendroff substeps,
+        reward, terminate / truncate -- one kernel launch for all envs."""
+        nact = self._cfg.action_dim
+        if isinstance(action, torch.Tensor):
+            a = action.to(self.device, torch.float64)
+        else:
+            a = torch.from_numpy(np.ascontiguousarray(np.asarray(action, dtype=np.float64))).to(self.device)
+        if a.numel() == nact and self.num_envs != 1:
+            a = a.reshape(1, nact).expand(self.num_envs, nact)
+        if a.numel() != self.num_envs * nact:
+            raise ValueError(f"action must have shape ({self.num_envs}, {nact})")
+        a = a.reshape(self.num_envs, nact).contiguous()
+        self._buf.action = a.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pdecg_arz_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
+        obs = self._obs.clone() if self.copy_obs else self._obs
+        return obs, self._reward.clone(), self._terminated.bool(), self._truncated.bool(), self.info
+
+    # reference attributes
+    r = property(lambda s: s._ry[:, 0, :])
+    y = property(lambda s: s._ry[:, 1, :])
+    rs = property(lambda s: s._fenv[:, F_RS])
+    vs = property(lambda s: s._fenv[:, F_VS])
+    qs = property(lambda s: s._fenv[:, F_QS])
+    time_index = property(lambda s: s._fenv[:, F_TIME])
+
+    @property
+    def v(self):
+        r, y = self.r, self.y
+        return y / r + self.vm * (1 - r / self.rm)
+
+    @property
+    def ps(self):
+        return self.vm / self.rm * self.qs / self.vs                      # :64
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close(self):
+        pass

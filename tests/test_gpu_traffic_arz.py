@@ -1,0 +1,88 @@
+"""CUDA parity: TrafficPDE1D kernel vs the numpy oracle.  States / observations BIT-IDENTICAL (no
+transcendental in the step), rewards (two L2 norms) to 1e-12 relative, flags exact.  The reference
+publishes no golden for this env; pin S1 below was produced by running the reference."""
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def run(cuda_device, st, cf, limit, steps=400, B=4, T=20, X=500, dx=10, dt=0.25, rs=None, seed=3):
+    import torch
+    import pdecontrolgym_b200 as pcg
+    kw = dict(T=T, dt=dt, X=X, dx=dx)
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, simulation_type=st, control_freq=cf,
+                   limit_pde_state_size=limit, reward_class=pcg.TrafficARZReward(), **kw)
+    orc = O.TrafficARZOracle(B, simulation_type=st, control_freq=cf, limit_pde_state_size=limit, **kw)
+    if st == "outlet-train":
+        o_g, _ = env.reset(options={"rs": rs})
+        o_r = orc.reset(rs=rs)
+    else:
+        o_g, _ = env.reset()
+        o_r = orc.reset()
+    assert np.array_equal(o_g.cpu().numpy(), o_r)
+    rng = np.random.default_rng(seed)
+    nact = 2 if st == "both" else 1
+    n_term = 0
+    for k in range(steps):
+        a = rng.uniform(0.7 * 1.2, 1.3 * 1.2, size=(B, nact))
+        o_r, r_r, te_r, tr_r = orc.step(a)
+        o_g, r_g, te_g, tr_g, info = env.step(torch.from_numpy(a))
+        assert np.array_equal(o_g.cpu().numpy(), o_r), f"step {k}: obs not bit-identical"
+        np.testing.assert_allclose(r_g.cpu().numpy(), r_r, rtol=1e-12, err_msg=f"step {k}")
+        assert np.array_equal(te_g.cpu().numpy(), te_r) and np.array_equal(tr_g.cpu().numpy(), tr_r), f"step {k}: flags"
+        assert np.array_equal(env.time_index.cpu().numpy(), orc.time_index)
+        n_term += int(te_r.any())
+    return n_term
+
+
+@pytest.mark.parametrize("st", ["inlet", "outlet", "both"])
+@pytest.mark.parametrize("cf", [1, 3])
+@pytest.mark.parametrize("limit", [False, True])
+def test_vs_oracle(cuda_device, st, cf, limit):
+    assert run(cuda_device, st, cf, limit) >= 1       # crosses the time-based termination + time reset
+
+
+def test_outlet_train(cuda_device):
+    run(cuda_device, "outlet-train", 2, False, rs=np.array([0.115, 0.12, 0.125, 0.12]))
+
+
+@pytest.mark.parametrize("X,dx", [(100, 10), (310, 10), (640, 10), (500, 4), (500, 2)])
+def test_grid_sizes(cuda_device, X, dx):
+    run(cuda_device, "both", 2, True, steps=60, B=3, X=X, dx=dx, dt=0.25 * dx / 10)
+
+
+def test_pin_s1_full_episode(cuda_device):
+    """SURVEY.md Appendix B pin S1: tutorial defaults, action == qs: 3,840 steps, first / last / sum reward."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=2, device=cuda_device, simulation_type="outlet",
+                   reward_class=pcg.TrafficARZReward(), T=240, dt=0.25, X=500, dx=10, copy_obs=False)
+    env.reset()
+    a = torch.full((2, 1), 1.2, dtype=torch.float64, device=cuda_device)
+    rewards, n = [], 0
+    while True:
+        _, r, te, tr, _ = env.step(a)
+        rewards.append(r)
+        n += 1
+        if n % 256 == 0 or n >= 3840:
+            if bool(te.any()) or bool(tr.any()) or n > 4000:
+                break
+    rew = torch.stack(rewards).cpu().numpy()
+    assert n == 3840
+    np.testing.assert_allclose(rew[0], -0.9956612448005211, rtol=1e-12)
+    np.testing.assert_allclose(rew[-1], -0.2512486635597482, rtol=1e-12)
+    np.testing.assert_allclose(rew.sum(axis=0), -1106.0954718055284, rtol=1e-11)
+
+
+def test_errors(cuda_device):
+    import pdecontrolgym_b200 as pcg
+    kw = dict(T=20, dt=0.25, X=500, dx=10, num_envs=1, device=cuda_device)
+    with pytest.raises(ValueError, match="Invalid simulation type"):
+        pcg.make("PDEControlGym-TrafficPDE1D", simulation_type="sideways", **kw)
+    with pytest.raises(ValueError, match="equilibrium"):
+        pcg.make("PDEControlGym-TrafficPDE1D", v_steady=11, **kw)
+    with pytest.raises(AssertionError, match="control_freq"):
+        pcg.make("PDEControlGym-TrafficPDE1D", control_freq=0, **kw)
