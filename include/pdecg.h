@@ -243,6 +243,54 @@ int pdecg_arz_reset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, cons
 int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Family 4: NavierStokes2D (Chorin projection, Jacobi pressure solve) + NSReward   -- all float64
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { PDECG_NS_DIRICHLET = 0, PDECG_NS_NEUMANN = 1, PDECG_NS_CONTROLLABLE = 2 } pdecg_ns_bc;
+/* side order = the order apply_boundary visits them (navier_stokes2D.py:76): lower (row 0),
+ * upper (row -1), left (col 0), right (col -1); per side [condition of u, condition of v]. */
+enum { PDECG_NS_LOWER = 0, PDECG_NS_UPPER = 1, PDECG_NS_LEFT = 2, PDECG_NS_RIGHT = 3 };
+
+typedef struct {
+    int32_t abi_version;
+    int32_t nx, ny;               /* int(round(X/dx + 1)), int(round(Y/dy + 1))   base_env_2d.py:28-29 */
+    int32_t nt;                   /* int(round(T/dt))                             base_env_2d.py:27    */
+    int32_t n_pressure_iters;     /* maximum_pressure_iteration                   navier_stokes2D.py:52 */
+    int32_t bc[4][2];             /* pdecg_ns_bc per side per component           :61-91                */
+    int32_t n_action_ref;         /* length of action_ref                                               */
+    int32_t n_uref;               /* number of time rows of U_ref                                       */
+    double dt, dx, dy;
+    double viscosity, density;
+    double gamma;                 /* NSReward(gamma)                              ns_reward.py:15       */
+} pdecg_ns_cfg;
+
+typedef struct {
+    int64_t n_envs;
+    double* u;               /* [n_envs, ny, nx]  x-velocity (row = y index, col = x index, as the reference) */
+    double* v;               /* [n_envs, ny, nx]                                                            */
+    double* p;               /* [n_envs, ny, nx]  pressure, warm start of the next solve (:115,129)          */
+    double* obs;             /* [n_envs, ny, nx, 2] = U[t]                                                  */
+    const double* action;    /* [n_envs]                                                                    */
+    const double* u_ref;     /* [n_uref, ny, nx, 2] shared reference trajectory                             */
+    const double* action_ref;/* [n_action_ref]                                                              */
+    int32_t* time_index;     /* [n_envs]                                                                    */
+    double* reward;          /* [n_envs]                                                                    */
+    uint8_t* terminated;     /* [n_envs]                                                                    */
+    uint8_t* truncated;      /* [n_envs] always 0 (:155)                                                    */
+    uint8_t* valid;          /* [n_envs] 0 where the reference would raise IndexError (step past nt-1)      */
+} pdecg_ns_buffers;
+
+/* NavierStokes2D.reset (:171-194): u, v, p <- init_* ([n_envs or 1, ny, nx]); time_index <- 0; obs <- U[0]. */
+int pdecg_ns_reset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* init_u,
+                   const double* init_v, const double* init_p, int64_t init_env_stride,
+                   const uint8_t* mask, pdecg_stream_t stream);
+/* NavierStokes2D.step (:118-157) incl. apply_boundary, solve_pressure, terminate and NSReward.reward. */
+int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, pdecg_stream_t stream);
+/* NavierStokes2D.solve_pressure (:94-116) alone, for callers such as examples/NavierStokes/NS2Doptimization.py:
+ * p <- n_pressure_iters Jacobi sweeps on rhs = density/dt * (d u/dx + d v/dy), warm-started from p. */
+int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v,
+                            double* p, pdecg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Misc
  * ------------------------------------------------------------------------------------------ */
 const char* pdecg_last_error(void);

@@ -16,6 +16,7 @@ from .rewards import (BaseReward, BrainTumorReward, NormReward, NSReward, Traffi
 from .envs_bc1d import ReactionDiffusionPDE1D, TransportPDE1D
 from .envs_brain_tumor import BrainTumor1D, TherapyWrapper
 from .envs_traffic_arz import TrafficPDE1D
+from .envs_navier_stokes import NavierStokes2D, central_difference, laplace
 
 __version__ = "0.1.0"
 
@@ -26,6 +27,7 @@ REGISTRY = {
     "PDEControlGym-ReactionDiffusionPDE1D": ReactionDiffusionPDE1D,
     "PDEControlGym-BrainTumor1D": BrainTumor1D,
     "PDEControlGym-TrafficPDE1D": TrafficPDE1D,
+    "PDEControlGym-NavierStokes2D": NavierStokes2D,
 }
 
 
@@ -38,5 +40,5 @@ def make(id: str, num_envs: int = 1, device="cuda", precision: str = "ref", **kw
 
 make_vec = make
 
-__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "BaseReward",
+__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "BaseReward",
            "NormReward", "TunedReward1D", "NSReward", "TrafficARZReward", "BrainTumorReward"]

@@ -81,6 +81,23 @@ class ArzBuffers(C.Structure):
     ]
 
 
+class NsCfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nt", C.c_int32),
+        ("n_pressure_iters", C.c_int32), ("bc", (C.c_int32 * 2) * 4), ("n_action_ref", C.c_int32),
+        ("n_uref", C.c_int32), ("dt", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
+        ("viscosity", C.c_double), ("density", C.c_double), ("gamma", C.c_double),
+    ]
+
+
+class NsBuffers(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("u", C.c_void_p), ("v", C.c_void_p), ("p", C.c_void_p), ("obs", C.c_void_p),
+        ("action", C.c_void_p), ("u_ref", C.c_void_p), ("action_ref", C.c_void_p), ("time_index", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("valid", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -118,6 +135,13 @@ def lib():
     L.pdecg_arz_reset.restype = C.c_int
     L.pdecg_arz_step.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p]
     L.pdecg_arz_step.restype = C.c_int
+    L.pdecg_ns_reset.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p]
+    L.pdecg_ns_reset.restype = C.c_int
+    L.pdecg_ns_step.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers), C.c_void_p]
+    L.pdecg_ns_step.restype = C.c_int
+    L.pdecg_ns_solve_pressure.argtypes = [C.POINTER(NsCfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdecg_ns_solve_pressure.restype = C.c_int
     L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double), C.c_void_p]
     L.pdecg_probe_fp_issue.restype = C.c_int

@@ -1,0 +1,333 @@
+// navier_stokes.cu -- NavierStokes2D step / reset / pressure-solve kernels + C ABI (sm_100a, float64).
+//
+// Reference behaviour restated here (no code shared): environments2d/navier_stokes2D.py:9-194,
+// base_env_2d.py:24-63 and rewards/ns_reward.py:18-28 of lukebhan/PDEControlGym.
+//
+// Generic kernel: one CTA = one env; u, v, u*, v*, p (ping-pong) live in shared memory for the whole
+// control step (predictor -> boundary conditions -> N Jacobi sweeps -> corrector -> boundary
+// conditions -> reward); HBM sees each field once in and once out.  No tensor cores: nothing here is
+// a dense contraction.
+//
+// Jacobi sweep identity used below (derived from navier_stokes2D.py:105-113, order of the four
+// Neumann copies included): after a sweep every boundary value equals the NEW value of the nearest
+// interior point (index clamped to [1, n-2] in both directions).  Each thread therefore evaluates the
+// Jacobi formula at the clamped index of its own point -- boundary points recompute their neighbour's
+// value (same inputs, same operation order => same bits) instead of waiting for a second barrier.
+#include "pdecg_internal.h"
+
+namespace pdecg {
+
+struct NsArgs {
+    pdecg_ns_cfg cfg;
+    pdecg_ns_buffers buf;
+    // solve-only entry point
+    const double* su;
+    const double* sv;
+    double* sp;
+    int solve_only;
+};
+
+using D = Strict<double>;
+constexpr int kNsThreads = 256;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// central_difference (:9-15) and laplace (:17-22) at an INTERIOR point of a smem field with row pitch nx
+__device__ __forceinline__ double cd_x(const double* f, int i, int j, int nx, double two_dx) {
+    return D::div(D::sub(f[i * nx + j + 1], f[i * nx + j - 1]), two_dx);
+}
+__device__ __forceinline__ double cd_y(const double* f, int i, int j, int nx, double two_dy) {
+    return D::div(D::sub(f[(i + 1) * nx + j], f[(i - 1) * nx + j]), two_dy);
+}
+__device__ __forceinline__ double lap5(const double* f, int i, int j, int nx, double dxdy) {
+    const double c = f[i * nx + j];
+    double s = D::add(f[i * nx + j - 1], f[(i - 1) * nx + j]);
+    s = D::sub(s, D::mul(4.0, c));
+    s = D::add(s, f[i * nx + j + 1]);
+    s = D::add(s, f[(i + 1) * nx + j]);
+    return D::div(s, dxdy);
+}
+
+// apply_boundary (:68-91): sides in the reference's order, u before v; a barrier between sides keeps the
+// corner values order-dependent exactly like the sequential numpy assignments.
+__device__ void apply_boundary(const pdecg_ns_cfg& cfg, double* fu, double* fv, double action, int tid, int nthreads) {
+    const int nx = cfg.nx, ny = cfg.ny;
+    for (int side = 0; side < 4; ++side) {
+        const int len = (side < 2) ? nx : ny;
+        for (int comp = 0; comp < 2; ++comp) {
+            double* f = comp == 0 ? fu : fv;
+            const int cond = cfg.bc[side][comp];
+            for (int q = tid; q < len; q += nthreads) {
+                int dst, src;
+                if (side == PDECG_NS_LOWER) { dst = q; src = nx + q; }
+                else if (side == PDECG_NS_UPPER) { dst = (ny - 1) * nx + q; src = (ny - 2) * nx + q; }
+                else if (side == PDECG_NS_LEFT) { dst = q * nx; src = q * nx + 1; }
+                else { dst = q * nx + nx - 1; src = q * nx + nx - 2; }
+                if (cond == PDECG_NS_NEUMANN) f[dst] = f[src];
+                else if (cond == PDECG_NS_DIRICHLET) f[dst] = 0.0;
+                else f[dst] = action;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// N Jacobi sweeps (:104-114) on smem ping-pong buffers pa (current) / pb; returns the buffer holding the result.
+// `b` = (dx*dy) * rhs, per point (only interior entries are read).
+__device__ double* jacobi(const pdecg_ns_cfg& cfg, double* pa, double* pb, const double* b, int tid, int nthreads) {
+    const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny;
+    // each thread owns up to 2 points (npt <= 2*nthreads is enforced on the host)
+    int idx[2], ci[2];
+    double bb[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int q = tid + s * nthreads;
+        idx[s] = q < npt ? q : -1;
+        const int i = clampi((q < npt ? q : 0) / nx, 1, ny - 2), j = clampi((q < npt ? q : 0) % nx, 1, nx - 2);
+        ci[s] = i * nx + j;
+        bb[s] = b[ci[s]];
+    }
+    for (int it = 0; it < cfg.n_pressure_iters; ++it) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (idx[s] >= 0) {
+                const int c = ci[s];
+                double acc = D::add(pa[c - 1], pa[c - nx]);     // ((left + up) + right) + down
+                acc = D::add(acc, pa[c + 1]);
+                acc = D::add(acc, pa[c + nx]);
+                pb[idx[s]] = D::mul(0.25, D::sub(acc, bb[s]));
+            }
+        }
+        __syncthreads();
+        double* t = pa; pa = pb; pb = t;
+    }
+    return pa;
+}
+
+__global__ void __launch_bounds__(kNsThreads) ns_step_kernel(const NsArgs a) {
+    extern __shared__ double smem[];
+    const pdecg_ns_cfg& cfg = a.cfg;
+    const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int64_t env = blockIdx.x;
+    double* su = smem;                 // u  -> u_next
+    double* sv = su + npt;             // v  -> v_next
+    double* sus = sv + npt;            // u* (predictor)
+    double* svs = sus + npt;           // v*
+    double* sp0 = svs + npt;           // pressure ping
+    double* sp1 = sp0 + npt;           // pressure pong
+    double* sb = sp1 + npt;            // (dx*dy) * rhs
+    __shared__ double red[kNsThreads / 32];
+
+    const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
+    const double dxdy = D::mul(cfg.dx, cfg.dy);
+
+    if (a.solve_only) {
+        const double* gu = a.su + env * npt;
+        const double* gv = a.sv + env * npt;
+        double* gp = a.sp + env * npt;
+        for (int q = tid; q < npt; q += nth) { sus[q] = gu[q]; svs[q] = gv[q]; sp0[q] = gp[q]; sb[q] = 0.0; }
+        __syncthreads();
+        const double rho_dt = D::div(cfg.density, cfg.dt);
+        for (int q = tid; q < npt; q += nth) {
+            const int i = q / nx, j = q % nx;
+            if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2)
+                sb[q] = D::mul(dxdy, D::mul(rho_dt, D::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
+        }
+        __syncthreads();
+        double* pf = jacobi(cfg, sp0, sp1, sb, tid, nth);
+        for (int q = tid; q < npt; q += nth) gp[q] = pf[q];
+        return;
+    }
+
+    const int t0 = a.buf.time_index[env];
+    if (t0 + 1 >= cfg.nt || t0 + 1 >= cfg.n_uref || t0 + 1 >= cfg.n_action_ref) {
+        // the reference raises IndexError here (U[time_index] / U_ref / action_ref out of range)
+        if (tid == 0) {
+            if (a.buf.valid) a.buf.valid[env] = 0;
+            a.buf.terminated[env] = 1;
+            a.buf.truncated[env] = 0;
+            a.buf.reward[env] = 0.0;
+        }
+        return;
+    }
+    double* gu = a.buf.u + env * npt;
+    double* gv = a.buf.v + env * npt;
+    double* gp = a.buf.p + env * npt;
+    const double action = a.buf.action[env];
+    for (int q = tid; q < npt; q += nth) { su[q] = gu[q]; sv[q] = gv[q]; sp0[q] = gp[q]; }
+    __syncthreads();
+
+    // ---- predictor (:130-138) ----
+    for (int q = tid; q < npt; q += nth) {
+        const int i = q / nx, j = q % nx;
+        double us = su[q], vs = sv[q];
+        if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2) {
+            const double u0 = su[q], v0 = sv[q];
+            // u + dt * (((-u)*dudx - v*dudy) + nu*lap(u))
+            double adv = D::sub(D::mul(-u0, cd_x(su, i, j, nx, two_dx)), D::mul(v0, cd_y(su, i, j, nx, two_dy)));
+            us = D::add(u0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap5(su, i, j, nx, dxdy)))));
+            adv = D::sub(D::mul(-u0, cd_x(sv, i, j, nx, two_dx)), D::mul(v0, cd_y(sv, i, j, nx, two_dy)));
+            vs = D::add(v0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap5(sv, i, j, nx, dxdy)))));
+        }
+        sus[q] = us;
+        svs[q] = vs;
+    }
+    __syncthreads();
+    apply_boundary(cfg, sus, svs, action, tid, nth);
+
+    // ---- pressure Poisson (:94-116) ----
+    const double rho_dt = D::div(cfg.density, cfg.dt);
+    for (int q = tid; q < npt; q += nth) {
+        const int i = q / nx, j = q % nx;
+        double bv = 0.0;
+        if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2)
+            bv = D::mul(dxdy, D::mul(rho_dt, D::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
+        sb[q] = bv;
+    }
+    __syncthreads();
+    double* pf = jacobi(cfg, sp0, sp1, sb, tid, nth);
+
+    // ---- corrector (:143-146) ----
+    const double dt_rho = D::div(cfg.dt, cfg.density);
+    for (int q = tid; q < npt; q += nth) {
+        const int i = q / nx, j = q % nx;
+        double un = sus[q], vn = svs[q];
+        if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2) {
+            un = D::sub(un, D::mul(dt_rho, cd_x(pf, i, j, nx, two_dx)));
+            vn = D::sub(vn, D::mul(dt_rho, cd_y(pf, i, j, nx, two_dy)));
+        }
+        su[q] = un;
+        sv[q] = vn;
+    }
+    __syncthreads();
+    apply_boundary(cfg, su, sv, action, tid, nth);
+
+    // ---- store, observation U[t], reward (:147-157, ns_reward.py:28) ----
+    const int t1 = t0 + 1;
+    const double* uref = a.buf.u_ref + static_cast<int64_t>(t1) * npt * 2;
+    double* gobs = a.buf.obs + env * npt * 2;
+    double ss = 0.0;
+    for (int q = tid; q < npt; q += nth) {
+        const double un = su[q], vn = sv[q];
+        gu[q] = un;
+        gv[q] = vn;
+        gp[q] = pf[q];
+        gobs[2 * q] = un;
+        gobs[2 * q + 1] = vn;
+        const double du = D::sub(un, uref[2 * q]), dv = D::sub(vn, uref[2 * q + 1]);
+        ss += du * du;
+        ss += dv * dv;
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (nth >> 5); ++w) tot += red[w];
+        const double nrm = sqrt(tot);
+        // -1/2 * norm**2 / shape[1] / shape[2] - gamma/2 * norm(a - a_ref[t])**2
+        double r1 = D::div(D::div(D::mul(-0.5, D::mul(nrm, nrm)), static_cast<double>(nx)), static_cast<double>(ny));   // / shape[1] / shape[2]
+        const double da = fabs(D::sub(action, a.buf.action_ref[t1]));
+        const double r2 = D::mul(D::div(cfg.gamma, 2.0), D::mul(da, da));
+        a.buf.reward[env] = D::sub(r1, r2);
+        a.buf.time_index[env] = t1;
+        a.buf.terminated[env] = (t1 >= cfg.nt - 1) ? 1 : 0;      // :159-168
+        a.buf.truncated[env] = 0;
+        if (a.buf.valid) a.buf.valid[env] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, const double* __restrict__ iu, const double* __restrict__ iv,
+                                                              const double* __restrict__ ip, int64_t stride, const uint8_t* __restrict__ mask) {
+    const int64_t env = blockIdx.x;
+    if (mask != nullptr && mask[env] == 0) return;
+    const int npt = a.cfg.nx * a.cfg.ny;
+    for (int q = threadIdx.x; q < npt; q += blockDim.x) {
+        const double un = iu[env * stride + q], vn = iv[env * stride + q];
+        a.buf.u[env * npt + q] = un;
+        a.buf.v[env * npt + q] = vn;
+        a.buf.p[env * npt + q] = ip[env * stride + q];
+        a.buf.obs[(env * npt + q) * 2] = un;
+        a.buf.obs[(env * npt + q) * 2 + 1] = vn;
+    }
+    if (threadIdx.x == 0) {
+        a.buf.time_index[env] = 0;
+        a.buf.reward[env] = 0.0;
+        a.buf.terminated[env] = 0;
+        a.buf.truncated[env] = 0;
+        if (a.buf.valid) a.buf.valid[env] = 1;
+    }
+}
+
+static int ns_validate_cfg(const pdecg_ns_cfg* cfg) {
+    if (!cfg) return fail(PDECG_ERR_INVALID, "null cfg");
+    if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
+    if (cfg->nx < 3 || cfg->ny < 3) return fail(PDECG_ERR_INVALID, "need nx, ny >= 3");
+    if (cfg->nx * cfg->ny > 2 * kNsThreads) return fail(PDECG_ERR_UNSUPPORTED, "grid %dx%d exceeds the shared-memory-resident limit of %d points per env", cfg->nx, cfg->ny, 2 * kNsThreads);
+    if (cfg->n_pressure_iters < 0) return fail(PDECG_ERR_INVALID, "maximum_pressure_iteration < 0");
+    if (!(cfg->dt > 0) || !(cfg->dx > 0) || !(cfg->dy > 0)) return fail(PDECG_ERR_INVALID, "dt, dx, dy must be positive");
+    for (int s = 0; s < 4; ++s)
+        for (int c = 0; c < 2; ++c)
+            if (cfg->bc[s][c] < PDECG_NS_DIRICHLET || cfg->bc[s][c] > PDECG_NS_CONTROLLABLE) return fail(PDECG_ERR_INVALID, "bad boundary condition code");
+    return PDECG_OK;
+}
+
+static size_t ns_smem_bytes(const pdecg_ns_cfg* cfg) { return static_cast<size_t>(7) * cfg->nx * cfg->ny * sizeof(double); }
+
+static int ns_prepare_launch(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(ns_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return PDECG_OK;
+}
+
+}  // namespace pdecg
+
+using namespace pdecg;
+
+extern "C" int pdecg_ns_reset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* init_u, const double* init_v,
+                              const double* init_p, int64_t init_env_stride, const uint8_t* mask, pdecg_stream_t stream) {
+    int rc = ns_validate_cfg(cfg);
+    if (rc != PDECG_OK) return rc;
+    if (!buf || buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "bad buffers");
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!init_u || !init_v || !init_p || !buf->u || !buf->v || !buf->p || !buf->obs || !buf->time_index || !buf->reward || !buf->terminated || !buf->truncated)
+        return fail(PDECG_ERR_INVALID, "null device buffer");
+    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0};
+    ns_reset_kernel<<<static_cast<unsigned>(buf->n_envs), kNsThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init_u, init_v, init_p, init_env_stride, mask);
+    count_launch();
+    return check_launch("ns_reset_kernel");
+}
+
+extern "C" int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, pdecg_stream_t stream) {
+    int rc = ns_validate_cfg(cfg);
+    if (rc != PDECG_OK) return rc;
+    if (!buf || buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "bad buffers");
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!buf->u || !buf->v || !buf->p || !buf->obs || !buf->action || !buf->u_ref || !buf->action_ref || !buf->time_index || !buf->reward || !buf->terminated || !buf->truncated)
+        return fail(PDECG_ERR_INVALID, "null device buffer");
+    const size_t smem = ns_smem_bytes(cfg);
+    if ((rc = ns_prepare_launch(smem)) != PDECG_OK) return rc;
+    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0};
+    ns_step_kernel<<<static_cast<unsigned>(buf->n_envs), kNsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    count_launch();
+    return check_launch("ns_step_kernel");
+}
+
+extern "C" int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v, double* p,
+                                       pdecg_stream_t stream) {
+    int rc = ns_validate_cfg(cfg);
+    if (rc != PDECG_OK) return rc;
+    if (n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
+    if (n_envs == 0) return PDECG_OK;
+    if (!u || !v || !p) return fail(PDECG_ERR_INVALID, "null device buffer");
+    const size_t smem = ns_smem_bytes(cfg);
+    if ((rc = ns_prepare_launch(smem)) != PDECG_OK) return rc;
+    NsArgs a{};
+    a.cfg = *cfg;
+    a.buf.n_envs = n_envs;
+    a.su = u; a.sv = v; a.sp = p; a.solve_only = 1;
+    ns_step_kernel<<<static_cast<unsigned>(n_envs), kNsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    count_launch();
+    return check_launch("ns_step_kernel(solve_pressure)");
+}
