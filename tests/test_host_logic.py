@@ -1,0 +1,62 @@
+"""CPU: host-side logic that needs no GPU -- registry ids, reward descriptors, constructor validation
+messages (same text as the reference), kernel-variant selection rules."""
+import math
+
+import numpy as np
+import pytest
+
+import pdecontrolgym_b200 as pcg
+
+
+def test_registry_has_the_five_reference_ids():
+    # pde_control_gym/__init__.py:4,8,12,13,17
+    assert sorted(pcg.REGISTRY) == sorted([
+        "PDEControlGym-TransportPDE1D", "PDEControlGym-ReactionDiffusionPDE1D", "PDEControlGym-BrainTumor1D",
+        "PDEControlGym-TrafficPDE1D", "PDEControlGym-NavierStokes2D"])
+    with pytest.raises(KeyError):
+        pcg.make("PDEControlGym-NeuronPDE1D")
+
+
+def test_reward_descriptors_mirror_reference_signatures():
+    r = pcg.TunedReward1D(50000, -1e3, 3e2)
+    assert (r.nt, r.truncate_penalty, r.terminate_reward) == (50000, -1e3, 3e2)
+    assert pcg.TunedReward1D(10).truncate_penalty == -1e-4 and pcg.TunedReward1D(10).terminate_reward == 1e2
+    with pytest.raises(Exception, match="Number of simulation steps"):
+        pcg.TunedReward1D(None)
+    with pytest.raises(Exception, match="Number of simulation steps"):
+        pcg.NormReward()
+    n = pcg.NormReward(100, "inf", "t-horizon", t_horizon_length=3)
+    assert n._ord == 3 and n._horizon == 2 and n.norm_coeff == 1.0
+    assert pcg.NormReward(100, norm=math.inf)._ord == 3 and pcg.NormReward(100, norm=1)._ord == 1
+    with pytest.raises(ValueError):
+        pcg.NormReward(100, norm="3")
+    with pytest.raises(ValueError):
+        pcg.NormReward(100, horizon="spatial")
+    assert pcg.NSReward().gamma == 0.1
+    assert issubclass(pcg.NormReward, pcg.BaseReward) and issubclass(pcg.BrainTumorReward, pcg.BaseReward)
+    with pytest.raises(NotImplementedError):
+        pcg.TunedReward1D(10).reward(None, 0, False, False, 0.0)
+
+
+def test_constructor_validation_precedes_device_use():
+    kw = dict(T=1, dt=1e-4, X=1, dx=1e-2, num_envs=1)
+    with pytest.raises(ValueError, match="precision"):
+        pcg.make("PDEControlGym-TransportPDE1D", precision="fp16", reward_class=pcg.TunedReward1D(10000), **kw)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        pcg.make("PDEControlGym-TransportPDE1D", device="cpu", reward_class=pcg.TunedReward1D(10000), **kw)
+    with pytest.raises(NotImplementedError, match="inlet-train"):
+        pcg.make("PDEControlGym-TrafficPDE1D", simulation_type="inlet-train", T=240, dt=0.25, X=500, dx=10)
+    with pytest.raises(ValueError, match="Invalid simulation type"):
+        pcg.make("PDEControlGym-TrafficPDE1D", simulation_type="x", T=240, dt=0.25, X=500, dx=10)
+    with pytest.raises(TypeError):
+        pcg.make("PDEControlGym-NavierStokes2D", T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05, reward_class=None)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        pcg.make("PDEControlGym-BrainTumor1D", T=600, dt=1, X=200, dx=1, device="cpu", total_dosage=61.2)
+
+
+def test_traffic_static_helpers_match_reference_formulas():
+    T = pcg.TrafficPDE1D
+    assert T.Veq(40, 0.16, 0.12) == 10.000000000000002 or T.Veq(40, 0.16, 0.12) == 40 * (1 - 0.12 / 0.16)
+    rho, y = np.array([0.1, 0.12]), np.array([0.3, -0.2])
+    assert np.array_equal(T.F_r(40, 0.16, rho, y), y + rho * (40 * (1 - rho / 0.16)))
+    assert np.array_equal(T.F_y(40, 0.16, rho, y), y * (y / rho + 40 * (1 - rho / 0.16)))

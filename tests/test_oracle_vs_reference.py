@@ -1,0 +1,141 @@
+"""CPU, build container only: the numpy oracle vs the LIVE unmodified reference (imported from
+/root/reference through oracle/ref_loader.py).  Everything is compared bit for bit, rewards included
+(the oracle calls the same numpy routines on the same rows).  Skipped where the reference tree is absent
+(e.g. on the GPU box); tests/test_oracle_goldens.py covers that case with committed reference runs."""
+import contextlib
+import io
+import itertools
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+from oracle.ref_loader import load_reference, make_shimmed_norm_reward, reference_available
+from tests.helpers import bc1d_case, make_ics
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+quiet = lambda: contextlib.redirect_stdout(io.StringIO())  # noqa: E731
+
+
+def _bc1d_pair(env, ct, sl, st, nz, bd, ad, rk, precision, limit=False, steps=12):
+    ref = load_reference()
+    kw, npts, beta, nt = bc1d_case(env, None, steps)
+    beta = beta.astype(bd)
+    nt_r = nt - 1
+    if rk == "tuned":
+        rr, orr = ref.TunedReward1D(nt_r, -1e3, 3e2), O.TunedReward1DSpec(nt_r, -1e3, 3e2)
+    else:
+        rr = make_shimmed_norm_reward(ref, nt=nt_r, norm=rk[1], horizon=rk[0])
+        orr = O.NormRewardSpec(nt_r, norm=rk[1], horizon=rk[0])
+    rng = np.random.default_rng(1)
+    ic = make_ics(rng, 1, npts)[0]
+    common = dict(normalize=nz, sensing_loc=sl, control_type=ct, sensing_type=st, limit_pde_state_size=limit,
+                  max_state_value=30.0, max_control_value=20, **kw)
+    Ref = ref.ReactionDiffusionPDE1D if env == "rd" else ref.TransportPDE1D
+    renv = Ref(reward_class=rr, sensing_noise_func=lambda s: s, reset_init_condition_func=lambda nx: ic,
+               reset_recirculation_func=lambda nx: beta, **common)
+    Orc = O.ReactionDiffusionOracle if env == "rd" else O.TransportOracle
+    oenv = Orc(1, reward=orr, precision=precision, **common)
+    o1, _ = renv.reset()
+    if precision == "fp64":       # the fp64 mode of SURVEY 8(c): same reference code, float64 state buffer
+        renv.u = np.zeros(renv.u.shape, dtype=np.float64)
+        renv.u[0] = ic
+        renv.beta = np.asarray(renv.beta, dtype=np.float64)
+        o1 = renv.sensing_update(renv.u[0], renv.dx, renv.sensing_noise_func)
+    o2 = oenv.reset(ic, beta)
+    assert np.array_equal(np.asarray(o1), np.asarray(o2).reshape(np.shape(o1)))
+    for k in range(steps):
+        a = np.array([rng.uniform(-1, 1) if nz else rng.uniform(-3, 3)], dtype=ad)
+        o1, r1, te1, tr1, _ = renv.step(a)
+        o2, r2, te2, tr2 = oenv.step(a)
+        o1 = np.asarray(o1)
+        o2 = np.asarray(o2).reshape(o1.shape)
+        assert o1.dtype == o2.dtype
+        assert np.array_equal(o1, o2, equal_nan=True), f"step {k}"
+        assert float(r1) == float(r2[0]) or (np.isnan(r1) and np.isnan(r2[0])), f"step {k}: reward {r1} vs {r2}"
+        assert (bool(te1), bool(tr1)) == (bool(te2[0]), bool(tr2[0]))
+
+
+SENSINGS = [("full", None), ("collocated", None), ("opposite", "Neumann"), ("opposite", "Dirchilet")]
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("precision", ["ref", "fp64"])
+def test_bc1d_all_variants(env, precision):
+    warnings.simplefilter("ignore")
+    for ct, (sl, st), nz, bd, ad in itertools.product(("Dirchilet", "Neumann"), SENSINGS, (False, True),
+                                                      (np.float32, np.float64), (np.float32, np.float64)):
+        if env == "rd" and st == "Dirchilet":
+            continue
+        _bc1d_pair(env, ct, sl, st, nz, bd, ad, "tuned", precision, steps=6)
+        _bc1d_pair(env, ct, sl, st, nz, bd, ad, ("temporal", 2), precision, steps=6)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("rk", ["tuned", ("temporal", 1), ("temporal", np.inf), ("differential", 2), ("t-horizon", 2)])
+def test_bc1d_rewards_full_episode(env, rk):
+    _bc1d_pair(env, "Dirchilet", "full", None, True, np.float32, np.float32, rk, "ref")
+    _bc1d_pair(env, "Dirchilet", "full", None, False, np.float64, np.float64, rk, "ref", limit=True)
+
+
+@pytest.mark.parametrize("st", ["inlet", "outlet", "both"])
+@pytest.mark.parametrize("cf", [1, 3])
+def test_traffic_arz(st, cf):
+    ref = load_reference()
+    kw = dict(T=20, dt=0.25, X=500, dx=10)
+    with quiet():
+        renv = ref.TrafficPDE1D(simulation_type=st, control_freq=cf, limit_pde_state_size=True, reward_class=ref.TrafficARZReward(), **kw)
+    oenv = O.TrafficARZOracle(1, simulation_type=st, control_freq=cf, limit_pde_state_size=True, **kw)
+    o1, _ = renv.reset()
+    assert np.array_equal(o1, oenv.reset()[0])
+    rng = np.random.default_rng(3)
+    for k in range(400):
+        a = rng.uniform(0.7 * 1.2, 1.3 * 1.2, size=2 if st == "both" else 1)
+        o1, r1, te1, tr1, _ = renv.step(a.copy())
+        o2, r2, te2, tr2 = oenv.step(a[None, :])
+        assert np.array_equal(o1, o2[0]) and r1 == r2[0] and (bool(te1), bool(tr1)) == (bool(te2[0]), bool(tr2[0])), f"step {k}"
+
+
+def test_brain_tumor_wrapper_schedules():
+    from tests.golden.gen_golden import BT_P, bt_ic
+    ref = load_reference()
+    rng = np.random.default_rng(0)
+    for props, weekends in (([], False), ([1 / 34] * 34, True), (list(rng.uniform(0, 0.3, 60)), True)):
+        renv = ref.BrainTumor1D(reward_class=ref.BrainTumorReward(), normalize=True, reset_init_condition_func=bt_ic, verbose=False, **BT_P)
+        rw = ref.TherapyWrapper(renv, weekends=weekends, verbose=False)
+        oenv = O.BrainTumorOracle(1, **BT_P)
+        ow = O.TherapyWrapperOracle(oenv, bt_ic(200, 201), weekends=weekends)
+        with quiet():
+            assert rw.benchmark() == ow.benchmark()
+            o1, _ = rw.reset()
+        assert np.array_equal(o1, ow.reset()[0])
+        te = tr = False
+        k = 0
+        while not (te or tr):
+            a = props[k] if k < len(props) else 0
+            k += 1
+            with quiet():
+                o1, r1, te, tr, _ = rw.step(a)
+            o2, r2, te2, tr2 = ow.step(a)
+            assert np.array_equal(o1, o2[0]) and float(r1) == float(r2[0]) and (bool(te), bool(tr)) == (bool(te2[0]), bool(tr2[0]))
+        assert renv.cDeathDay == oenv.cDeathDay[0] and rw.soft_constraint_violations == ow.soft_constraint_violations
+
+
+def test_navier_stokes():
+    ref = load_reference()
+    rng = np.random.default_rng(5)
+    uref = rng.uniform(-1, 1, (200, 21, 21, 2))
+    bc = {"upper": ["Controllable", "Neumann"], "lower": ["Neumann", "Dirchilet"], "left": ["Dirchilet", "Controllable"], "right": ["Neumann", "Neumann"]}
+    u0, v0, p0 = (rng.uniform(-1, 1, (21, 21)) for _ in range(3))
+    P = dict(T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05)
+    renv = ref.NavierStokes2D(reset_init_condition_func=lambda X: (u0.copy(), v0.copy(), p0.copy()), boundary_condition=bc, U_ref=uref,
+                              action_ref=2.0 * np.ones(1000), reward_class=ref.NSReward(0.1), action_dim=1, maximum_pressure_iteration=41, **P)
+    oenv = O.NavierStokesOracle(1, boundary_condition=bc, U_ref=uref, action_ref=2.0 * np.ones(1000), maximum_pressure_iteration=41, **P)
+    renv.reset()
+    oenv.reset(u0, v0, p0)
+    for k in range(8):
+        a = rng.uniform(2, 4)
+        o1, r1, te, tr, _ = renv.step(a)
+        o2, r2, te2, tr2 = oenv.step(np.array([a]))
+        assert np.array_equal(o1, o2[0]) and r1 == r2[0] and te == te2[0] and np.array_equal(renv.p, oenv.p[0])
