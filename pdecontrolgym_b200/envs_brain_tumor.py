@@ -134,6 +134,8 @@ class BrainTumor1D:
         `reset_init_condition_func(X, nx)` callback; options["mask"]: reset only those envs."""
         options = options or {}
         ic = options.get("init_condition")
+        if ic is None and self.reset_init_condition_func is None and self._ic is not None:
+            ic = self._ic                      # re-use the last explicit initial condition (e.g. benchmark())
         if ic is None:
             if self.reset_init_condition_func is None:
                 raise Exception("Please pass an initial condition function")

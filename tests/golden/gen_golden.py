@@ -19,7 +19,16 @@ warnings.simplefilter("ignore")
 from oracle.ref_loader import load_reference, make_shimmed_norm_reward  # noqa: E402
 from tests.helpers import bc1d_case, make_ics  # noqa: E402
 
-ref = load_reference()
+
+class _LazyRef:
+    """The reference is imported on first use so that test modules can import the case tables below on
+    machines without /root/reference (the GPU box)."""
+
+    def __getattr__(self, name):
+        return getattr(load_reference(), name)
+
+
+ref = _LazyRef()
 quiet = lambda: contextlib.redirect_stdout(io.StringIO())  # noqa: E731
 
 BC1D_CASES = [
