@@ -305,6 +305,11 @@ int64_t pdecg_launch_count(void);
 int pdecg_probe_fp_issue(int32_t dtype, int32_t blocks, int32_t threads, int32_t iters, float* ms,
                          double* total_ops, pdecg_stream_t stream);
 
+/* Self-test of the kernels' "division by a loop-invariant divisor" helper: out_fast[i] = helper(x[i], d),
+ * out_ref[i] = IEEE x[i] / d; the two must be bit-identical for every input (tests/test_gpu_constdiv.py). */
+int pdecg_selftest_constdiv(int32_t dtype, int64_t n, const void* x, double d, void* out_fast, void* out_ref,
+                            pdecg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,6 +142,8 @@ def lib():
     L.pdecg_ns_step.restype = C.c_int
     L.pdecg_ns_solve_pressure.argtypes = [C.POINTER(NsCfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_ns_solve_pressure.restype = C.c_int
+    L.pdecg_selftest_constdiv.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdecg_selftest_constdiv.restype = C.c_int
     L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double), C.c_void_p]
     L.pdecg_probe_fp_issue.restype = C.c_int

@@ -46,9 +46,31 @@ __global__ void __launch_bounds__(256) probe_fp_kernel(int iters, T* sink) {
     if (s == T(-1)) sink[0] = s;   // never true; keeps the chains alive
 }
 
+template <typename T>
+__global__ void constdiv_selftest_kernel(const T* __restrict__ x, T d, T* __restrict__ fast, T* __restrict__ ref, int64_t n) {
+    const ConstDiv<T> cd(d);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        fast[i] = cd(x[i]);
+        ref[i] = Strict<T>::div(x[i], d);
+    }
+}
+
 }  // namespace pdecg
 
 using namespace pdecg;
+
+extern "C" int pdecg_selftest_constdiv(int32_t dtype, int64_t n, const void* x, double d, void* out_fast, void* out_ref,
+                                       pdecg_stream_t stream) {
+    if (n < 0 || (n > 0 && (!x || !out_fast || !out_ref))) return fail(PDECG_ERR_INVALID, "bad arguments");
+    if (n == 0) return PDECG_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PDECG_F64)
+        constdiv_selftest_kernel<double><<<592, 256, 0, st>>>(static_cast<const double*>(x), d, static_cast<double*>(out_fast), static_cast<double*>(out_ref), n);
+    else
+        constdiv_selftest_kernel<float><<<592, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float>(d), static_cast<float*>(out_fast), static_cast<float*>(out_ref), n);
+    count_launch();
+    return check_launch("constdiv_selftest_kernel");
+}
 
 extern "C" const char* pdecg_last_error(void) { return g_err; }
 extern "C" int32_t pdecg_abi_version(void) { return PDECG_ABI_VERSION; }

@@ -55,19 +55,17 @@ __device__ __forceinline__ typename M::S rd_point(typename M::S pl, typename M::
 }
 
 // Transport, hyperbolic.py:146-155:
-//   n_j = p_j + dt*(((p_{j+1} - p_j)/dx) + (p_0 * beta_j))
+//   n_j = p_j + dt*(((p_{j+1} - p_j)/dx) + (p_0 * beta_j))        dq = (p_{j+1} - p_j)/dx, divided beforehand
 template <class M>
-__device__ __forceinline__ typename M::S tr_point(typename M::S p, typename M::S pr, typename M::S p0,
-                                                   typename M::S dx, typename M::C dt, typename M::C beta) {
+__device__ __forceinline__ typename M::S tr_point(typename M::S p, typename M::S dq, typename M::S p0,
+                                                   typename M::C dt, typename M::C beta) {
     using S = typename M::S;
     using C = typename M::C;
     if constexpr (M::kFast) {
-        S d = (pr - p) / dx;
-        return fmaf(dt, fmaf(p0, beta, d), p);
+        return fmaf(dt, fmaf(p0, beta, dq), p);
     } else {
-        S d = Strict<S>::div(Strict<S>::sub(pr, p), dx);                 // state dtype
         C e = Strict<C>::mul(static_cast<C>(p0), beta);                  // promoted to beta's dtype
-        C f = Strict<C>::add(static_cast<C>(d), e);
+        C f = Strict<C>::add(static_cast<C>(dq), e);
         C g = Strict<C>::mul(dt, f);
         return static_cast<S>(Strict<C>::add(static_cast<C>(p), g));
     }
@@ -129,10 +127,13 @@ struct Integrator {
     S fk[K];        // RD, kVarFast: F on interior points, 0 on frozen slots
     C dk[K];        // Transport, kVarFast: dt on updated points, 0 on frozen slots
     S g;            // value of the actuated point
+    ConstDiv<S> by_dx;
     S Fs, dxs;
     C dtc;
     int lane, j0, jb;
     double bsum_dyn;
+
+    __device__ __forceinline__ explicit Integrator(S dx) : by_dx(dx) {}
 
     __device__ __forceinline__ void substep(const Bc1dArgs& a, int64_t env, const S (&p)[K], S (&n)[K]) {
         if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
@@ -155,11 +156,29 @@ struct Integrator {
         } else {
             const S p0 = __shfl_sync(kFull, p[0], 0);
             const S hr = __shfl_down_sync(kFull, p[0], 1);
+            // (p_{j+1} - p_j) / dx for the whole chunk: 3-instruction exact tail per point, ONE range test
+            // per substep; operands outside the window (zero, denormal, inf, ...) redo the chunk exactly
+            S x[K], dq[K];
+            bool ok = true;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const S pr = (k == K - 1) ? hr : p[k < K - 1 ? k + 1 : K - 1];
-                n[k] = tr_point<M>(p[k], pr, p0, dxs, (VAR == kVarFast) ? dk[k] : dtc, coef[k]);
+                if constexpr (M::kFast) {
+                    dq[k] = (pr - p[k]) * by_dx.y;
+                } else {
+                    x[k] = Strict<S>::sub(pr, p[k]);
+                    dq[k] = by_dx.fast(x[k]);
+                    ok = ok & by_dx.in_range(x[k]);
+                }
             }
+            if constexpr (!M::kFast) {
+                if (!ok) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) dq[k] = by_dx.exact(x[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) n[k] = tr_point<M>(p[k], dq[k], p0, (VAR == kVarFast) ? dk[k] : dtc, coef[k]);
         }
         if constexpr (VAR != kVarFast) {
 #pragma unroll
@@ -206,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) bc1d_step_kernel(const Bc1dArgs a) {
     const int npts = a.npts;
     const int j0 = lane * K;
 
-    Integrator<ENV, M, K, VAR> I;
+    Integrator<ENV, M, K, VAR> I{static_cast<S>(cfg.dx)};
     I.lane = lane;
     I.j0 = j0;
     I.jb = npts - 1;                               // actuated point (x = X; ghost point for RD)
@@ -217,6 +236,12 @@ __global__ void __launch_bounds__(kThreads) bc1d_step_kernel(const Bc1dArgs a) {
 
     S* urow = static_cast<S*>(a.buf.u) + env * npts;
     load_row_chunk<S, S, K>(I.u, urow, npts, sm, lane);
+    if constexpr (ENV == PDECG_ENV_TRANSPORT) {
+        // padding slots (never stored, never read by valid points) hold a ramp instead of zeros so that the
+        // differences (u[j+1]-u[j]) formed there are ordinary numbers and stay on the division fast path
+#pragma unroll
+        for (int k = 0; k < K; ++k) I.u[k] = (j0 + k >= npts) ? static_cast<S>(j0 + k - npts + 1) : I.u[k];
+    }
 
     // per-slot coefficient: RD -> c_j = dt*beta_j (parabolic.py:144, left-assoc `dt*beta*u`);
     //                       Transport -> beta_j
