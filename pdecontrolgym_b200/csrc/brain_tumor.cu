@@ -38,11 +38,15 @@ __device__ __forceinline__ int rightmost_ge(const double (&c)[K], int j0, int nx
 
 // _update_fd (:221-245).  rin < 0 encodes "R is None"; treat_to = number of leading points with
 // xScale <= treatmentRadius (they receive R = rin, the others R = 1 - exp(-alpha*0) = 0).
+struct BtDivs {      // the two loop-invariant divisors of _update_fd (:236-237)
+    ConstDiv<double> by_dx2, by_k;
+    __device__ __forceinline__ explicit BtDivs(const pdecg_bt_cfg& cfg) : by_dx2(cfg.dx * cfg.dx), by_k(cfg.k) {}   // self.dx ** 2 (one rounded multiply)
+};
+
 template <int K>
-__device__ __forceinline__ void bt_fd(const pdecg_bt_cfg& cfg, const double (&c)[K], double (&n)[K], int lane, int j0,
+__device__ __forceinline__ void bt_fd(const pdecg_bt_cfg& cfg, const BtDivs& dv, const double (&c)[K], double (&n)[K], int lane, int j0,
                                        double D, double rho, bool has_r, double rin, int treat_to) {
     const int nx = cfg.nx;
-    const double dx2 = __dmul_rn(cfg.dx, cfg.dx);          // self.dx ** 2
     const double hl = __shfl_up_sync(kFull, c[K - 1], 1);
     const double hr = __shfl_down_sync(kFull, c[0], 1);
 #pragma unroll
@@ -51,10 +55,10 @@ __device__ __forceinline__ void bt_fd(const pdecg_bt_cfg& cfg, const double (&c)
         const double cr = (k == K - 1) ? hr : c[k < K - 1 ? k + 1 : K - 1];
         const double cc = c[k];
         // diffusion = D * (((u_r - 2.0*u_c) + u_l) / dx**2)
-        const double lap = __ddiv_rn(__dadd_rn(__dsub_rn(cr, __dmul_rn(2.0, cc)), cl), dx2);
+        const double lap = dv.by_dx2(__dadd_rn(__dsub_rn(cr, __dmul_rn(2.0, cc)), cl));
         const double diff = __dmul_rn(D, lap);
         // proliferation = (rho*u_c) * (1.0 - u_c/k)
-        const double om = __dsub_rn(1.0, __ddiv_rn(cc, cfg.k));
+        const double om = __dsub_rn(1.0, dv.by_k(cc));
         const double pro = __dmul_rn(__dmul_rn(rho, cc), om);
         double acc = __dadd_rn(diff, pro);
         if (has_r) {
@@ -94,7 +98,7 @@ __device__ __forceinline__ void bt_book(BtEnv& e) {
 
 // One call of BrainTumor1D.step (:123-218) for an env with t < nt-1.
 template <int K>
-__device__ __forceinline__ void bt_day(const BtArgs& a, BtEnv& e, double (&u)[K], int lane, int j0, double control,
+__device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, BtEnv& e, double (&u)[K], int lane, int j0, double control,
                                         double& reward, bool& term, bool& trunc) {
     const pdecg_bt_cfg& cfg = a.cfg;
     const int nx = cfg.nx;
@@ -118,9 +122,9 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, BtEnv& e, double (&u)[K]
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
         const double bed = __dadd_rn(applied, __ddiv_rn(__dmul_rn(applied, applied), cfg.alpha_beta_ratio));
         const double rin = __dsub_rn(1.0, exp(__dmul_rn(-cfg.alpha, bed)));
-        bt_fd<K>(cfg, u, n, lane, j0, e.D, e.rho, true, rin, cnt);
+        bt_fd<K>(cfg, dv, u, n, lane, j0, e.D, e.rho, true, rin, cnt);
     } else {
-        bt_fd<K>(cfg, u, n, lane, j0, e.D, e.rho, false, 0.0, 0);
+        bt_fd<K>(cfg, dv, u, n, lane, j0, e.D, e.rho, false, 0.0, 0);
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) u[k] = n[k];
@@ -207,13 +211,14 @@ __global__ void __launch_bounds__(kThreads) bt_run_kernel(const BtArgs a) {
     double u[K];
     load_row_chunk<double, double, K>(u, urow, nx, sm, lane);
 
+    const BtDivs dv(cfg);
     double reward = 0.0;
     bool term = false, trunc = false, valid = true, wrote_obs = false;
     const int last = cfg.nt - 1;
 
     if (a.mode == PDECG_BT_RAW_STEP) {
         if (e.t < last) {
-            bt_day<K>(a, e, u, lane, j0, a.buf.action[env], reward, term, trunc);
+            bt_day<K>(a, dv, e, u, lane, j0, a.buf.action[env], reward, term, trunc);
         } else {
             valid = false;                       // the reference returns None here (:135)
             term = true;
@@ -222,21 +227,21 @@ __global__ void __launch_bounds__(kThreads) bt_run_kernel(const BtArgs a) {
         // TherapyWrapper.reset (:408-427)
         e.consecutive = 0;
         while (e.stage == PDECG_BT_GROWTH && e.t < last) {
-            bt_day<K>(a, e, u, lane, j0, 0.0, reward, term, trunc);
+            bt_day<K>(a, dv, e, u, lane, j0, 0.0, reward, term, trunc);
             if (term || trunc) break;
         }
     } else if (a.mode == PDECG_BT_RUN_TO_END) {
         // TherapyWrapper.benchmark (:480-505): zero-dose episode, then t_benchmark <- simulationDays
-        while (!(term || trunc) && e.t < last) bt_day<K>(a, e, u, lane, j0, 0.0, reward, term, trunc);
+        while (!(term || trunc) && e.t < last) bt_day<K>(a, dv, e, u, lane, j0, 0.0, reward, term, trunc);
         e.t_benchmark = e.simulationDays;
     } else {
         // TherapyWrapper.step (:429-478)
         if (e.stage == PDECG_BT_POST) {
-            while (!(term || trunc) && e.t < last) bt_day<K>(a, e, u, lane, j0, 0.0, reward, term, trunc);
+            while (!(term || trunc) && e.t < last) bt_day<K>(a, dv, e, u, lane, j0, 0.0, reward, term, trunc);
             if (e.t >= last && !(term || trunc)) { valid = false; term = true; }
         } else if (e.t < last) {
             const double control = a.buf.action[env];
-            bt_day<K>(a, e, u, lane, j0, control, reward, term, trunc);
+            bt_day<K>(a, dv, e, u, lane, j0, control, reward, term, trunc);
             e.treatment_calls += 1;
             if (reward < 0.0) e.violations += 1;
             if (cfg.weekends) {
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) bt_run_kernel(const BtArgs a) {
                         if (e.t < last) {
                             double r2;
                             bool te2, tr2;
-                            bt_day<K>(a, e, u, lane, j0, 0.0, r2, te2, tr2);
+                            bt_day<K>(a, dv, e, u, lane, j0, 0.0, r2, te2, tr2);
                         }
                         if (term || trunc) break;
                     }

@@ -18,13 +18,18 @@ struct ArzArgs {
 
 using D = Strict<double>;
 
-__device__ __forceinline__ double veq(const pdecg_arz_cfg& c, double rho) {          // :271-272
-    return D::mul(c.vm, D::sub(1.0, D::div(rho, c.rm)));
+struct ArzCtx {      // vm and the hoisted exact division by the constant rm
+    double vm;
+    ConstDiv<double> by_rm;
+    __device__ __forceinline__ explicit ArzCtx(const pdecg_arz_cfg& c) : vm(c.vm), by_rm(c.rm) {}
+};
+__device__ __forceinline__ double veq(const ArzCtx& c, double rho) {          // :271-272
+    return D::mul(c.vm, D::sub(1.0, c.by_rm(rho)));
 }
-__device__ __forceinline__ double flux_r(const pdecg_arz_cfg& c, double rho, double y) {   // :275-276
+__device__ __forceinline__ double flux_r(const ArzCtx& c, double rho, double y) {   // :275-276
     return D::add(y, D::mul(rho, veq(c, rho)));
 }
-__device__ __forceinline__ double flux_y(const pdecg_arz_cfg& c, double rho, double y) {   // :279-280
+__device__ __forceinline__ double flux_y(const ArzCtx& c, double rho, double y) {   // :279-280
     return D::mul(y, D::add(D::div(y, rho), veq(c, rho)));
 }
 __device__ __forceinline__ double clipd(double v, double lo, double hi) {            // np.clip keeps NaN
@@ -43,6 +48,7 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
     const pdecg_arz_cfg& cfg = a.cfg;
     const int M = cfg.M;
     const int j0 = lane * K;
+    const ArzCtx ctx(cfg);
 
     double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
     const double fv = (lane < PDECG_ARZ_NF64) ? frow[lane] : 0.0;
@@ -79,11 +85,11 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
                 const double rp = (k > 0) ? r[k > 0 ? k - 1 : 0] : r_left;            // r[j-1]
                 if (j == 0) {
                     r[k] = rn;
-                    y[k] = D::sub(q_in, D::mul(r[k], veq(cfg, r[k])));
+                    y[k] = D::sub(q_in, D::mul(r[k], veq(ctx, r[k])));
                 }
                 if (j == M - 1) {
                     r[k] = rp;
-                    y[k] = D::sub(q_out, D::mul(r[k], veq(cfg, r[k])));
+                    y[k] = D::sub(q_out, D::mul(r[k], veq(ctx, r[k])));
                 }
             }
         }
@@ -91,8 +97,8 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
         double fr[K], fy[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            fr[k] = flux_r(cfg, r[k], y[k]);
-            fy[k] = flux_y(cfg, r[k], y[k]);
+            fr[k] = flux_r(ctx, r[k], y[k]);
+            fy[k] = flux_y(ctx, r[k], y[k]);
         }
         const double r_nx = __shfl_down_sync(kFull, r[0], 1), y_nx = __shfl_down_sync(kFull, y[0], 1);
         const double fr_nx = __shfl_down_sync(kFull, fr[0], 1), fy_nx = __shfl_down_sync(kFull, fy[0], 1);
@@ -107,8 +113,8 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
             const double ysum = D::add(yb, y[k]);
             const double ymid = D::sub(D::sub(D::mul(0.5, ysum), D::mul(cfg.c1, D::sub(fyb, fy[k]))), D::mul(cfg.c2, ysum));
             ym[k] = ymid;
-            frm[k] = flux_r(cfg, rmid, ymid);
-            fym[k] = flux_y(cfg, rmid, ymid);
+            frm[k] = flux_r(ctx, rmid, ymid);
+            fym[k] = flux_y(ctx, rmid, ymid);
         }
         const double ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1);
         const double frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1);
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const bool valid = j0 + k < M;
-        v[k] = valid ? D::add(D::div(y[k], r[k]), veq(cfg, r[k])) : 0.0;
+        v[k] = valid ? D::add(D::div(y[k], r[k]), veq(ctx, r[k])) : 0.0;
         const double dv = D::sub(v[k], vs), dr = D::sub(r[k], rs);
         if (valid) {
             sv += dv * dv;
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, co
     if (env >= a.buf.n_envs) return;
     if (mask != nullptr && mask[env] == 0) return;
     const pdecg_arz_cfg& cfg = a.cfg;
+    const ArzCtx ctx(cfg);
     const int M = cfg.M;
     const double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
     const double rs = frow[PDECG_ARZ_F_RS], vs = frow[PDECG_ARZ_F_VS], qs = frow[PDECG_ARZ_F_QS];
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, co
         // :259-261  r = rs*profile ; y = qs*1 - vm*r + (vm/rm)*r**2 ; v = y/r + Veq(r)
         const double r = D::mul(rs, profile[j]);
         const double y = D::add(D::sub(D::mul(qs, 1.0), D::mul(cfg.vm, r)), D::mul(cfg.vm_over_rm, D::mul(r, r)));
-        const double v = D::add(D::div(y, r), veq(cfg, r));
+        const double v = D::add(D::div(y, r), veq(ctx, r));
         rrow[j] = r;
         rrow[M + j] = y;
         if (cfg.simulation_type == PDECG_ARZ_OUTLET_TRAIN && false) {
