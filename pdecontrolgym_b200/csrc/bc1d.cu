@@ -37,7 +37,10 @@ __host__ __device__ inline int ring_len_for(int substeps) {
 // ---- per-point updates -----------------------------------------------------------------------
 // ReactionDiffusion, parabolic.py:143-144:
 //   n_j = (p_j + F*((p_{j-1} - 2 p_j) + p_{j+1})) + ((dt*beta_j) * p_j)          c = dt*beta_j (hoisted)
-template <class M>
+// FUSED2 (float64 only): (p_{j-1} - 2 p_j) as ONE fma(-2, p_j, p_{j-1}).  2*p_j is exact, so the fma rounds
+// the same exact value as sub(p_{j-1}, mul(2, p_j)) -- bit-identical -- unless 2*p_j overflows.  The kernel
+// enables it per env only when a rigorous growth bound keeps |u| < 2^1000 for the whole control step.
+template <class M, bool FUSED2 = false>
 __device__ __forceinline__ typename M::S rd_point(typename M::S pl, typename M::S p, typename M::S pr,
                                                    typename M::S F, typename M::C c) {
     using S = typename M::S;
@@ -45,6 +48,10 @@ __device__ __forceinline__ typename M::S rd_point(typename M::S pl, typename M::
     if constexpr (M::kFast) {
         S lap = (pl - S(2) * p) + pr;
         return fmaf(c, p, fmaf(F, lap, p));
+    } else if constexpr (FUSED2) {
+        S lap = Strict<S>::add(__fma_rn(S(-2), p, pl), pr);
+        S diff = Strict<S>::add(p, Strict<S>::mul(F, lap));
+        return Strict<S>::add(diff, Strict<S>::mul(c, p));
     } else {
         S lap = Strict<S>::add(Strict<S>::sub(pl, Strict<S>::mul(S(2), p)), pr);
         S diff = Strict<S>::add(p, Strict<S>::mul(F, lap));
@@ -135,6 +142,7 @@ struct Integrator {
 
     __device__ __forceinline__ explicit Integrator(S dx) : by_dx(dx) {}
 
+    template <bool FUSED2>
     __device__ __forceinline__ void substep(const Bc1dArgs& a, int64_t env, const S (&p)[K], S (&n)[K]) {
         if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
             if constexpr (VAR == kVarDyn) {
@@ -148,7 +156,7 @@ struct Integrator {
             for (int k = 0; k < K; ++k) {
                 const S pl = (k == 0) ? hl : p[k > 0 ? k - 1 : 0];
                 const S pr = (k == K - 1) ? hr : p[k < K - 1 ? k + 1 : K - 1];
-                n[k] = rd_point<M>(pl, p[k], pr, (VAR == kVarFast) ? fk[k] : Fs, coef[k]);
+                n[k] = rd_point<M, FUSED2>(pl, p[k], pr, (VAR == kVarFast) ? fk[k] : Fs, coef[k]);
             }
             if constexpr (VAR != kVarFast) {
                 if (lane == 0) n[0] = S(0);            // parabolic.py:146
@@ -187,18 +195,27 @@ struct Integrator {
     }
 
     // `cnt` substeps in place (register ping-pong: no copies in the steady state)
-    __device__ __forceinline__ void advance(const Bc1dArgs& a, int64_t env, int cnt) {
+    template <bool FUSED2>
+    __device__ __forceinline__ void advance_t(const Bc1dArgs& a, int64_t env, int cnt) {
         S v[K];
         int i = 0;
         for (; i + 2 <= cnt; i += 2) {
-            substep(a, env, u, v);
-            substep(a, env, v, u);
+            substep<FUSED2>(a, env, u, v);
+            substep<FUSED2>(a, env, v, u);
         }
         if (i < cnt) {
-            substep(a, env, u, v);
+            substep<FUSED2>(a, env, u, v);
 #pragma unroll
             for (int k = 0; k < K; ++k) u[k] = v[k];
         }
+    }
+    static constexpr bool kCanFuse = (ENV == PDECG_ENV_REACTION_DIFFUSION) && !M::kFast && (sizeof(S) == 8) && (sizeof(C) == 8);
+    bool fuse2;     // warp-uniform, set per env per control step (see rd_point)
+    __device__ __forceinline__ void advance(const Bc1dArgs& a, int64_t env, int cnt) {
+        if constexpr (kCanFuse) {
+            if (fuse2) { advance_t<true>(a, env, cnt); return; }
+        }
+        advance_t<false>(a, env, cnt);
     }
 
     // write the boundary values the reference assigns explicitly
@@ -280,6 +297,28 @@ __global__ void __launch_bounds__(kThreads) bc1d_step_kernel(const Bc1dArgs a) {
     double bsum = carry[0];
 
     I.g = actuate<S>(a, env, S(0));               // constant over the step unless kVarDyn
+    I.fuse2 = false;
+    if constexpr (Integrator<ENV, M, K, VAR>::kCanFuse) {
+        // |n_j| <= (1 + 4F + max|c|) * max(|p|, |g|): after nsub substeps |u| <= m * rho^nsub.  Require that to
+        // stay below 2^1000 so that 2*u_j can never overflow inside this control step.
+        if (VAR != kVarDyn) {
+            double m = fabs(static_cast<double>(I.g)), cm = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                m = fmax(m, fabs(static_cast<double>(I.u[k])));      // fmax drops NaN -> checked below
+                cm = fmax(cm, fabs(static_cast<double>(I.coef[k])));
+            }
+            bool finite = true;
+#pragma unroll
+            for (int k = 0; k < K; ++k) finite = finite & (fabs(static_cast<double>(I.u[k])) < 1.0e300);
+            m = warp_max(m);
+            cm = warp_max(cm);
+            finite = __all_sync(kFull, finite);
+            const double rho = 1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm;
+            const double lg = log2(fmax(m, 1.0)) + static_cast<double>(nsub) * log2(rho) * 1.0000001 + 1.0;
+            I.fuse2 = finite && (lg < 1000.0);
+        }
+    }
 
     // reward bookkeeping that needs mid-step rows (uniform over the warp)
     const bool tuned = cfg.reward_kind == PDECG_REWARD_TUNED1D;
