@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpdecg.so")
+LIB_PATH = os.environ.get("PDECG_LIB", os.path.join(_HERE, "lib", "libpdecg.so"))   # override: A/B testing of builds
 
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3

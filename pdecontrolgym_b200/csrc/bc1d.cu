@@ -29,6 +29,9 @@ struct Bc1dArgs {
 //   [0]            sum_t |u_t[-1]|              (tuned_reward_1d.py:37: np.sum(abs(uVec[:, -1])))
 //   [1 .. ring]    ring of step-end L2 norms    (tuned_reward_1d.py:40: norm(uVec[t-100]))
 constexpr int kLookback = 100;
+#ifndef PDECG_BC1D_MINBLOCKS
+#define PDECG_BC1D_MINBLOCKS 1
+#endif
 
 __host__ __device__ inline int ring_len_for(int substeps) {
     return (substeps >= 1 && substeps <= kLookback && kLookback % substeps == 0) ? kLookback / substeps : 1;
@@ -229,7 +232,7 @@ struct Integrator {
 };
 
 template <int ENV, class M, int K, int VAR>
-__global__ void __launch_bounds__(kThreads) bc1d_step_kernel(const Bc1dArgs a) {
+__global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const Bc1dArgs a) {
     using S = typename M::S;
     using C = typename M::C;
     __shared__ S sm_all[kWarpsPerBlock][32 * K];
@@ -632,6 +635,32 @@ extern "C" int pdecg_bc1d_reset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buff
     return check_launch("bc1d_reset_kernel");
 }
 
+// Host-buffer step, pipelined: the batch is cut into chunks that alternate between two library-owned
+// streams, so the D2H copy of chunk c overlaps the kernel of chunk c+1 (the observation copy-out is the
+// PCIe-bound part of an end-to-end step with full-state sensing).
+namespace {
+struct HostPipe {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
+    int device = -1;
+};
+thread_local HostPipe g_pipe;
+
+int ensure_pipe() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    if (g_pipe.device == dev) return PDECG_OK;
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&g_pipe.s[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        if ((e = cudaEventCreateWithFlags(&g_pipe.done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    }
+    if ((e = cudaEventCreateWithFlags(&g_pipe.start, cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    g_pipe.device = dev;
+    return PDECG_OK;
+}
+}  // namespace
+
 extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
                                     const void* action_host, void* obs_host, double* reward_host,
                                     uint8_t* terminated_host, uint8_t* truncated_host, pdecg_stream_t stream) {
@@ -640,23 +669,53 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
     if (rc != PDECG_OK) return rc;
     if (buf->n_envs == 0) return PDECG_OK;
     if (!action_host || !buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t n = static_cast<size_t>(buf->n_envs);
+    if ((rc = ensure_pipe()) != PDECG_OK) return rc;
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    const int64_t n = buf->n_envs;
     const size_t asz = cfg->action_dtype == PDECG_F32 ? 4 : 8;
     const size_t ssz = cfg->precision == PDECG_PREC_FP64 ? 8 : 4;
-    cudaError_t e = cudaMemcpyAsync(const_cast<void*>(buf->action), action_host, n * asz, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
-    rc = pdecg_bc1d_step(cfg, buf, stream);
-    if (rc != PDECG_OK) return rc;
-    if (obs_host) {
-        if (cfg->sensing_loc == PDECG_SENSE_FULL) e = cudaMemcpyAsync(obs_host, buf->u, n * a.npts * ssz, cudaMemcpyDeviceToHost, st);
-        else e = cudaMemcpyAsync(obs_host, buf->obs, n * ssz, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+    const size_t bsz = (cfg->precision == PDECG_PREC_REF) ? (cfg->beta_dtype == PDECG_F64 ? 8 : 4) : ssz;
+    const bool full = cfg->sensing_loc == PDECG_SENSE_FULL;
+    const size_t obs_row = full ? static_cast<size_t>(a.npts) * ssz : ssz;
+    // chunks of >= 4096 envs, at most 8 of them
+    int nchunk = static_cast<int>(n / 4096);
+    nchunk = nchunk < 1 ? 1 : (nchunk > 8 ? 8 : nchunk);
+    const int64_t per = ((n + nchunk - 1) / nchunk + 3) / 4 * 4;
+    cudaError_t e = cudaEventRecord(g_pipe.start, user);      // order after whatever the caller queued
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_pipe.s[i], g_pipe.start, 0);
+    auto off = [](const void* p, size_t bytes) { return p ? static_cast<const char*>(p) + bytes : nullptr; };
+    for (int c = 0; c * per < n; ++c) {
+        const int64_t lo = c * per, cnt = (lo + per <= n) ? per : n - lo;
+        cudaStream_t st = g_pipe.s[c & 1];
+        pdecg_bc1d_buffers b = *buf;
+        b.n_envs = cnt;
+        b.u = const_cast<char*>(off(buf->u, lo * a.npts * ssz));
+        b.beta = off(buf->beta, lo * buf->beta_env_stride * bsz);
+        b.action = off(buf->action, lo * asz);
+        b.obs = const_cast<char*>(off(buf->obs, lo * ssz));
+        b.reward = buf->reward + lo;
+        b.terminated = buf->terminated + lo;
+        b.truncated = buf->truncated + lo;
+        b.time_index = buf->time_index + lo;
+        b.carry = buf->carry + lo * a.carry_len;
+        if ((e = cudaMemcpyAsync(const_cast<void*>(b.action), off(action_host, lo * asz), cnt * asz, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
+        if ((rc = pdecg_bc1d_step(cfg, &b, st)) != PDECG_OK) return rc;
+        if (obs_host) {
+            const void* src = full ? static_cast<const void*>(b.u) : static_cast<const void*>(b.obs);
+            if ((e = cudaMemcpyAsync(static_cast<char*>(obs_host) + lo * obs_row, src, cnt * obs_row, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+                return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+        }
+        if (reward_host && (e = cudaMemcpyAsync(reward_host + lo, b.reward, cnt * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
+        if (terminated_host && (e = cudaMemcpyAsync(terminated_host + lo, b.terminated, cnt, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
+        if (truncated_host && (e = cudaMemcpyAsync(truncated_host + lo, b.truncated, cnt, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
     }
-    if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
-    if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
-    if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
-    e = cudaStreamSynchronize(st);
+    for (int i = 0; i < 2; ++i) {                              // the caller's stream continues after both pipes
+        cudaEventRecord(g_pipe.done[i], g_pipe.s[i]);
+        cudaStreamWaitEvent(user, g_pipe.done[i], 0);
+    }
+    e = cudaStreamSynchronize(user);
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
     return PDECG_OK;
 }

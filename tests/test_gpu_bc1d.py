@@ -151,3 +151,31 @@ def test_empty_batch_and_errors(cuda_device):
                    reward_class=pcg.NormReward(nt - 1), **kw2)
     with pytest.raises(PdecgError, match="register-resident"):
         big.reset(options={"init_condition": np.zeros(400), "beta": np.zeros(400)})
+
+
+@pytest.mark.parametrize("N", [3, 4099, 20001])
+def test_step_host_matches_device_step(cuda_device, N):
+    """pdecg_bc1d_step_host (H2D -> chunked, two-stream pipelined kernels -> D2H) == pdecg_bc1d_step."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    kw, npts, beta, nt = bc1d_case("rd", None, 3)
+    rng = np.random.default_rng(N)
+    ics = make_ics(rng, N, npts)
+    mk = lambda: pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=N, device=cuda_device, precision="fp64",  # noqa: E731
+                          reward_class=pcg.NormReward(nt - 1), normalize=True, **kw)
+    e1, e2 = mk(), mk()
+    for e in (e1, e2):
+        e.reset(options={"init_condition": ics, "beta": np.tile(beta, (N, 1)) * rng.uniform(0.9, 1.1)})
+    e2.beta.copy_(e1.beta)
+    obs_h = torch.empty(N, npts, dtype=torch.float64).pin_memory()
+    rew_h = torch.empty(N, dtype=torch.float64).pin_memory()
+    te_h = torch.empty(N, dtype=torch.uint8).pin_memory()
+    tr_h = torch.empty(N, dtype=torch.uint8).pin_memory()
+    for k in range(3):
+        a = rng.uniform(-1, 1, N).astype(np.float32)
+        o, r, te, tr, _ = e1.step(torch.from_numpy(a))
+        e2.step_host(torch.from_numpy(a).pin_memory(), obs_h, rew_h, te_h, tr_h)
+        assert np.array_equal(o.cpu().numpy(), obs_h.numpy())
+        assert np.array_equal(r.cpu().numpy(), rew_h.numpy())
+        assert np.array_equal(te.cpu().numpy(), te_h.numpy().astype(bool)) and np.array_equal(tr.cpu().numpy(), tr_h.numpy().astype(bool))
+    assert te_h.all()
