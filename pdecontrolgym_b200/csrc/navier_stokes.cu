@@ -13,6 +13,8 @@
 // interior point (index clamped to [1, n-2] in both directions).  Each thread therefore evaluates the
 // Jacobi formula at the clamped index of its own point -- boundary points recompute their neighbour's
 // value (same inputs, same operation order => same bits) instead of waiting for a second barrier.
+#include <cstdlib>
+
 #include "pdecg_internal.h"
 
 namespace pdecg {
@@ -260,6 +262,225 @@ __global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Specialised kernel for the reference grid (nx = ny = N+2): ONE WARP = ONE ENV, Jacobi in registers.
+//
+// The N x N interior is tiled over the lanes as an RG x CG grid of BR x BC blocks (N=19: 10 x 3 lanes,
+// 2 x 7 points each, 30 of 32 lanes).  By the sweep identity above, after the first sweep every boundary
+// value is a copy of the nearest interior value, so sweeps 2..n only need the interior with CLAMPED
+// neighbours: inside a block neighbours are registers, across blocks they come from 2(BR+BC) f64 shuffles
+// per sweep, and the clamps are selects with four lane-uniform predicates at compile-time slots.  No
+// barrier and no shared-memory traffic inside the 2000-sweep loop: 5 DADD/DMUL per point per sweep.
+// The first sweep reads the true boundary values of the warm-start pressure from shared memory, so an
+// arbitrary initial pressure field is handled exactly.
+template <int N, int BR, int BC, int RG, int CG>
+__global__ void __launch_bounds__(kThreads) ns_step_warp_kernel(const NsArgs a) {
+    static_assert(RG * CG <= 32 && RG * BR >= N && CG * BC >= N, "bad tiling");
+    constexpr int NX = N + 2, NPT = NX * NX;
+    extern __shared__ double smem[];
+    const pdecg_ns_cfg& cfg = a.cfg;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
+    if (env >= a.buf.n_envs) return;
+    double* f0 = smem + static_cast<size_t>(wib) * 4 * NPT;   // u   -> (dx*dy)*rhs
+    double* f1 = f0 + NPT;                                     // v   -> pressure
+    double* f2 = f1 + NPT;                                     // u*  -> u_next
+    double* f3 = f2 + NPT;                                     // v*  -> v_next
+
+    const int t0 = a.buf.time_index[env];
+    if (t0 + 1 >= cfg.nt || t0 + 1 >= cfg.n_uref || t0 + 1 >= cfg.n_action_ref) {
+        if (lane == 0) {
+            if (a.buf.valid) a.buf.valid[env] = 0;
+            a.buf.terminated[env] = 1;
+            a.buf.truncated[env] = 0;
+            a.buf.reward[env] = 0.0;
+        }
+        return;
+    }
+    const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
+    const double dxdy = D::mul(cfg.dx, cfg.dy);
+    const ConstDiv<double> by_2dx(two_dx), by_2dy(two_dy), by_dxdy(dxdy);
+    double* gu = a.buf.u + env * NPT;
+    double* gv = a.buf.v + env * NPT;
+    double* gp = a.buf.p + env * NPT;
+    const double action = a.buf.action[env];
+
+    for (int q = lane; q < NPT; q += 32) { f0[q] = gu[q]; f1[q] = gv[q]; }
+    __syncwarp();
+    auto interior = [](int q) { const int i = q / NX, j = q - i * NX; return i >= 1 && i <= N && j >= 1 && j <= N; };
+    auto cdx = [&](const double* f, int q) { return by_2dx(D::sub(f[q + 1], f[q - 1])); };
+    auto cdy = [&](const double* f, int q) { return by_2dy(D::sub(f[q + NX], f[q - NX])); };
+    auto lap = [&](const double* f, int q) {
+        double s = D::add(f[q - 1], f[q - NX]);
+        s = D::sub(s, D::mul(4.0, f[q]));
+        s = D::add(s, f[q + 1]);
+        s = D::add(s, f[q + NX]);
+        return by_dxdy(s);
+    };
+    // ---- predictor (:130-138) ----
+    for (int q = lane; q < NPT; q += 32) {
+        double us = f0[q], vs = f1[q];
+        if (interior(q)) {
+            const double u0 = us, v0 = vs;
+            double adv = D::sub(D::mul(-u0, cdx(f0, q)), D::mul(v0, cdy(f0, q)));
+            us = D::add(u0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap(f0, q)))));
+            adv = D::sub(D::mul(-u0, cdx(f1, q)), D::mul(v0, cdy(f1, q)));
+            vs = D::add(v0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap(f1, q)))));
+        }
+        f2[q] = us;
+        f3[q] = vs;
+    }
+    __syncwarp();
+    // apply_boundary (:68-91): sides in the reference's order, u before v
+    auto apply_bc = [&](double* fu, double* fv) {
+        for (int side = 0; side < 4; ++side) {
+            for (int comp = 0; comp < 2; ++comp) {
+                double* f = comp == 0 ? fu : fv;
+                const int cond = cfg.bc[side][comp];
+                if (lane < NX) {
+                    const int q = lane;
+                    int dst, src;
+                    if (side == PDECG_NS_LOWER) { dst = q; src = NX + q; }
+                    else if (side == PDECG_NS_UPPER) { dst = (NX - 1) * NX + q; src = (NX - 2) * NX + q; }
+                    else if (side == PDECG_NS_LEFT) { dst = q * NX; src = q * NX + 1; }
+                    else { dst = q * NX + NX - 1; src = q * NX + NX - 2; }
+                    if (cond == PDECG_NS_NEUMANN) f[dst] = f[src];
+                    else if (cond == PDECG_NS_DIRICHLET) f[dst] = 0.0;
+                    else f[dst] = action;
+                }
+            }
+            __syncwarp();
+        }
+    };
+    apply_bc(f2, f3);
+    // ---- (dx*dy)*rhs into f0, warm-start pressure into f1 ----
+    const double rho_dt = D::div(cfg.density, cfg.dt);
+    for (int q = lane; q < NPT; q += 32) {
+        f0[q] = interior(q) ? D::mul(dxdy, D::mul(rho_dt, D::add(cdx(f2, q), cdy(f3, q)))) : 0.0;
+        f1[q] = gp[q];
+    }
+    __syncwarp();
+
+    // ---- Jacobi sweeps (:104-114) on registers ----
+    const int rg = lane / CG, cg = lane - rg * CG;
+    const int i0 = rg * BR, j0 = cg * BC;                    // interior coordinates of this lane's block
+    if (cfg.n_pressure_iters >= 1) {
+        double p[BR][BC], b[BR][BC];
+#pragma unroll
+        for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < BC; ++cc) {
+                const int i = i0 + rr, j = j0 + cc;
+                const bool ok = (lane < RG * CG) && i < N && j < N;
+                const int q = ok ? (i + 1) * NX + (j + 1) : NX + 1;
+                b[rr][cc] = ok ? f0[q] : 0.0;
+                // sweep 1: true neighbours (incl. stored boundary values) from shared memory
+                double acc = D::add(f1[q - 1], f1[q - NX]);
+                acc = D::add(acc, f1[q + 1]);
+                acc = D::add(acc, f1[q + NX]);
+                p[rr][cc] = ok ? D::mul(0.25, D::sub(acc, b[rr][cc])) : 0.0;
+            }
+        constexpr int RLAST = (N - 1) / BR, RSLOT = (N - 1) % BR;     // block / slot holding interior row N-1
+        constexpr int CLAST = (N - 1) / BC, CSLOT = (N - 1) % BC;
+        const bool top = rg == 0, bottom = rg == RLAST, leftmost = cg == 0, rightmost = cg == CLAST;
+        for (int it = 1; it < cfg.n_pressure_iters; ++it) {
+            double up_h[BC], dn_h[BC], lf_h[BR], rt_h[BR];
+#pragma unroll
+            for (int cc = 0; cc < BC; ++cc) {
+                up_h[cc] = __shfl_up_sync(kFull, p[BR - 1][cc], CG);
+                dn_h[cc] = __shfl_down_sync(kFull, p[0][cc], CG);
+            }
+#pragma unroll
+            for (int rr = 0; rr < BR; ++rr) {
+                lf_h[rr] = __shfl_up_sync(kFull, p[rr][BC - 1], 1);
+                rt_h[rr] = __shfl_down_sync(kFull, p[rr][0], 1);
+            }
+            double n[BR][BC];
+#pragma unroll
+            for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+                for (int cc = 0; cc < BC; ++cc) {
+                    const double self = p[rr][cc];
+                    double up = (rr > 0) ? p[rr > 0 ? rr - 1 : 0][cc] : up_h[cc];
+                    if (rr == 0) up = top ? self : up;
+                    double dn = (rr < BR - 1) ? p[rr < BR - 1 ? rr + 1 : 0][cc] : dn_h[cc];
+                    if (rr == RSLOT) dn = bottom ? self : dn;
+                    double lf = (cc > 0) ? p[rr][cc > 0 ? cc - 1 : 0] : lf_h[rr];
+                    if (cc == 0) lf = leftmost ? self : lf;
+                    double rt = (cc < BC - 1) ? p[rr][cc < BC - 1 ? cc + 1 : 0] : rt_h[rr];
+                    if (cc == CSLOT) rt = rightmost ? self : rt;
+                    double acc = D::add(lf, up);             // ((left + up) + right) + down
+                    acc = D::add(acc, rt);
+                    acc = D::add(acc, dn);
+                    n[rr][cc] = D::mul(0.25, D::sub(acc, b[rr][cc]));
+                }
+#pragma unroll
+            for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+                for (int cc = 0; cc < BC; ++cc) p[rr][cc] = n[rr][cc];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < BC; ++cc) {
+                const int i = i0 + rr, j = j0 + cc;
+                if ((lane < RG * CG) && i < N && j < N) f1[(i + 1) * NX + (j + 1)] = p[rr][cc];
+            }
+        __syncwarp();
+        // boundary values = nearest interior value (the four Neumann copies of :110-113, in their order)
+        for (int q = lane; q < NPT; q += 32) {
+            if (!interior(q)) {
+                const int i = q / NX, j = q - i * NX;
+                f1[q] = f1[clampi(i, 1, N) * NX + clampi(j, 1, N)];
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- corrector (:143-146) ----
+    const double dt_rho = D::div(cfg.dt, cfg.density);
+    for (int q = lane; q < NPT; q += 32) {
+        if (interior(q)) {
+            f2[q] = D::sub(f2[q], D::mul(dt_rho, cdx(f1, q)));
+            f3[q] = D::sub(f3[q], D::mul(dt_rho, cdy(f1, q)));
+        }
+    }
+    __syncwarp();
+    apply_bc(f2, f3);
+
+    // ---- store, observation U[t], reward ----
+    const int t1 = t0 + 1;
+    const double* uref = a.buf.u_ref + static_cast<int64_t>(t1) * NPT * 2;
+    double* gobs = a.buf.obs + env * NPT * 2;
+    double ss = 0.0;
+    for (int q = lane; q < NPT; q += 32) {
+        const double un = f2[q], vn = f3[q];
+        gu[q] = un;
+        gv[q] = vn;
+        gp[q] = f1[q];
+        const double du = D::sub(un, uref[2 * q]), dv = D::sub(vn, uref[2 * q + 1]);
+        ss += du * du;
+        ss += dv * dv;
+    }
+    // interleaved (u, v) observation: coalesced 16-byte pairs
+    for (int q = lane; q < NPT; q += 32) {
+        reinterpret_cast<double2*>(gobs)[q] = make_double2(f2[q], f3[q]);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) {
+        const double nrm = sqrt(ss);
+        double r1 = D::div(D::div(D::mul(-0.5, D::mul(nrm, nrm)), static_cast<double>(NX)), static_cast<double>(NX));
+        const double da = fabs(D::sub(action, a.buf.action_ref[t1]));
+        const double r2 = D::mul(D::div(cfg.gamma, 2.0), D::mul(da, da));
+        a.buf.reward[env] = D::sub(r1, r2);
+        a.buf.time_index[env] = t1;
+        a.buf.terminated[env] = (t1 >= cfg.nt - 1) ? 1 : 0;
+        a.buf.truncated[env] = 0;
+        if (a.buf.valid) a.buf.valid[env] = 1;
+    }
+}
+
 static int ns_validate_cfg(const pdecg_ns_cfg* cfg) {
     if (!cfg) return fail(PDECG_ERR_INVALID, "null cfg");
     if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
@@ -306,9 +527,21 @@ extern "C" int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* bu
     if (buf->n_envs == 0) return PDECG_OK;
     if (!buf->u || !buf->v || !buf->p || !buf->obs || !buf->action || !buf->u_ref || !buf->action_ref || !buf->time_index || !buf->reward || !buf->terminated || !buf->truncated)
         return fail(PDECG_ERR_INVALID, "null device buffer");
+    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0};
+    if (cfg->nx == 21 && cfg->ny == 21 && !getenv("PDECG_NS_GENERIC")) {
+        // the reference grid (examples/NavierStokes/NS2Dppo.py:29-32): warp-per-env register kernel
+        constexpr int kN = 19;
+        const size_t smem_w = static_cast<size_t>(kWarpsPerBlock) * 4 * (kN + 2) * (kN + 2) * sizeof(double);
+        auto kern = ns_step_warp_kernel<kN, 2, 7, 10, 3>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_w));
+        if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        kern<<<grid, kThreads, smem_w, static_cast<cudaStream_t>(stream)>>>(a);
+        count_launch();
+        return check_launch("ns_step_warp_kernel");
+    }
     const size_t smem = ns_smem_bytes(cfg);
     if ((rc = ns_prepare_launch(smem)) != PDECG_OK) return rc;
-    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0};
     ns_step_kernel<<<static_cast<unsigned>(buf->n_envs), kNsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     count_launch();
     return check_launch("ns_step_kernel");
