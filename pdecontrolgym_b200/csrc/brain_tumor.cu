@@ -40,7 +40,11 @@ __device__ __forceinline__ int rightmost_ge(const double (&c)[K], int j0, int nx
 // xScale <= treatmentRadius (they receive R = rin, the others R = 1 - exp(-alpha*0) = 0).
 struct BtDivs {      // the two loop-invariant divisors of _update_fd (:236-237)
     ConstDiv<double> by_dx2, by_k;
-    __device__ __forceinline__ explicit BtDivs(const pdecg_bt_cfg& cfg) : by_dx2(cfg.dx * cfg.dx), by_k(cfg.k) {}   // self.dx ** 2 (one rounded multiply)
+    unsigned tiny_hi;   // high word of the largest power of two <= k*2^-60
+    __device__ __forceinline__ explicit BtDivs(const pdecg_bt_cfg& cfg) : by_dx2(cfg.dx * cfg.dx), by_k(cfg.k) {   // self.dx ** 2 (one rounded multiply)
+        const unsigned khi = static_cast<unsigned>(__double2hiint(cfg.k)) & 0x7ff00000u;    // 2^floor(log2 k)
+        tiny_hi = (khi > (61u << 20)) ? khi - (60u << 20) : 0u;
+    }
 };
 
 template <int K>
@@ -58,7 +62,11 @@ __device__ __forceinline__ void bt_fd(const pdecg_bt_cfg& cfg, const BtDivs& dv,
         const double lap = dv.by_dx2(__dadd_rn(__dsub_rn(cr, __dmul_rn(2.0, cc)), cl));
         const double diff = __dmul_rn(D, lap);
         // proliferation = (rho*u_c) * (1.0 - u_c/k)
-        const double om = __dsub_rn(1.0, dv.by_k(cc));
+        // (1.0 - u_c/k): for |u_c| < k*2^-60 the quotient is below 2^-60 and the difference rounds to exactly
+        // 1.0 whatever its low bits are -- skip the division there (the far field is full of denormals, which
+        // would otherwise take div.rn's slow path every day).
+        const unsigned cc_hi = static_cast<unsigned>(__double2hiint(cc)) & 0x7fffffffu;
+        const double om = (cc_hi < dv.tiny_hi) ? 1.0 : __dsub_rn(1.0, dv.by_k(cc));
         const double pro = __dmul_rn(__dmul_rn(rho, cc), om);
         double acc = __dadd_rn(diff, pro);
         if (has_r) {

@@ -62,6 +62,12 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
     double r[K], y[K];
     load_row_chunk<double, double, K>(r, rrow, M, sm, lane);
     load_row_chunk<double, double, K>(y, yrow, M, sm, lane);
+    // padding slots (never stored, never read by valid points) hold (rho, y) = (1, 1) so that the divisions
+    // evaluated there stay on the fast path instead of div.rn's slow 0/0 path
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (j0 + k >= M) { r[k] = 1.0; y[k] = 1.0; }
+    }
 
     // :148-170 -- float time advances once per step; actions clipped to the action space
     time = D::add(time, cfg.dt);
