@@ -119,6 +119,15 @@ int pdecg_bc1d_reset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, c
                      int32_t init_dtype, int64_t init_env_stride, const uint8_t* mask,
                      pdecg_stream_t stream);
 
+/* Randomised reset for RL rollouts: u[env] <- c_env * profile, c_env ~ U(lo, hi) -- the shape every example of
+ * the reference uses for its initial conditions (np.ones(nx) * np.random.uniform(1, 10),
+ * transport1Dppo.py:36-37, reactionDiffusion1Dppo.py:41-42).  c_env comes from Philox4x32-10 keyed by `seed`
+ * with counter (global env id = env_id_offset + env, episode[env]); episode[env] is incremented, so results
+ * do not depend on how the batch is sharded over GPUs.  `profile` is [1, npts] (dtype profile_dtype). */
+int pdecg_bc1d_reset_random(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* profile,
+                            int32_t profile_dtype, double lo, double hi, uint64_t seed, int64_t env_id_offset,
+                            int32_t* episode, const uint8_t* mask, pdecg_stream_t stream);
+
 /* Replaces TransportPDE1D.step / ReactionDiffusionPDE1D.step incl. terminate(), truncate(), the
  * sensing closure and reward_class.reward(...) (hyperbolic.py:126-194, parabolic.py:126-189,
  * tuned_reward_1d.py:25-40, norm_reward.py:29-73) for all n_envs in one launch. */

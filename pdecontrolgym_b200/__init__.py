@@ -13,7 +13,7 @@ instances whose state lives on the GPU and is advanced by hand-written sm_100a k
 """
 from .rewards import (BaseReward, BrainTumorReward, NormReward, NSReward, TrafficARZReward,
                       TunedReward1D)
-from .envs_bc1d import ReactionDiffusionPDE1D, TransportPDE1D
+from .envs_bc1d import ReactionDiffusionPDE1D, TransportPDE1D, UniformScaleIC
 from .envs_brain_tumor import BrainTumor1D, TherapyWrapper
 from .envs_traffic_arz import TrafficPDE1D
 from .envs_navier_stokes import NavierStokes2D, central_difference, laplace
@@ -41,5 +41,5 @@ def make(id: str, num_envs: int = 1, device="cuda", precision: str = "ref", **kw
 
 make_vec = make
 
-__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "EpisodeStats", "shard_range", "BaseReward",
+__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "EpisodeStats", "shard_range", "UniformScaleIC", "BaseReward",
            "NormReward", "TunedReward1D", "NSReward", "TrafficARZReward", "BrainTumorReward"]

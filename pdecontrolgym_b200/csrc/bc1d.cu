@@ -445,9 +445,18 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
 }
 
 // ---- reset -------------------------------------------------------------------------------------
+struct RandomIc {          // optional: u <- c * profile with c ~ U(lo, hi) from Philox (pdecg_bc1d_reset_random)
+    int enabled;
+    double lo, hi;
+    uint64_t seed;
+    int64_t env_id_offset;
+    int32_t* episode;
+};
+
 template <typename S, typename I>
 __global__ void __launch_bounds__(kThreads) bc1d_reset_kernel(const Bc1dArgs a, const I* __restrict__ init,
-                                                             int64_t init_stride, const uint8_t* __restrict__ mask) {
+                                                             int64_t init_stride, const uint8_t* __restrict__ mask,
+                                                             const RandomIc rnd) {
     const int lane = threadIdx.x & 31;
     const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
     if (env >= a.buf.n_envs) return;
@@ -455,19 +464,30 @@ __global__ void __launch_bounds__(kThreads) bc1d_reset_kernel(const Bc1dArgs a, 
     const int npts = a.npts;
     S* urow = static_cast<S*>(a.buf.u) + env * npts;
     const I* irow = init + env * init_stride;
+    double scale = 1.0;
+    if (rnd.enabled) {
+        const int ep = rnd.episode[env];
+        const double u01 = Philox4x32::uniform53(rnd.seed, static_cast<uint64_t>(rnd.env_id_offset + env), static_cast<uint32_t>(ep));
+        scale = __dadd_rn(rnd.lo, __dmul_rn(__dsub_rn(rnd.hi, rnd.lo), u01));
+        __syncwarp();
+        if (lane == 0) rnd.episode[env] = ep + 1;
+    }
+    auto ic = [&](int j) -> S {                        // `u[0] = init_condition` casts to the state dtype
+        return rnd.enabled ? static_cast<S>(__dmul_rn(scale, static_cast<double>(irow[j]))) : static_cast<S>(irow[j]);
+    };
     double ss = 0.0;
     S last = S(0), first = S(0), second = S(0), blast = S(0);
     for (int j = lane; j < npts; j += 32) {
-        S v = static_cast<S>(irow[j]);                 // `u[0] = init_condition` casts to the state dtype
+        S v = ic(j);
         urow[j] = v;
         double dv = static_cast<double>(v);
         ss += dv * dv;
     }
     ss = warp_sum(ss);
-    if (npts >= 1) last = static_cast<S>(irow[npts - 1]);
-    if (npts >= 2) blast = static_cast<S>(irow[npts - 2]);
-    first = static_cast<S>(irow[0]);
-    if (npts >= 2) second = static_cast<S>(irow[1]);
+    if (npts >= 1) last = ic(npts - 1);
+    if (npts >= 2) blast = ic(npts - 2);
+    first = ic(0);
+    if (npts >= 2) second = ic(1);
     if (lane == 0) {
         double* carry = a.buf.carry + env * a.carry_len;
         carry[0] = fabs(static_cast<double>(last));    // row 0 of uVec[:, -1]
@@ -612,9 +632,8 @@ extern "C" int pdecg_bc1d_step(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffe
                                             : launch_mode<PDECG_ENV_REACTION_DIFFUSION>(a, st);
 }
 
-extern "C" int pdecg_bc1d_reset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* init,
-                                int32_t init_dtype, int64_t init_env_stride, const uint8_t* mask,
-                                pdecg_stream_t stream) {
+static int reset_impl(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* init, int32_t init_dtype,
+                      int64_t init_env_stride, const uint8_t* mask, const RandomIc& rnd, pdecg_stream_t stream) {
     Bc1dArgs a;
     int rc = validate(cfg, buf, &a);
     if (rc != PDECG_OK) return rc;
@@ -625,14 +644,29 @@ extern "C" int pdecg_bc1d_reset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buff
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const bool s64 = cfg->precision == PDECG_PREC_FP64;
     if (s64) {
-        if (init_dtype == PDECG_F32) bc1d_reset_kernel<double, float><<<grid, kThreads, 0, st>>>(a, static_cast<const float*>(init), init_env_stride, mask);
-        else bc1d_reset_kernel<double, double><<<grid, kThreads, 0, st>>>(a, static_cast<const double*>(init), init_env_stride, mask);
+        if (init_dtype == PDECG_F32) bc1d_reset_kernel<double, float><<<grid, kThreads, 0, st>>>(a, static_cast<const float*>(init), init_env_stride, mask, rnd);
+        else bc1d_reset_kernel<double, double><<<grid, kThreads, 0, st>>>(a, static_cast<const double*>(init), init_env_stride, mask, rnd);
     } else {
-        if (init_dtype == PDECG_F32) bc1d_reset_kernel<float, float><<<grid, kThreads, 0, st>>>(a, static_cast<const float*>(init), init_env_stride, mask);
-        else bc1d_reset_kernel<float, double><<<grid, kThreads, 0, st>>>(a, static_cast<const double*>(init), init_env_stride, mask);
+        if (init_dtype == PDECG_F32) bc1d_reset_kernel<float, float><<<grid, kThreads, 0, st>>>(a, static_cast<const float*>(init), init_env_stride, mask, rnd);
+        else bc1d_reset_kernel<float, double><<<grid, kThreads, 0, st>>>(a, static_cast<const double*>(init), init_env_stride, mask, rnd);
     }
     count_launch();
     return check_launch("bc1d_reset_kernel");
+}
+
+extern "C" int pdecg_bc1d_reset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* init,
+                                int32_t init_dtype, int64_t init_env_stride, const uint8_t* mask,
+                                pdecg_stream_t stream) {
+    RandomIc rnd{};
+    return reset_impl(cfg, buf, init, init_dtype, init_env_stride, mask, rnd, stream);
+}
+
+extern "C" int pdecg_bc1d_reset_random(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* profile,
+                                       int32_t profile_dtype, double lo, double hi, uint64_t seed, int64_t env_id_offset,
+                                       int32_t* episode, const uint8_t* mask, pdecg_stream_t stream) {
+    if (!episode && buf && buf->n_envs > 0) return fail(PDECG_ERR_INVALID, "null episode counter buffer");
+    RandomIc rnd{1, lo, hi, seed, env_id_offset, episode};
+    return reset_impl(cfg, buf, profile, profile_dtype, 0, mask, rnd, stream);
 }
 
 // Host-buffer step, pipelined: the batch is cut into chunks that alternate between two library-owned

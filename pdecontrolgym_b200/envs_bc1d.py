@@ -28,8 +28,16 @@ _SENSE_LOC = {"full": 0, "collocated": 1, "opposite": 2}
 _SENSE_TYPE = {"Dirchilet": 0, "Neumann": 1}
 
 
-def _np_to_torch_dtype(dt):
-    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dt)]
+class UniformScaleIC:
+    """On-device random initial condition `u(x, 0) = c * profile(x)`, c ~ U(lo, hi) per env and per episode
+    -- the family every reference example draws from (`np.ones(nx) * np.random.uniform(1, 10)`,
+    transport1Dppo.py:36-37).  Pass it as `reset(seed=..., options={"init_condition": UniformScaleIC(1, 10)})`;
+    with `autoreset=True` every new episode gets a fresh draw.  c comes from Philox4x32-10 keyed by the seed
+    with counter (global env id, episode index), so a batch sharded over several GPUs reproduces the
+    single-GPU draws (`env_id_offset`)."""
+
+    def __init__(self, lo: float, hi: float, profile=None):
+        self.lo, self.hi, self.profile = float(lo), float(hi), profile
 
 
 class PDEVecEnv1D:
@@ -75,6 +83,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                  control_sample_rate: float = 0.1,
                  autoreset: bool = False,
                  copy_obs: bool = True,
+                 env_id_offset: int = 0,
                  **kwargs):
         super().__init__(**kwargs)
         self.sensing_noise_func = sensing_noise_func
@@ -87,6 +96,8 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         self.control_sample_rate = control_sample_rate
         self.autoreset = bool(autoreset)
         self.copy_obs = bool(copy_obs)   # False: full-state observations are zero-copy views of the live state
+        self.env_id_offset = int(env_id_offset)   # global index of env 0 (multi-GPU sharding)
+        self._seed, self._random_ic = 0, None
         # same messages as hyperbolic.py:60-62,87-89,122-124 / parabolic.py:85,114
         if sensing_loc not in _SENSE_LOC:
             raise Exception("Invalid sensing_loc parameter. Please use 'full', 'collocated', or 'opposite'. See documentation for details.")
@@ -147,6 +158,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             self.time_index = torch.zeros((N,), dtype=torch.int32, device=dev)
             self._carry = torch.zeros((N, carry_len), dtype=torch.float64, device=dev)
             self._done = torch.zeros((N,), dtype=torch.uint8, device=dev)
+            self._episode = torch.zeros((N,), dtype=torch.int32, device=dev)
         self.beta = None
         self._ic = None
         self._kernel_events = None
@@ -216,6 +228,14 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         options = options or {}
         ic = options.get("init_condition")
         beta = options.get("beta")
+        self._random_ic = None
+        if isinstance(ic, UniformScaleIC):
+            self._random_ic = ic
+            if seed is not None:
+                self._seed = int(seed)
+                if options.get("mask") is None:
+                    self._episode.zero_()
+            ic = np.ones(self.npts) if ic.profile is None else ic.profile
         if ic is None:
             ic = self._call_callback(self.reset_init_condition_func, "init_condition")
         if beta is None:
@@ -246,6 +266,15 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         return self._sense(), {}
 
     def _reset_kernel(self, mask_t):
+        if self._random_ic is not None:
+            r = self._random_ic
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pdecg_bc1d_reset_random(
+                    C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
+                    _lib.F64 if self._ic.dtype == torch.float64 else _lib.F32, r.lo, r.hi,
+                    self._seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset, self._episode.data_ptr(),
+                    None if mask_t is None else mask_t.data_ptr(), self._stream()))
+            return
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_bc1d_reset(
                 C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),

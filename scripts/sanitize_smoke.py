@@ -1,0 +1,51 @@
+"""Small-batch pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool memcheck python scripts/sanitize_smoke.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import pdecontrolgym_b200 as pcg
+
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(0)
+for eid, npts, kw, rew in (
+        ("PDEControlGym-TransportPDE1D", 100, dict(T=0.3, dt=1e-4, X=1, dx=1e-2, control_sample_rate=0.05), pcg.TunedReward1D(3000)),
+        ("PDEControlGym-ReactionDiffusionPDE1D", 201, dict(T=0.003, dt=1e-5, X=1, dx=5e-3, control_sample_rate=1e-3), pcg.NormReward(300, "inf", "t-horizon"))):
+    for prec in ("ref", "fp64", "fp32"):
+        for ct, sl in (("Dirchilet", "full"), ("Neumann", "collocated")):
+            env = pcg.make(eid, num_envs=7, device=dev, precision=prec, reward_class=rew, control_type=ct, sensing_loc=sl, autoreset=True, **kw)
+            env.reset(options={"init_condition": rng.uniform(1, 2, (7, npts)), "beta": rng.uniform(-1, 1, npts)})
+            for _ in range(4):
+                env.step(rng.uniform(-1, 1, 7).astype(np.float32))
+env = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=9001, device=dev, precision="fp64", reward_class=pcg.NormReward(300),
+               T=0.003, dt=1e-5, X=1, dx=5e-3, control_sample_rate=1e-3)
+env.reset(options={"init_condition": np.ones(201), "beta": np.zeros(201)})
+a = torch.zeros(9001).pin_memory()
+o = torch.empty(9001, 201, dtype=torch.float64).pin_memory()
+env.step_host(a, o, torch.empty(9001, dtype=torch.float64).pin_memory(), torch.empty(9001, dtype=torch.uint8).pin_memory(), torch.empty(9001, dtype=torch.uint8).pin_memory())
+env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=5, device=dev, simulation_type="both", control_freq=2, T=5, dt=0.25, X=500, dx=10)
+env.reset()
+for _ in range(25):
+    env.step(rng.uniform(1.0, 1.4, (5, 2)))
+xs = np.linspace(0, 200, 201)
+bt = pcg.make("PDEControlGym-BrainTumor1D", num_envs=5, device=dev, total_dosage=61.2, T=600, dt=1, X=200, dx=1)
+bt.reset(options={"init_condition": 0.8e5 * np.exp(-0.25 * xs ** 2)})
+w = pcg.TherapyWrapper(bt, weekends=True)
+w.benchmark()
+w.reset()
+for _ in range(40):
+    w.step(rng.uniform(0, 0.1, 5))
+bc = {"upper": ["Controllable", "Neumann"], "lower": ["Neumann", "Dirchilet"], "left": ["Dirchilet", "Controllable"], "right": ["Neumann", "Neumann"]}
+for n in (21, 12):
+    h = 1.0 / (n - 1)
+    ns = pcg.make("PDEControlGym-NavierStokes2D", num_envs=5, device=dev, boundary_condition=bc, U_ref=np.zeros((50, n, n, 2)), action_ref=np.ones(100),
+                  reward_class=pcg.NSReward(), action_dim=1, maximum_pressure_iteration=20, T=0.02, dt=1e-3 * (h / 0.05) ** 2, X=1, dx=h, Y=1, dy=h)
+    ns.reset(options={"init": tuple(rng.uniform(-1, 1, (5, n, n)) for _ in range(3))})
+    for _ in range(3):
+        ns.step(rng.uniform(2, 4, 5))
+    ns.solve_pressure(rng.uniform(-1, 1, (5, n, n)), rng.uniform(-1, 1, (5, n, n)), np.zeros((n, n)))
+torch.cuda.synchronize()
+print("sanitize_smoke: done")
