@@ -355,6 +355,12 @@ def run_ours(args):
     # algorithmic HBM bytes per launch: state row in + out, action, reward, 2 flags, time_index r/w, carry r/w (2 doubles)
     bytes_per_env = 2 * NX_PTS * 8 + 4 + 8 + 2 + 8 + 2 * 2 * 8
     bytes_per_launch = E * bytes_per_env + NX_PTS * 8
+    traffic = None                # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_rd_traffic.json")) as f:
+            traffic = float(json.load(f)["dram_bytes_per_launch"]) if E == 65536 else None
+    except Exception:  # noqa: BLE001
+        pass
     achieved_tflops = flops_per_launch / (k_ms * 1e-3) / 1e12
     achieved_gbs = bytes_per_launch / (k_ms * 1e-3) / 1e9
 
@@ -380,7 +386,8 @@ def run_ours(args):
                    "l2": "no flush: state (105 MB) + observation copy (105 MB) written every step exceed the 126 MB L2",
                    "autoreset": True},
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / fp64_peak_tflops, "traffic": None,
+                     "frac": achieved_tflops / fp64_peak_tflops, "traffic": traffic,
+                     "traffic_source": "profiles/r1_rd_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full launch)",
                      "kernel": "bc1d_step_kernel<RD, fp64, K=7>", "kernel_ms": k_ms,
                      "kernel_share_of_step": k_ms * K / ms_total,
                      "flops_per_launch": flops_per_launch,

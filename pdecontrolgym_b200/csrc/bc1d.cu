@@ -1,448 +1,11 @@
-// bc1d.cu -- TransportPDE1D and ReactionDiffusionPDE1D: step / reset kernels + C ABI (sm_100a).
+// bc1d.cu -- TransportPDE1D and ReactionDiffusionPDE1D: reset kernel, validation, dispatch and C ABI (sm_100a).
 //
 // Reference behaviour restated here (no code shared): hyperbolic.py:126-227, parabolic.py:126-221,
 // base_env_1d.py:20-45, tuned_reward_1d.py:25-40, norm_reward.py:29-73 of lukebhan/PDEControlGym.
-//
-// One warp integrates one env.  All `substeps` explicit finite-difference updates of a control step
-// run on registers; actuation (Dirichlet / Neumann, optional normalisation), sensing, the reward
-// (TunedReward1D / NormReward) and terminate / truncate are fused into the same launch, so HBM
-// carries one state row in and out (+ a few scalars) per env per control step.
-#include "pdecg_internal.h"
+// The step kernel templates live in bc1d_kernels.cuh.
+#include "bc1d_kernels.cuh"
 
 namespace pdecg {
-
-// precision / arithmetic variants ---------------------------------------------------------------
-struct ModeRefB32 { using S = float;  using C = float;  static constexpr bool kFast = false; };  // f32 state, beta f32
-struct ModeRefB64 { using S = float;  using C = double; static constexpr bool kFast = false; };  // f32 state, beta f64
-struct ModeFp64   { using S = double; using C = double; static constexpr bool kFast = false; };
-struct ModeFp32   { using S = float;  using C = float;  static constexpr bool kFast = true;  };
-
-struct Bc1dArgs {
-    pdecg_bc1d_cfg cfg;
-    pdecg_bc1d_buffers buf;
-    int npts;
-    int carry_len;
-    int ring_len;   // TunedReward1D look-back ring (entries) -- see carry layout below
-};
-
-// carry layout (doubles, per env):
-//   [0]            sum_t |u_t[-1]|              (tuned_reward_1d.py:37: np.sum(abs(uVec[:, -1])))
-//   [1 .. ring]    ring of step-end L2 norms    (tuned_reward_1d.py:40: norm(uVec[t-100]))
-constexpr int kLookback = 100;
-#ifndef PDECG_BC1D_MINBLOCKS
-#define PDECG_BC1D_MINBLOCKS 1
-#endif
-
-__host__ __device__ inline int ring_len_for(int substeps) {
-    return (substeps >= 1 && substeps <= kLookback && kLookback % substeps == 0) ? kLookback / substeps : 1;
-}
-
-// ---- per-point updates -----------------------------------------------------------------------
-// ReactionDiffusion, parabolic.py:143-144:
-//   n_j = (p_j + F*((p_{j-1} - 2 p_j) + p_{j+1})) + ((dt*beta_j) * p_j)          c = dt*beta_j (hoisted)
-// FUSED2 (float64 only): (p_{j-1} - 2 p_j) as ONE fma(-2, p_j, p_{j-1}).  2*p_j is exact, so the fma rounds
-// the same exact value as sub(p_{j-1}, mul(2, p_j)) -- bit-identical -- unless 2*p_j overflows.  The kernel
-// enables it per env only when a rigorous growth bound keeps |u| < 2^1000 for the whole control step.
-template <class M, bool FUSED2 = false>
-__device__ __forceinline__ typename M::S rd_point(typename M::S pl, typename M::S p, typename M::S pr,
-                                                   typename M::S F, typename M::C c) {
-    using S = typename M::S;
-    using C = typename M::C;
-    if constexpr (M::kFast) {
-        S lap = (pl - S(2) * p) + pr;
-        return fmaf(c, p, fmaf(F, lap, p));
-    } else if constexpr (FUSED2) {
-        S lap = Strict<S>::add(__fma_rn(S(-2), p, pl), pr);
-        S diff = Strict<S>::add(p, Strict<S>::mul(F, lap));
-        return Strict<S>::add(diff, Strict<S>::mul(c, p));
-    } else {
-        S lap = Strict<S>::add(Strict<S>::sub(pl, Strict<S>::mul(S(2), p)), pr);
-        S diff = Strict<S>::add(p, Strict<S>::mul(F, lap));
-        // f32 state with f64 beta: the reaction product and the final sum are evaluated in f64
-        C react = Strict<C>::mul(c, static_cast<C>(p));
-        return static_cast<S>(Strict<C>::add(static_cast<C>(diff), react));
-    }
-}
-
-// Transport, hyperbolic.py:146-155:
-//   n_j = p_j + dt*(((p_{j+1} - p_j)/dx) + (p_0 * beta_j))        dq = (p_{j+1} - p_j)/dx, divided beforehand
-template <class M>
-__device__ __forceinline__ typename M::S tr_point(typename M::S p, typename M::S dq, typename M::S p0,
-                                                   typename M::C dt, typename M::C beta) {
-    using S = typename M::S;
-    using C = typename M::C;
-    if constexpr (M::kFast) {
-        return fmaf(dt, fmaf(p0, beta, dq), p);
-    } else {
-        C e = Strict<C>::mul(static_cast<C>(p0), beta);                  // promoted to beta's dtype
-        C f = Strict<C>::add(static_cast<C>(dq), e);
-        C g = Strict<C>::mul(dt, f);
-        return static_cast<S>(Strict<C>::add(static_cast<C>(p), g));
-    }
-}
-
-// ---- actuation -------------------------------------------------------------------------------
-// Boundary value written at the actuated point, evaluated in numpy's promoted dtype:
-//   Dirichlet : normalize(a)                      in the action dtype A
-//   Neumann   : normalize(a*dx + neighbour)       a*dx in A, sum and normalize in promote(A, S)
-// (hyperbolic.py:143-145 reads the not-yet-written new row -> neighbour == 0; parabolic.py:148-150
-//  reads the previous row's u[nx-1].)
-template <typename S>
-__device__ __forceinline__ S actuate(const Bc1dArgs& a, int64_t env, S neighbour) {
-    const pdecg_bc1d_cfg& c = a.cfg;
-    const bool nz = c.normalize != 0;
-    if (c.action_dtype == PDECG_F32) {
-        float act = static_cast<const float*>(a.buf.action)[env];
-        if (c.control_type == PDECG_CONTROL_DIRICHLET)
-            return static_cast<S>(normalize_action<float>(act, nz, static_cast<float>(c.max_control_value)));
-        float adx = __fmul_rn(act, static_cast<float>(c.dx));
-        S w = Strict<S>::add(static_cast<S>(adx), neighbour);          // promote(f32, S) == S
-        return normalize_action<S>(w, nz, static_cast<S>(c.max_control_value));
-    } else {
-        double act = static_cast<const double*>(a.buf.action)[env];
-        if (c.control_type == PDECG_CONTROL_DIRICHLET)
-            return static_cast<S>(normalize_action<double>(act, nz, c.max_control_value));
-        double w = __dadd_rn(__dmul_rn(act, c.dx), static_cast<double>(neighbour));
-        return static_cast<S>(normalize_action<double>(w, nz, c.max_control_value));
-    }
-}
-
-// value of point `jq` of the row, broadcast to all lanes
-template <typename S, int K>
-__device__ __forceinline__ S row_value(const S (&u)[K], int jq) {
-    int src = jq / K, slot = jq - src * K;
-    S v = u[0];
-#pragma unroll
-    for (int k = 1; k < K; ++k) v = (slot == k) ? u[k] : v;
-    return __shfl_sync(kFull, v, src);
-}
-
-// Kernel variants (uniform over the batch, chosen on the host):
-//   kVarFast : boundary / padding points are "frozen slots" -- their per-slot coefficients are zero, so
-//              the unmodified stencil leaves them unchanged (x + 0*finite == x).  The inner loop is then
-//              pure stencil arithmetic + 2 halo shuffles: no per-point selects.  The actuated value is
-//              written once, after the first substep (it is constant over a control step).  Requires
-//              lane 31 to hold padding only (npts <= 31*K) so no non-finite value can wrap around.
-//   kVarSafe : boundary points overwritten with selects every substep (any npts <= 32*K).
-//   kVarDyn  : kVarSafe + the actuated value recomputed every substep from u[nx-1]
-//              (ReactionDiffusion with Neumann control, parabolic.py:148-150).
-enum { kVarFast = 0, kVarSafe = 1, kVarDyn = 2 };
-
-template <int ENV, class M, int K, int VAR>
-struct Integrator {
-    using S = typename M::S;
-    using C = typename M::C;
-    S u[K];
-    C coef[K];      // RD: dt*beta_j ; Transport: beta_j      (zero on frozen slots in kVarFast)
-    S fk[K];        // RD, kVarFast: F on interior points, 0 on frozen slots
-    C dk[K];        // Transport, kVarFast: dt on updated points, 0 on frozen slots
-    S g;            // value of the actuated point
-    ConstDiv<S> by_dx;
-    S Fs, dxs;
-    C dtc;
-    int lane, j0, jb;
-    double bsum_dyn;
-
-    __device__ __forceinline__ explicit Integrator(S dx) : by_dx(dx) {}
-
-    template <bool FUSED2>
-    __device__ __forceinline__ void substep(const Bc1dArgs& a, int64_t env, const S (&p)[K], S (&n)[K]) {
-        if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
-            if constexpr (VAR == kVarDyn) {
-                g = actuate<S>(a, env, row_value<S, K>(p, jb - 1));
-                bsum_dyn += fabs(static_cast<double>(g));
-            }
-            S hl = __shfl_up_sync(kFull, p[K - 1], 1);
-            if constexpr (VAR == kVarFast) hl = (lane == 0) ? S(0) : hl;   // keep u_0's frozen slot finite
-            const S hr = __shfl_down_sync(kFull, p[0], 1);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const S pl = (k == 0) ? hl : p[k > 0 ? k - 1 : 0];
-                const S pr = (k == K - 1) ? hr : p[k < K - 1 ? k + 1 : K - 1];
-                n[k] = rd_point<M, FUSED2>(pl, p[k], pr, (VAR == kVarFast) ? fk[k] : Fs, coef[k]);
-            }
-            if constexpr (VAR != kVarFast) {
-                if (lane == 0) n[0] = S(0);            // parabolic.py:146
-            }
-        } else {
-            const S p0 = __shfl_sync(kFull, p[0], 0);
-            const S hr = __shfl_down_sync(kFull, p[0], 1);
-            // (p_{j+1} - p_j) / dx for the whole chunk: 3-instruction exact tail per point, ONE range test
-            // per substep; operands outside the window (zero, denormal, inf, ...) redo the chunk exactly
-            S x[K], dq[K];
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const S pr = (k == K - 1) ? hr : p[k < K - 1 ? k + 1 : K - 1];
-                if constexpr (M::kFast) {
-                    dq[k] = (pr - p[k]) * by_dx.y;
-                } else {
-                    x[k] = Strict<S>::sub(pr, p[k]);
-                    dq[k] = by_dx.fast(x[k]);
-                    ok = ok & by_dx.in_range(x[k]);
-                }
-            }
-            if constexpr (!M::kFast) {
-                if (!ok) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) dq[k] = by_dx.exact(x[k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) n[k] = tr_point<M>(p[k], dq[k], p0, (VAR == kVarFast) ? dk[k] : dtc, coef[k]);
-        }
-        if constexpr (VAR != kVarFast) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) n[k] = (j0 + k == jb) ? g : n[k];
-        }
-    }
-
-    // `cnt` substeps in place (register ping-pong: no copies in the steady state)
-    template <bool FUSED2>
-    __device__ __forceinline__ void advance_t(const Bc1dArgs& a, int64_t env, int cnt) {
-        S v[K];
-        int i = 0;
-        for (; i + 2 <= cnt; i += 2) {
-            substep<FUSED2>(a, env, u, v);
-            substep<FUSED2>(a, env, v, u);
-        }
-        if (i < cnt) {
-            substep<FUSED2>(a, env, u, v);
-#pragma unroll
-            for (int k = 0; k < K; ++k) u[k] = v[k];
-        }
-    }
-    static constexpr bool kCanFuse = (ENV == PDECG_ENV_REACTION_DIFFUSION) && !M::kFast && (sizeof(S) == 8) && (sizeof(C) == 8);
-    bool fuse2;     // warp-uniform, set per env per control step (see rd_point)
-    __device__ __forceinline__ void advance(const Bc1dArgs& a, int64_t env, int cnt) {
-        if constexpr (kCanFuse) {
-            if (fuse2) { advance_t<true>(a, env, cnt); return; }
-        }
-        advance_t<false>(a, env, cnt);
-    }
-
-    // write the boundary values the reference assigns explicitly
-    __device__ __forceinline__ void fix_boundaries() {
-#pragma unroll
-        for (int k = 0; k < K; ++k) u[k] = (j0 + k == jb) ? g : u[k];
-        if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
-            if (lane == 0) u[0] = S(0);
-        }
-    }
-};
-
-template <int ENV, class M, int K, int VAR>
-__global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const Bc1dArgs a) {
-    using S = typename M::S;
-    using C = typename M::C;
-    __shared__ S sm_all[kWarpsPerBlock][32 * K];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
-    if (env >= a.buf.n_envs) return;
-    S* sm = sm_all[wib];
-    const pdecg_bc1d_cfg& cfg = a.cfg;
-    const int npts = a.npts;
-    const int j0 = lane * K;
-
-    Integrator<ENV, M, K, VAR> I{static_cast<S>(cfg.dx)};
-    I.lane = lane;
-    I.j0 = j0;
-    I.jb = npts - 1;                               // actuated point (x = X; ghost point for RD)
-    I.Fs = static_cast<S>(cfg.dt / (cfg.dx * cfg.dx));     // parabolic.py:138 (python float -> S)
-    I.dxs = static_cast<S>(cfg.dx);
-    I.dtc = static_cast<C>(cfg.dt);
-    I.bsum_dyn = 0.0;
-
-    S* urow = static_cast<S*>(a.buf.u) + env * npts;
-    load_row_chunk<S, S, K>(I.u, urow, npts, sm, lane);
-    if constexpr (ENV == PDECG_ENV_TRANSPORT) {
-        // padding slots (never stored, never read by valid points) hold a ramp instead of zeros so that the
-        // differences (u[j+1]-u[j]) formed there are ordinary numbers and stay on the division fast path
-#pragma unroll
-        for (int k = 0; k < K; ++k) I.u[k] = (j0 + k >= npts) ? static_cast<S>(j0 + k - npts + 1) : I.u[k];
-    }
-
-    // per-slot coefficient: RD -> c_j = dt*beta_j (parabolic.py:144, left-assoc `dt*beta*u`);
-    //                       Transport -> beta_j
-    {
-        const C* brow = static_cast<const C*>(a.buf.beta) + env * a.buf.beta_env_stride;
-        if constexpr (sizeof(C) <= sizeof(S)) {
-            load_row_chunk<C, C, K>(I.coef, brow, npts, reinterpret_cast<C*>(sm), lane);
-        } else {
-            // f64 beta with f32 state: direct (L1-served) chunk loads; once per control step
-#pragma unroll
-            for (int k = 0; k < K; ++k) I.coef[k] = (j0 + k < npts) ? brow[j0 + k] : C(0);
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int j = j0 + k;
-            if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
-                I.coef[k] = M::kFast ? I.dtc * I.coef[k] : Strict<C>::mul(I.dtc, I.coef[k]);
-                const bool interior = (j >= 1) && (j < npts - 1);
-                I.fk[k] = interior ? I.Fs : S(0);
-                I.dk[k] = C(0);
-                if (VAR == kVarFast && !interior) I.coef[k] = C(0);
-            } else {
-                const bool updated = j < npts - 1;          // hyperbolic.py:146: u[0 : Nx-1]
-                I.dk[k] = updated ? I.dtc : C(0);
-                I.fk[k] = S(0);
-            }
-        }
-    }
-
-    const int t0 = a.buf.time_index[env];
-    int nsub = cfg.nt - 1 - t0;
-    nsub = nsub < 0 ? 0 : (nsub > cfg.substeps ? cfg.substeps : nsub);
-    const int t_end = t0 + nsub;
-
-    double* carry = a.buf.carry + env * a.carry_len;
-    double bsum = carry[0];
-
-    I.g = actuate<S>(a, env, S(0));               // constant over the step unless kVarDyn
-    I.fuse2 = false;
-    if constexpr (Integrator<ENV, M, K, VAR>::kCanFuse) {
-        // |n_j| <= (1 + 4F + max|c|) * max(|p|, |g|): after nsub substeps |u| <= m * rho^nsub.  Require that to
-        // stay below 2^1000 so that 2*u_j can never overflow inside this control step.
-        if (VAR != kVarDyn) {
-            double m = fabs(static_cast<double>(I.g)), cm = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                m = fmax(m, fabs(static_cast<double>(I.u[k])));      // fmax drops NaN -> checked below
-                cm = fmax(cm, fabs(static_cast<double>(I.coef[k])));
-            }
-            bool finite = true;
-#pragma unroll
-            for (int k = 0; k < K; ++k) finite = finite & (fabs(static_cast<double>(I.u[k])) < 1.0e300);
-            m = warp_max(m);
-            cm = warp_max(cm);
-            finite = __all_sync(kFull, finite);
-            const double rho = 1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm;
-            const double lg = log2(fmax(m, 1.0)) + static_cast<double>(nsub) * log2(rho) * 1.0000001 + 1.0;
-            I.fuse2 = finite && (lg < 1000.0);
-        }
-    }
-
-    // reward bookkeeping that needs mid-step rows (uniform over the warp)
-    const bool tuned = cfg.reward_kind == PDECG_REWARD_TUNED1D;
-    const int snap_at = (tuned && cfg.substeps > kLookback) ? nsub - kLookback : -1;   // substeps done when row t-100 is live
-    const bool want_diff = !tuned && cfg.horizon == PDECG_HORIZON_DIFFERENTIAL && nsub > 0;
-    const bool want_hor = !tuned && cfg.horizon == PDECG_HORIZON_T;
-    const int hor_m = t_end > cfg.t_horizon_length ? cfg.t_horizon_length : t_end;   // norm_reward.py:65-72
-    const int hor_from = nsub - hor_m + 1;          // rows after `done` substeps, done in [hor_from, nsub]
-    double lb_norm = 0.0;                          // ||u_{t-100}||_2
-    double diff_norm = 0.0;                        // ||u_t - u_{t-1}||_p   (NormReward differential)
-    double hor_acc = 0.0;                          // sum of the last L row norms (NormReward t-horizon)
-    S prev[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) prev[k] = S(0);
-
-    int done = 0;
-    while (true) {
-        // ---- events at the current row (after `done` substeps) ----
-        if (VAR == kVarFast && done == 1) I.fix_boundaries();
-        if (done == snap_at) lb_norm = sqrt(chunk_sumsq<S, K>(I.u, j0, npts));
-        if (want_hor && done >= hor_from && done >= 1)
-            hor_acc += static_cast<double>(static_cast<S>(chunk_norm<S, K>(I.u, j0, npts, cfg.norm_ord)));
-        if (want_diff && done == nsub) {
-            S d[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) d[k] = Strict<S>::sub(I.u[k], prev[k]);
-            diff_norm = chunk_norm<S, K>(d, j0, npts, cfg.norm_ord);
-        }
-        if (done >= nsub) break;
-        if (want_diff && done == nsub - 1) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) prev[k] = I.u[k];
-        }
-        // ---- next stop ----
-        int next = nsub;
-        if (VAR == kVarFast && done == 0) next = 1;
-        if (snap_at > done && snap_at < next) next = snap_at;
-        if (want_diff && nsub - 1 > done && nsub - 1 < next) next = nsub - 1;
-        if (want_hor) {
-            int h = hor_from > done + 1 ? hor_from : done + 1;
-            if (h < next) next = h;
-        }
-        I.advance(a, env, next - done);
-        done = next;
-    }
-    if constexpr (VAR == kVarDyn) bsum += I.bsum_dyn;
-    else bsum += static_cast<double>(nsub) * fabs(static_cast<double>(I.g));
-
-    // ---- write back state, bookkeeping ---------------------------------------------------------
-    if (nsub > 0) {
-        if constexpr (VAR == kVarFast) I.fix_boundaries();   // frozen slots may have absorbed a NaN/inf neighbour
-        store_row_chunk<S, K>(I.u, urow, npts, sm, lane);
-    }
-    S (&u)[K] = I.u;
-
-    const double sumsq = chunk_sumsq<S, K>(u, j0, npts);
-    const S norm2 = static_cast<S>(sqrt(sumsq));               // np.linalg.norm(u[t]) in the state dtype
-    const bool terminated = t_end >= cfg.nt - 1;                // hyperbolic.py:171-180
-    const bool truncated = cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value));
-    const S dxs = I.dxs;
-
-    double reward;
-    if (tuned) {
-        // look-back norm from the ring when the row t-100 sits on an earlier step boundary
-        if (cfg.substeps <= kLookback && cfg.substeps >= 1) {
-            const int slot = 1 + ((t_end / cfg.substeps) % a.ring_len);
-            lb_norm = carry[slot];
-            __syncwarp();
-            if (lane == 0 && nsub > 0) carry[slot] = static_cast<double>(norm2);
-        }
-        if (terminated && norm2 < S(20)) {
-            // tuned_reward_1d.py:36-37, evaluated in the state dtype like numpy (python floats are weak)
-            S acc = static_cast<S>(bsum);
-            S r = Strict<S>::sub(Strict<S>::sub(static_cast<S>(cfg.terminate_reward), Strict<S>::div(acc, S(1000))), norm2);
-            reward = static_cast<double>(r);
-        } else if (truncated) {
-            reward = cfg.truncate_penalty * static_cast<double>(cfg.reward_nt - t_end);
-        } else {
-            reward = static_cast<double>(Strict<S>::sub(static_cast<S>(lb_norm), norm2));
-        }
-    } else {
-        const S coeff = static_cast<S>(cfg.norm_coeff);
-        if (terminated) {
-            reward = cfg.terminate_reward;
-        } else if (truncated) {
-            reward = cfg.truncate_penalty * static_cast<double>(cfg.reward_nt - t_end);
-        } else if (cfg.horizon == PDECG_HORIZON_TEMPORAL || nsub == 0) {
-            S nn = (cfg.norm_ord == kNormL2) ? norm2 : static_cast<S>(chunk_norm<S, K>(u, j0, npts, cfg.norm_ord));
-            reward = static_cast<double>(Strict<S>::div(-nn, coeff));
-        } else if (cfg.horizon == PDECG_HORIZON_DIFFERENTIAL) {
-            reward = static_cast<double>(Strict<S>::div(static_cast<S>(diff_norm), coeff));
-        } else {
-            // norm_reward.py:63-73: python-level accumulation of S-typed norms
-            S mean = Strict<S>::div(static_cast<S>(hor_acc), static_cast<S>(hor_m));
-            reward = static_cast<double>(Strict<S>::div(-mean, coeff));
-        }
-    }
-
-    // ---- sensing (hyperbolic.py:69-120, parabolic.py:69-118) ------------------------------------
-    if (cfg.sensing_loc != PDECG_SENSE_FULL) {
-        S o;
-        if (cfg.sensing_loc == PDECG_SENSE_COLLOCATED) {
-            const S ub = row_value<S, K>(u, npts - 1);
-            if (cfg.control_type == PDECG_CONTROL_NEUMANN) o = ub;
-            else o = Strict<S>::div(Strict<S>::sub(ub, row_value<S, K>(u, npts - 2)), dxs);
-        } else {
-            const S u0 = row_value<S, K>(u, 0);
-            if (cfg.sensing_type == PDECG_SENSETYPE_NEUMANN) o = Strict<S>::div(Strict<S>::sub(row_value<S, K>(u, 1), u0), dxs);
-            else o = u0;
-        }
-        if (lane == 0) static_cast<S*>(a.buf.obs)[env] = o;
-    }
-
-    if (lane == 0) {
-        carry[0] = bsum;
-        a.buf.time_index[env] = t_end;
-        a.buf.reward[env] = reward;
-        a.buf.terminated[env] = terminated ? 1 : 0;
-        a.buf.truncated[env] = truncated ? 1 : 0;
-    }
-}
 
 // ---- reset -------------------------------------------------------------------------------------
 struct RandomIc {          // optional: u <- c * profile with c ~ U(lo, hi) from Philox (pdecg_bc1d_reset_random)
@@ -562,47 +125,11 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     return PDECG_OK;
 }
 
-// points per lane and kernel variant for this configuration (uniform over the batch)
-static void pick_variant(const Bc1dArgs& a, int* K, int* var) {
-    const int k_min = (a.npts + 31) / 32;
-    const bool dyn = a.cfg.env == PDECG_ENV_REACTION_DIFFUSION && a.cfg.control_type == PDECG_CONTROL_NEUMANN;
-    if (dyn) { *K = k_min; *var = kVarDyn; return; }
-    if (a.npts <= 31 * k_min) { *K = k_min; *var = kVarFast; return; }
-    if (k_min + 1 <= 8 && a.npts <= 31 * (k_min + 1)) { *K = k_min + 1; *var = kVarFast; return; }
-    *K = k_min; *var = kVarSafe;
-}
-
-template <int ENV, class M, int VAR>
-static int launch_k(const Bc1dArgs& a, int K, cudaStream_t st) {
-    const unsigned grid = static_cast<unsigned>((a.buf.n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    switch (K) {
-#define PDECG_CASE(KK) case KK: bc1d_step_kernel<ENV, M, KK, VAR><<<grid, kThreads, 0, st>>>(a); break;
-        PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
-#undef PDECG_CASE
-        default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
-    }
-    count_launch();
-    return check_launch("bc1d_step_kernel");
-}
-
-template <int ENV, class M>
-static int launch_var(const Bc1dArgs& a, cudaStream_t st) {
-    int K, var;
-    pick_variant(a, &K, &var);
-    if (var == kVarFast) return launch_k<ENV, M, kVarFast>(a, K, st);
-    if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
-        if (var == kVarDyn) return launch_k<ENV, M, kVarDyn>(a, K, st);
-    }
-    return launch_k<ENV, M, kVarSafe>(a, K, st);
-}
-
-template <int ENV>
 static int launch_mode(const Bc1dArgs& a, cudaStream_t st) {
     switch (a.cfg.precision) {
-        case PDECG_PREC_REF:
-            return a.cfg.beta_dtype == PDECG_F32 ? launch_var<ENV, ModeRefB32>(a, st) : launch_var<ENV, ModeRefB64>(a, st);
-        case PDECG_PREC_FP64: return launch_var<ENV, ModeFp64>(a, st);
-        default: return launch_var<ENV, ModeFp32>(a, st);
+        case PDECG_PREC_REF: return a.cfg.beta_dtype == PDECG_F32 ? launch_bc1d_refb32(a, st) : launch_bc1d_refb64(a, st);
+        case PDECG_PREC_FP64: return launch_bc1d_fp64(a, st);
+        default: return launch_bc1d_fp32(a, st);
     }
 }
 
@@ -628,8 +155,7 @@ extern "C" int pdecg_bc1d_step(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffe
     if (!buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
     if (!buf->beta) return fail(PDECG_ERR_INVALID, "null beta buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return cfg->env == PDECG_ENV_TRANSPORT ? launch_mode<PDECG_ENV_TRANSPORT>(a, st)
-                                            : launch_mode<PDECG_ENV_REACTION_DIFFUSION>(a, st);
+    return launch_mode(a, st);
 }
 
 static int reset_impl(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* init, int32_t init_dtype,
