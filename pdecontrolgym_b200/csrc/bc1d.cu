@@ -120,8 +120,7 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     out->npts = pdecg_bc1d_npts(cfg);
     out->ring_len = ring_len_for(cfg->substeps);
     out->carry_len = 1 + out->ring_len;
-    const int K = (out->npts + 31) / 32;
-    if (K > 8) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", out->npts);
+    if ((out->npts + 31) / 32 > 8) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", out->npts);
     return PDECG_OK;
 }
 

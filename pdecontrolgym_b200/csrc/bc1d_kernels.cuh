@@ -9,6 +9,8 @@
 // (TunedReward1D / NormReward) and terminate / truncate are fused into the same launch, so HBM
 // carries one state row in and out (+ a few scalars) per env per control step.
 #pragma once
+#include <cstdlib>
+
 #include "pdecg_internal.h"
 
 namespace pdecg {
@@ -110,27 +112,27 @@ __device__ __forceinline__ S actuate(const Bc1dArgs& a, int64_t env, S neighbour
 }
 
 // value of point `jq` of the row, broadcast to all lanes
-template <typename S, int K>
-__device__ __forceinline__ S row_value(const S (&u)[K], int jq) {
+template <typename S, int K, int LPE = 32>
+__device__ __forceinline__ S row_value(const S (&u)[K], int jq, unsigned m = kFull) {
     int src = jq / K, slot = jq - src * K;
     S v = u[0];
 #pragma unroll
     for (int k = 1; k < K; ++k) v = (slot == k) ? u[k] : v;
-    return __shfl_sync(kFull, v, src);
+    return __shfl_sync(m, v, src, LPE);
 }
 
 // Kernel variants (uniform over the batch, chosen on the host):
 //   kVarFast : boundary / padding points are "frozen slots" -- their per-slot coefficients are zero, so
 //              the unmodified stencil leaves them unchanged (x + 0*finite == x).  The inner loop is then
 //              pure stencil arithmetic + 2 halo shuffles: no per-point selects.  The actuated value is
-//              written once, after the first substep (it is constant over a control step).  Requires
-//              lane 31 to hold padding only (npts <= 31*K) so no non-finite value can wrap around.
+//              written once, after the first substep (it is constant over a control step).  The halos of
+//              the segment's two edge lanes are forced to 0 so no non-finite value can wrap around.
 //   kVarSafe : boundary points overwritten with selects every substep (any npts <= 32*K).
 //   kVarDyn  : kVarSafe + the actuated value recomputed every substep from u[nx-1]
 //              (ReactionDiffusion with Neumann control, parabolic.py:148-150).
 enum { kVarFast = 0, kVarSafe = 1, kVarDyn = 2 };
 
-template <int ENV, class M, int K, int VAR>
+template <int ENV, class M, int K, int VAR, int LPE = 32>
 struct Integrator {
     using S = typename M::S;
     using C = typename M::C;
@@ -142,7 +144,8 @@ struct Integrator {
     ConstDiv<S> by_dx;
     S Fs, dxs;
     C dtc;
-    int lane, j0, jb;
+    int lane, j0, jb;       // lane = index inside the env's LPE-lane segment
+    unsigned mask;          // member mask of the segment
     double bsum_dyn;
 
     __device__ __forceinline__ explicit Integrator(S dx) : by_dx(dx) {}
@@ -151,12 +154,15 @@ struct Integrator {
     __device__ __forceinline__ void substep(const Bc1dArgs& a, int64_t env, const S (&p)[K], S (&n)[K]) {
         if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
             if constexpr (VAR == kVarDyn) {
-                g = actuate<S>(a, env, row_value<S, K>(p, jb - 1));
+                g = actuate<S>(a, env, row_value<S, K, LPE>(p, jb - 1, mask));
                 bsum_dyn += fabs(static_cast<double>(g));
             }
-            S hl = __shfl_up_sync(kFull, p[K - 1], 1);
-            if constexpr (VAR == kVarFast) hl = (lane == 0) ? S(0) : hl;   // keep u_0's frozen slot finite
-            const S hr = __shfl_down_sync(kFull, p[0], 1);
+            S hl = __shfl_up_sync(mask, p[K - 1], 1, LPE);
+            S hr = __shfl_down_sync(mask, p[0], 1, LPE);
+            if constexpr (VAR == kVarFast) {
+                hl = (lane == 0) ? S(0) : hl;          // the segment's edge lanes see 0, never a wrapped value:
+                hr = (lane == LPE - 1) ? S(0) : hr;    // frozen slots stay finite unless their real neighbour is not
+            }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const S pl = (k == 0) ? hl : p[k > 0 ? k - 1 : 0];
@@ -167,8 +173,9 @@ struct Integrator {
                 if (lane == 0) n[0] = S(0);            // parabolic.py:146
             }
         } else {
-            const S p0 = __shfl_sync(kFull, p[0], 0);
-            const S hr = __shfl_down_sync(kFull, p[0], 1);
+            const S p0 = __shfl_sync(mask, p[0], 0, LPE);
+            S hr = __shfl_down_sync(mask, p[0], 1, LPE);
+            if constexpr (VAR == kVarFast) hr = (lane == LPE - 1) ? S(0) : hr;   // never a wrapped value (see RD)
             // (p_{j+1} - p_j) / dx for the whole chunk: 3-instruction exact tail per point, ONE range test
             // per substep; operands outside the window (zero, denormal, inf, ...) redo the chunk exactly
             S x[K], dq[K];
@@ -233,22 +240,25 @@ struct Integrator {
     }
 };
 
-template <int ENV, class M, int K, int VAR>
+template <int ENV, class M, int K, int VAR, int LPE = 32>
 __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const Bc1dArgs a) {
     using S = typename M::S;
     using C = typename M::C;
-    __shared__ S sm_all[kWarpsPerBlock][32 * K];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
+    constexpr int EPW = 32 / LPE;                      // envs per warp
+    __shared__ S sm_all[kWarpsPerBlock * EPW][LPE * K];
+    const int lane = threadIdx.x & (LPE - 1);          // lane inside the env's segment
+    const int seg = (threadIdx.x >> 5) * EPW + ((threadIdx.x & 31) / LPE);
+    const unsigned mask = seg_mask<LPE>(threadIdx.x & 31);
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * (kWarpsPerBlock * EPW) + seg;
     if (env >= a.buf.n_envs) return;
-    S* sm = sm_all[wib];
+    S* sm = sm_all[seg];
     const pdecg_bc1d_cfg& cfg = a.cfg;
     const int npts = a.npts;
     const int j0 = lane * K;
 
-    Integrator<ENV, M, K, VAR> I{static_cast<S>(cfg.dx)};
+    Integrator<ENV, M, K, VAR, LPE> I{static_cast<S>(cfg.dx)};
     I.lane = lane;
+    I.mask = mask;
     I.j0 = j0;
     I.jb = npts - 1;                               // actuated point (x = X; ghost point for RD)
     I.Fs = static_cast<S>(cfg.dt / (cfg.dx * cfg.dx));     // parabolic.py:138 (python float -> S)
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     I.bsum_dyn = 0.0;
 
     S* urow = static_cast<S*>(a.buf.u) + env * npts;
-    load_row_chunk<S, S, K>(I.u, urow, npts, sm, lane);
+    load_row_chunk<S, S, K, LPE>(I.u, urow, npts, sm, lane, mask);
     if constexpr (ENV == PDECG_ENV_TRANSPORT) {
         // padding slots (never stored, never read by valid points) hold a ramp instead of zeros so that the
         // differences (u[j+1]-u[j]) formed there are ordinary numbers and stay on the division fast path
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     {
         const C* brow = static_cast<const C*>(a.buf.beta) + env * a.buf.beta_env_stride;
         if constexpr (sizeof(C) <= sizeof(S)) {
-            load_row_chunk<C, C, K>(I.coef, brow, npts, reinterpret_cast<C*>(sm), lane);
+            load_row_chunk<C, C, K, LPE>(I.coef, brow, npts, reinterpret_cast<C*>(sm), lane, mask);
         } else {
             // f64 beta with f32 state: direct (L1-served) chunk loads; once per control step
 #pragma unroll
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
 
     I.g = actuate<S>(a, env, S(0));               // constant over the step unless kVarDyn
     I.fuse2 = false;
-    if constexpr (Integrator<ENV, M, K, VAR>::kCanFuse) {
+    if constexpr (Integrator<ENV, M, K, VAR, LPE>::kCanFuse) {
         // |n_j| <= (1 + 4F + max|c|) * max(|p|, |g|): after nsub substeps |u| <= m * rho^nsub.  Require that to
         // stay below 2^1000 so that 2*u_j can never overflow inside this control step.
         if (VAR != kVarDyn) {
@@ -316,9 +326,9 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
             bool finite = true;
 #pragma unroll
             for (int k = 0; k < K; ++k) finite = finite & (fabs(static_cast<double>(I.u[k])) < 1.0e300);
-            m = warp_max(m);
-            cm = warp_max(cm);
-            finite = __all_sync(kFull, finite);
+            m = seg_max<LPE>(m, mask);
+            cm = seg_max<LPE>(cm, mask);
+            finite = __all_sync(mask, finite);
             const double rho = 1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm;
             const double lg = log2(fmax(m, 1.0)) + static_cast<double>(nsub) * log2(rho) * 1.0000001 + 1.0;
             I.fuse2 = finite && (lg < 1000.0);
@@ -343,14 +353,14 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     while (true) {
         // ---- events at the current row (after `done` substeps) ----
         if (VAR == kVarFast && done == 1) I.fix_boundaries();
-        if (done == snap_at) lb_norm = sqrt(chunk_sumsq<S, K>(I.u, j0, npts));
+        if (done == snap_at) lb_norm = sqrt(chunk_sumsq<S, K, LPE>(I.u, j0, npts, mask));
         if (want_hor && done >= hor_from && done >= 1)
-            hor_acc += static_cast<double>(static_cast<S>(chunk_norm<S, K>(I.u, j0, npts, cfg.norm_ord)));
+            hor_acc += static_cast<double>(static_cast<S>(chunk_norm<S, K, LPE>(I.u, j0, npts, cfg.norm_ord, mask)));
         if (want_diff && done == nsub) {
             S d[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) d[k] = Strict<S>::sub(I.u[k], prev[k]);
-            diff_norm = chunk_norm<S, K>(d, j0, npts, cfg.norm_ord);
+            diff_norm = chunk_norm<S, K, LPE>(d, j0, npts, cfg.norm_ord, mask);
         }
         if (done >= nsub) break;
         if (want_diff && done == nsub - 1) {
@@ -375,11 +385,11 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     // ---- write back state, bookkeeping ---------------------------------------------------------
     if (nsub > 0) {
         if constexpr (VAR == kVarFast) I.fix_boundaries();   // frozen slots may have absorbed a NaN/inf neighbour
-        store_row_chunk<S, K>(I.u, urow, npts, sm, lane);
+        store_row_chunk<S, K, LPE>(I.u, urow, npts, sm, lane, mask);
     }
     S (&u)[K] = I.u;
 
-    const double sumsq = chunk_sumsq<S, K>(u, j0, npts);
+    const double sumsq = chunk_sumsq<S, K, LPE>(u, j0, npts, mask);
     const S norm2 = static_cast<S>(sqrt(sumsq));               // np.linalg.norm(u[t]) in the state dtype
     const bool terminated = t_end >= cfg.nt - 1;                // hyperbolic.py:171-180
     const bool truncated = cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value));
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         if (cfg.substeps <= kLookback && cfg.substeps >= 1) {
             const int slot = 1 + ((t_end / cfg.substeps) % a.ring_len);
             lb_norm = carry[slot];
-            __syncwarp();
+            __syncwarp(mask);
             if (lane == 0 && nsub > 0) carry[slot] = static_cast<double>(norm2);
         }
         if (terminated && norm2 < S(20)) {
@@ -411,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         } else if (truncated) {
             reward = cfg.truncate_penalty * static_cast<double>(cfg.reward_nt - t_end);
         } else if (cfg.horizon == PDECG_HORIZON_TEMPORAL || nsub == 0) {
-            S nn = (cfg.norm_ord == kNormL2) ? norm2 : static_cast<S>(chunk_norm<S, K>(u, j0, npts, cfg.norm_ord));
+            S nn = (cfg.norm_ord == kNormL2) ? norm2 : static_cast<S>(chunk_norm<S, K, LPE>(u, j0, npts, cfg.norm_ord, mask));
             reward = static_cast<double>(Strict<S>::div(-nn, coeff));
         } else if (cfg.horizon == PDECG_HORIZON_DIFFERENTIAL) {
             reward = static_cast<double>(Strict<S>::div(static_cast<S>(diff_norm), coeff));
@@ -426,12 +436,12 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     if (cfg.sensing_loc != PDECG_SENSE_FULL) {
         S o;
         if (cfg.sensing_loc == PDECG_SENSE_COLLOCATED) {
-            const S ub = row_value<S, K>(u, npts - 1);
+            const S ub = row_value<S, K, LPE>(u, npts - 1, mask);
             if (cfg.control_type == PDECG_CONTROL_NEUMANN) o = ub;
-            else o = Strict<S>::div(Strict<S>::sub(ub, row_value<S, K>(u, npts - 2)), dxs);
+            else o = Strict<S>::div(Strict<S>::sub(ub, row_value<S, K, LPE>(u, npts - 2, mask)), dxs);
         } else {
-            const S u0 = row_value<S, K>(u, 0);
-            if (cfg.sensing_type == PDECG_SENSETYPE_NEUMANN) o = Strict<S>::div(Strict<S>::sub(row_value<S, K>(u, 1), u0), dxs);
+            const S u0 = row_value<S, K, LPE>(u, 0, mask);
+            if (cfg.sensing_type == PDECG_SENSETYPE_NEUMANN) o = Strict<S>::div(Strict<S>::sub(row_value<S, K, LPE>(u, 1, mask), u0), dxs);
             else o = u0;
         }
         if (lane == 0) static_cast<S*>(a.buf.obs)[env] = o;
@@ -446,24 +456,39 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     }
 }
 
-// points per lane and kernel variant for this configuration (uniform over the batch)
-inline void pick_variant(const Bc1dArgs& a, int* K, int* var) {
-    const int k_min = (a.npts + 31) / 32;
+// Lanes per env, points per lane and kernel variant for this configuration (uniform over the batch).
+// Two envs per warp (LPE = 16) are used for the reference's default grids when that wastes fewer lane-slots:
+// 201 points (RD) -> 16 x 13 = 208 slots instead of 32 x 7 = 224; 100 points (Transport) -> 16 x 7 = 112
+// instead of 32 x 4 = 128.
+inline void pick_variant(const Bc1dArgs& a, int* LPE, int* K, int* var) {
     const bool dyn = a.cfg.env == PDECG_ENV_REACTION_DIFFUSION && a.cfg.control_type == PDECG_CONTROL_NEUMANN;
-    if (dyn) { *K = k_min; *var = kVarDyn; return; }
-    if (a.npts <= 31 * k_min) { *K = k_min; *var = kVarFast; return; }
-    if (k_min + 1 <= 8 && a.npts <= 31 * (k_min + 1)) { *K = k_min + 1; *var = kVarFast; return; }
-    *K = k_min; *var = kVarSafe;
+    const int k32 = (a.npts + 31) / 32, k16 = (a.npts + 15) / 16;
+    const bool half = !dyn && (k16 == 7 || k16 == 13) && (k16 < 2 * k32) && !getenv("PDECG_BC1D_NO_HALFWARP");
+    *LPE = half ? 16 : 32;
+    *K = half ? k16 : k32;
+    // the frozen-slot variant zeroes the halos of the segment's edge lanes, so it is valid for every npts <= LPE*K
+    *var = dyn ? kVarDyn : (getenv("PDECG_BC1D_SAFE") ? kVarSafe : kVarFast);
 }
 
 template <int ENV, class M, int VAR>
-inline int launch_k(const Bc1dArgs& a, int K, cudaStream_t st) {
-    const unsigned grid = static_cast<unsigned>((a.buf.n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    switch (K) {
-#define PDECG_CASE(KK) case KK: bc1d_step_kernel<ENV, M, KK, VAR><<<grid, kThreads, 0, st>>>(a); break;
-        PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
+inline int launch_k(const Bc1dArgs& a, int LPE, int K, cudaStream_t st) {
+    const int64_t per_block = (LPE == 16) ? 2 * kWarpsPerBlock : kWarpsPerBlock;
+    const unsigned grid = static_cast<unsigned>((a.buf.n_envs + per_block - 1) / per_block);
+    if (LPE == 16) {
+        if constexpr (VAR == kVarFast) {
+            if (K == 7) bc1d_step_kernel<ENV, M, 7, VAR, 16><<<grid, kThreads, 0, st>>>(a);
+            else if (K == 13) bc1d_step_kernel<ENV, M, 13, VAR, 16><<<grid, kThreads, 0, st>>>(a);
+            else return fail(PDECG_ERR_UNSUPPORTED, "unsupported half-warp points-per-lane %d", K);
+        } else {
+            return fail(PDECG_ERR_UNSUPPORTED, "half-warp mapping only exists for the fast variant");
+        }
+    } else {
+        switch (K) {
+#define PDECG_CASE(KK) case KK: bc1d_step_kernel<ENV, M, KK, VAR, 32><<<grid, kThreads, 0, st>>>(a); break;
+            PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
 #undef PDECG_CASE
-        default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
+            default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
+        }
     }
     count_launch();
     return check_launch("bc1d_step_kernel");
@@ -471,13 +496,13 @@ inline int launch_k(const Bc1dArgs& a, int K, cudaStream_t st) {
 
 template <int ENV, class M>
 inline int launch_var(const Bc1dArgs& a, cudaStream_t st) {
-    int K, var;
-    pick_variant(a, &K, &var);
-    if (var == kVarFast) return launch_k<ENV, M, kVarFast>(a, K, st);
+    int LPE, K, var;
+    pick_variant(a, &LPE, &K, &var);
+    if (var == kVarFast) return launch_k<ENV, M, kVarFast>(a, LPE, K, st);
     if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
-        if (var == kVarDyn) return launch_k<ENV, M, kVarDyn>(a, K, st);
+        if (var == kVarDyn) return launch_k<ENV, M, kVarDyn>(a, LPE, K, st);
     }
-    return launch_k<ENV, M, kVarSafe>(a, K, st);
+    return launch_k<ENV, M, kVarSafe>(a, LPE, K, st);
 }
 
 // one function per precision mode, defined in bc1d_inst_<mode>.cu
