@@ -38,7 +38,7 @@ class BrainTumor1D:
                  t1_detection_radius: int = 15, t1_death_radius: int = 35,
                  reset_init_condition_func=None, total_dosage=None, verbose=False,
                  *, T, dt, X, dx, reward_class=None, normalize=False,
-                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True):
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False):
         if precision not in ("ref", "fp64"):
             raise ValueError("BrainTumor1D is float64 in the reference; precision must be 'ref' or 'fp64'")
         if reward_class is not None and not isinstance(reward_class, BrainTumorReward):
@@ -55,6 +55,7 @@ class BrainTumor1D:
         self.reward_class = reward_class
         self.verbose = verbose
         self.copy_obs = copy_obs
+        self.autoreset = bool(autoreset)
         self.reset_init_condition_func = reset_init_condition_func
         self.total_dosage = float(total_dosage)          # :89 (TypeError on None, like the reference)
         self.k = k
@@ -165,7 +166,14 @@ class BrainTumor1D:
         if self._ic is None:
             raise RuntimeError("call reset() before step()")
         self._run(RAW_STEP, self._prep_action(control))
-        return self._outputs(self.u)
+        out = self._outputs(self.u)
+        if self.autoreset:               # same-step auto-reset (the returned observation is the restarted state)
+            done = torch.bitwise_or(self._terminated, self._truncated)
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pdecg_bt_reset(C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
+                                                  0 if self._ic.shape[0] == 1 else self.nx, done.data_ptr(), self._stream()))
+            out = ((self.u.clone() if self.copy_obs else self.u),) + out[1:]
+        return out
 
     # -- reference attributes, as per-env tensors ------------------------------------------------
     def _icol(self, i):

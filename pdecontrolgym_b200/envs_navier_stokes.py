@@ -42,7 +42,7 @@ class NavierStokes2D:
                  viscosity: float = 0.1, density: float = 1.0, maximum_pressure_iteration: float = 2000,
                  stable_factor: float = 0.5,
                  *, T, dt, X, dx, Y, dy, action_dim: int = 1, reward_class=None, normalize: bool = False,
-                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True):
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False):
         if precision not in ("ref", "fp64"):
             raise ValueError("NavierStokes2D is float64 in the reference; precision must be 'ref' or 'fp64'")
         if not isinstance(reward_class, NSReward):
@@ -69,6 +69,8 @@ class NavierStokes2D:
         self.N_PRESSURE_POISSON_ITERATIONS = int(maximum_pressure_iteration)
         self.reward_class = reward_class
         self.copy_obs = copy_obs
+        self.autoreset = bool(autoreset)
+        self._init = None
         max_t = (0.5 * min(dx, dy) ** 2 / viscosity)
         if dt > stable_factor * max_t:
             raise RuntimeError("Stability is not guarenteed")      # :56-58
@@ -145,6 +147,7 @@ class NavierStokes2D:
             trip = [self.reset_init_condition_func(self.X) for _ in range(self.num_envs)]
             init = tuple(np.stack([np.asarray(t[c], dtype=np.float64) for t in trip]) for c in range(3))
         iu, iv, ip = (self._field(f, n) for f, n in zip(init, ("init_u", "init_v", "init_p")))
+        self._init = (iu, iv, ip)
         mask = options.get("mask")
         mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         with torch.cuda.device(self.device):
@@ -169,8 +172,15 @@ class NavierStokes2D:
         self._buf.action = a.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_ns_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
+        terminated, truncated, reward = self._terminated.bool(), self._truncated.bool(), self._reward.clone()
+        info = {"valid": self._valid.bool()}
+        if self.autoreset:               # same-step auto-reset to the last initial fields
+            iu, iv, ip = self._init
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pdecg_ns_reset(C.byref(self._cfg), C.byref(self._buf), iu.data_ptr(), iv.data_ptr(), ip.data_ptr(),
+                                                  self.nx * self.ny, self._terminated.data_ptr(), self._stream()))
         obs = self._obs.clone() if self.copy_obs else self._obs
-        return obs, self._reward.clone(), self._terminated.bool(), self._truncated.bool(), {"valid": self._valid.bool()}
+        return obs, reward, terminated, truncated, info
 
     def solve_pressure(self, u, v, p_prev):
         """Batched `solve_pressure` (navier_stokes2D.py:94-116) for external callers; returns the new p."""

@@ -29,7 +29,7 @@ class TrafficPDE1D:
                  v_max: float = 40, ro_max: float = 0.16, tau: float = 60,
                  limit_pde_state_size: bool = False, control_freq: int = 1,
                  *, T, dt, X, dx, reward_class=None, normalize=False,
-                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True):
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False):
         if precision not in ("ref", "fp64"):
             raise ValueError("TrafficPDE1D is float64 in the reference; precision must be 'ref' or 'fp64'")
         if reward_class is not None and not isinstance(reward_class, TrafficARZReward):
@@ -55,6 +55,7 @@ class TrafficPDE1D:
         self.limit_pde_state_size = limit_pde_state_size
         self.control_freq = control_freq
         self.copy_obs = copy_obs
+        self.autoreset = bool(autoreset)
         self.reward_class = reward_class
         if simulation_type != "outlet-train":
             if v_steady != self.Veq(v_max, ro_max, ro_steady):
@@ -176,8 +177,15 @@ class TrafficPDE1D:
         self._buf.action = a.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_arz_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
+        terminated, truncated, reward = self._terminated.bool(), self._truncated.bool(), self._reward.clone()
+        if self.autoreset:               # same-step auto-reset: finished envs restart from the initial condition
+            done = torch.bitwise_or(self._terminated, self._truncated)
+            if self.simulation_type == "outlet-train":
+                self.reset(options={"mask": done})
+            else:
+                self._reset_kernel(done)
         obs = self._obs.clone() if self.copy_obs else self._obs
-        return obs, self._reward.clone(), self._terminated.bool(), self._truncated.bool(), self.info
+        return obs, reward, terminated, truncated, self.info
 
     # reference attributes
     r = property(lambda s: s._ry[:, 0, :])

@@ -1,0 +1,77 @@
+"""GPU edge cases shared by all env families: empty batches, same-step auto-reset, masked resets."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+BC = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
+
+
+def test_empty_batches(cuda_device):
+    import pdecontrolgym_b200 as pcg
+    arz = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=0, device=cuda_device, T=5, dt=0.25, X=500, dx=10)
+    o, _ = arz.reset()
+    o, r, te, tr, _ = arz.step(np.zeros((0, 1)))
+    assert o.shape == (0, 102) and r.shape == (0,)
+    bt = pcg.make("PDEControlGym-BrainTumor1D", num_envs=0, device=cuda_device, total_dosage=61.2, T=600, dt=1, X=200, dx=1)
+    bt.reset(options={"init_condition": np.zeros(201)})
+    o, r, te, tr, info = bt.step(np.zeros(0))
+    assert o.shape == (0, 201)
+    w = pcg.TherapyWrapper(bt)
+    assert w.benchmark().shape == (0,)
+    ns = pcg.make("PDEControlGym-NavierStokes2D", num_envs=0, device=cuda_device, boundary_condition=BC, U_ref=np.zeros((200, 21, 21, 2)),
+                  action_ref=np.ones(1000), reward_class=pcg.NSReward(), T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05)
+    z = np.zeros((21, 21))
+    ns.reset(options={"init": (z, z, z)})
+    o, r, te, tr, _ = ns.step(np.zeros(0))
+    assert o.shape == (0, 21, 21, 2)
+
+
+def test_arz_autoreset_restarts_finished_envs(cuda_device):
+    import torch
+    import pdecontrolgym_b200 as pcg
+    kw = dict(T=2, dt=0.25, X=500, dx=10, simulation_type="inlet")
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=3, device=cuda_device, autoreset=True, **kw)
+    ref = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=3, device=cuda_device, **kw)
+    o0, _ = env.reset()
+    ref.reset()
+    a = torch.full((3, 1), 1.3, dtype=torch.float64)
+    for k in range(40):
+        o, r, te, tr, _ = env.step(a)
+        o2, r2, te2, tr2, _ = ref.step(a)
+        assert torch.equal(r, r2) and torch.equal(te, te2)
+        if te.any():
+            assert torch.equal(o[te], o0[te])            # restarted from the initial condition in the same step
+            ref.reset(options={"mask": te2})
+        else:
+            assert torch.equal(o, o2)
+    assert k == 39
+
+
+def test_brain_tumor_autoreset_and_masked_reset(cuda_device):
+    import torch
+    import pdecontrolgym_b200 as pcg
+    xs = np.linspace(0, 60, 61)
+    ic = 0.8e5 * np.exp(-0.25 * xs ** 2)
+    env = pcg.make("PDEControlGym-BrainTumor1D", num_envs=4, device=cuda_device, total_dosage=61.2, T=30, dt=1, X=60, dx=1, autoreset=True)
+    o0, _ = env.reset(options={"init_condition": ic})
+    for day in range(30):
+        o, r, te, tr, info = env.step(np.zeros(4))
+    assert te.all() and torch.equal(o, o0) and (env.time_index == 0).all() and (env.stage == 0).all()
+    env.step(np.zeros(4))
+    env.reset(options={"init_condition": ic, "mask": np.array([True, False, False, True])})
+    assert env.time_index.cpu().tolist() == [0, 1, 1, 0]
+
+
+def test_navier_stokes_autoreset(cuda_device):
+    import torch
+    import pdecontrolgym_b200 as pcg
+    ns = pcg.make("PDEControlGym-NavierStokes2D", num_envs=2, device=cuda_device, boundary_condition=BC, U_ref=np.zeros((50, 21, 21, 2)),
+                  action_ref=np.ones(100), reward_class=pcg.NSReward(), maximum_pressure_iteration=5, T=0.005, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05,
+                  autoreset=True)
+    z = np.ones((21, 21))
+    o0, _ = ns.reset(options={"init": (z, 2 * z, 0 * z)})
+    for k in range(4):
+        o, r, te, tr, _ = ns.step(np.full(2, 3.0))
+    assert te.all() and torch.equal(o, o0) and (ns.time_index == 0).all()
+    o, r, te, tr, info = ns.step(np.full(2, 3.0))
+    assert info["valid"].all() and not te.any()
