@@ -18,6 +18,7 @@ from .envs_brain_tumor import BrainTumor1D, TherapyWrapper
 from .envs_traffic_arz import TrafficPDE1D
 from .envs_navier_stokes import NavierStokes2D, central_difference, laplace
 from .dist import EpisodeStats, shard_range
+from . import adapters, controllers
 
 __version__ = "0.1.0"
 

@@ -228,6 +228,10 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         options = options or {}
         ic = options.get("init_condition")
         beta = options.get("beta")
+        if ic is None and self.reset_init_condition_func is None and self._ic is not None:
+            ic = self._random_ic if self._random_ic is not None else self._ic     # re-use the last specification
+        if beta is None and self.reset_recirculation_func is None and self.beta is not None:
+            beta = self.beta
         self._random_ic = None
         if isinstance(ic, UniformScaleIC):
             self._random_ic = ic

@@ -65,3 +65,36 @@ def test_cuda_reproduces_published_values(cuda_device, env):
     for i, u0 in enumerate((1, 10)):
         assert abs(total[i] - want[u0][0]) <= RTOL * abs(want[u0][0]), (u0, total[i], want[u0][0])
         assert abs(norm_sum[i] - want[u0][1]) <= RTOL * abs(want[u0][1]), (u0, norm_sum[i], want[u0][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", ["tr", "rd"])
+def test_cuda_closed_loop_on_device(cuda_device, env):
+    """Same published values with the batched device-side controllers (no host round trip per step) on a batch
+    that tiles the two initial conditions 8 times."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    from pdecontrolgym_b200.controllers import ReactionDiffusionBackstepping, TransportBackstepping
+    kw, npts, beta, _, nt_r, want, n_steps = _setup(env)
+    if env == "tr":
+        ctl = TransportBackstepping(KC.chebyshev_beta(np.linspace(1e-2, 1, 100), 7.35, 5), 1e-2, cuda_device)
+        eid = "PDEControlGym-TransportPDE1D"
+    else:
+        ctl = ReactionDiffusionBackstepping(KC.chebyshev_beta(np.linspace(5e-3, 1, 200), 8, 50), 5e-3, cuda_device)
+        eid = "PDEControlGym-ReactionDiffusionPDE1D"
+    N = 16
+    genv = pcg.make(eid, num_envs=N, device=cuda_device, precision="ref", reward_class=pcg.TunedReward1D(nt_r, -1e3, 3e2), copy_obs=False, **kw)
+    ic = np.tile(np.stack([np.ones(npts) * 1.0, np.ones(npts) * 10.0]), (N // 2, 1))
+    obs, _ = genv.reset(options={"init_condition": ic, "beta": beta})
+    total = torch.zeros(N, dtype=torch.float64, device=cuda_device)
+    norm_sum = torch.zeros(N, dtype=torch.float64, device=cuda_device)
+    for k in range(n_steps):
+        obs, r, te, tr, _ = genv.step(ctl(obs))
+        total += r
+        norm_sum += obs.double().norm(dim=1)
+    assert bool(te.all())
+    total, norm_sum = total.cpu().numpy(), norm_sum.cpu().numpy()
+    for i in range(N):
+        u0 = (1, 10)[i % 2]
+        assert abs(total[i] - want[u0][0]) <= RTOL * abs(want[u0][0]), (i, total[i], want[u0][0])
+        assert abs(norm_sum[i] - want[u0][1]) <= 2 * RTOL * abs(want[u0][1]), (i, norm_sum[i], want[u0][1])
