@@ -34,7 +34,7 @@ struct Bc1dArgs {
 //   [1 .. ring]    ring of step-end L2 norms    (tuned_reward_1d.py:40: norm(uVec[t-100]))
 constexpr int kLookback = 100;
 #ifndef PDECG_BC1D_MINBLOCKS
-#define PDECG_BC1D_MINBLOCKS 1
+#define PDECG_BC1D_MINBLOCKS 3   // <= 170 registers: 3 CTAs (12 warps) per SM; measured best for the fp64 two-envs-per-warp kernel
 #endif
 
 __host__ __device__ inline int ring_len_for(int substeps) {
