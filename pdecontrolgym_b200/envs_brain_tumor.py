@@ -109,6 +109,8 @@ class BrainTumor1D:
     def _run(self, mode, action=None):
         a = self._zero_action if action is None else action
         self._buf.action = a.data_ptr()
+        # the raw step's observation is the state itself: no second [N, nx] write (HBM-bound launch)
+        self._buf.obs = None if mode == RAW_STEP else self._obs.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_bt_run(C.byref(self._cfg), C.byref(self._buf), mode, self._stream()))
 
