@@ -19,6 +19,7 @@ from .envs_traffic_arz import TrafficPDE1D
 from .envs_navier_stokes import NavierStokes2D, central_difference, laplace
 from .dist import EpisodeStats, shard_range
 from . import adapters, controllers
+from .graph import GraphedStep
 
 __version__ = "0.1.0"
 
@@ -42,5 +43,5 @@ def make(id: str, num_envs: int = 1, device="cuda", precision: str = "ref", **kw
 
 make_vec = make
 
-__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "EpisodeStats", "shard_range", "UniformScaleIC", "BaseReward",
+__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "EpisodeStats", "shard_range", "UniformScaleIC", "GraphedStep", "BaseReward",
            "NormReward", "TunedReward1D", "NSReward", "TrafficARZReward", "BrainTumorReward"]

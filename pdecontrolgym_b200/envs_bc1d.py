@@ -260,6 +260,13 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             if self.beta is not None and beta_stride != 0:
                 self.beta[mask_t.bool()] = beta_t[mask_t.bool()]
                 beta_t = self.beta
+        # keep device addresses stable across resets (a captured CUDA graph has them baked in)
+        if self.beta is not None and self.beta is not beta_t and self.beta.shape == beta_t.shape and self.beta.dtype == beta_t.dtype:
+            self.beta.copy_(beta_t)
+            beta_t = self.beta
+        if self._ic is not None and self._ic is not ic_t and self._ic.shape == ic_t.shape and self._ic.dtype == ic_t.dtype:
+            self._ic.copy_(ic_t)
+            ic_t = self._ic
         self.beta = beta_t
         self._ic, self._ic_stride = ic_t, ic_stride
         self._cfg.beta_dtype = _lib.F64 if beta_t.dtype == torch.float64 else _lib.F32

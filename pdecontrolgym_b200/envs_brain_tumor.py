@@ -153,7 +153,11 @@ class BrainTumor1D:
             t = t.unsqueeze(0)
         if t.shape[-1] != self.nx or t.shape[0] not in (1, self.num_envs):
             raise ValueError(f"init_condition must have shape ({self.nx},) or ({self.num_envs}, {self.nx})")
-        self._ic = t.contiguous()
+        t = t.contiguous()
+        if self._ic is not None and self._ic is not t and self._ic.shape == t.shape:
+            self._ic.copy_(t)          # stable device address across resets (CUDA-graph friendly)
+        else:
+            self._ic = t
         mask = options.get("mask")
         mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         with torch.cuda.device(self.device):

@@ -147,6 +147,11 @@ class NavierStokes2D:
             trip = [self.reset_init_condition_func(self.X) for _ in range(self.num_envs)]
             init = tuple(np.stack([np.asarray(t[c], dtype=np.float64) for t in trip]) for c in range(3))
         iu, iv, ip = (self._field(f, n) for f, n in zip(init, ("init_u", "init_v", "init_p")))
+        if self._init is not None and all(a.shape == b.shape for a, b in zip(self._init, (iu, iv, ip))):
+            for dst, src in zip(self._init, (iu, iv, ip)):
+                if dst is not src:
+                    dst.copy_(src)     # stable device addresses across resets (CUDA-graph friendly)
+            iu, iv, ip = self._init
         self._init = (iu, iv, ip)
         mask = options.get("mask")
         mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()

@@ -77,7 +77,11 @@ def main():
     acts = torch.empty(64, N, 1, dtype=torch.float64, device=dev).uniform_(0.96, 1.44)
     ms = timed(lambda i: env.step(acts[i % 64]), 200)
     report("TrafficPDE1D outlet x16384 (control_freq=1)", N, ms, 49, {"hbm_gbs": N * (2 * 51 * 8 * 2 + 102 * 8 + 40) / (ms * 1e-3) / 1e9})
-    del env
+    g = pcg.GraphedStep(env, acts[0])
+    env.reset()
+    ms = timed(lambda i: g.step(acts[i % 64]), 200)
+    report("TrafficPDE1D outlet x16384 (control_freq=1), CUDA-graph replay", N, ms, 49, {"hbm_gbs": N * (2 * 51 * 8 * 2 + 102 * 8 + 40) / (ms * 1e-3) / 1e9})
+    del env, g
     N = 262144
     env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=dev, simulation_type="outlet", reward_class=pcg.TrafficARZReward(),
                    T=240, dt=0.25, X=500, dx=10, copy_obs=False)
@@ -99,6 +103,13 @@ def main():
         acts = torch.empty(16, N, dtype=torch.float64, device=dev).uniform_(0, 0.1)
         ms = timed(lambda i: env.step(acts[i % 16]), 150)
         report(f"BrainTumor1D raw step x{N}", N, ms, 199, {"hbm_gbs": N * (2 * 201 * 8 + 64 + 32 + 12) / (ms * 1e-3) / 1e9})
+        if N == 16384:
+            g = pcg.GraphedStep(env, acts[0])
+            env.reset(options={"init_condition": bt_ic(200, 201)})
+            ms = timed(lambda i: g.step(acts[i % 16]), 150)
+            report(f"BrainTumor1D raw step x{N}, CUDA-graph replay", N, ms, 199, {"hbm_gbs": N * (2 * 201 * 8 + 64 + 32 + 12) / (ms * 1e-3) / 1e9})
+            del g
+            env.reset(options={"init_condition": bt_ic(200, 201)})
         w = pcg.TherapyWrapper(env)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
