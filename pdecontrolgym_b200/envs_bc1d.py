@@ -22,6 +22,7 @@ import torch
 from . import _lib
 from .rewards import NormReward, TunedReward1D
 from .spaces import Box
+from .checkpoint import StateDictMixin
 
 _CONTROL = {"Dirchilet": 0, "Neumann": 1}
 _SENSE_LOC = {"full": 0, "collocated": 1, "opposite": 2}
@@ -40,7 +41,8 @@ class UniformScaleIC:
         self.lo, self.hi, self.profile = float(lo), float(hi), profile
 
 
-class PDEVecEnv1D:
+class PDEVecEnv1D(StateDictMixin):
+    _STATE_TENSORS = ('u', 'beta', '_ic', 'time_index', '_carry', '_episode', '_reward', '_terminated', '_truncated', '_obs_scalar')
     """Batched counterpart of `PDEEnv1D` (base_env_1d.py:9-68)."""
 
     ENV_KIND = -1

@@ -17,6 +17,7 @@ import torch
 from . import _lib
 from .rewards import BrainTumorReward
 from .spaces import Box
+from .checkpoint import StateDictMixin
 
 STAGE_NAMES = ("Growth", "Therapy", "Post-Therapy")
 RAW_STEP, WRAP_RESET, WRAP_STEP, RUN_TO_END = 0, 1, 2, 3
@@ -26,7 +27,8 @@ NINT, NF64 = 16, 4
 F_REMAINING, F_D, F_RHO, F_LAST_DOSE = range(4)
 
 
-class BrainTumor1D:
+class BrainTumor1D(StateDictMixin):
+    _STATE_TENSORS = ('u', '_obs', '_ienv', '_fenv', '_ic', '_reward', '_terminated', '_truncated', '_valid')
     """Batched `BrainTumor1D`: diffusion-proliferation-radiation PDE with the Growth -> Therapy ->
     Post-Therapy stage machine.  `step(action)` advances every env by one day."""
 

@@ -14,6 +14,7 @@ import torch
 from . import _lib
 from .rewards import NSReward
 from .spaces import Box
+from .checkpoint import StateDictMixin
 
 _BC = {"Dirchilet": 0, "Neumann": 1, "Controllable": 2}
 _SIDES = ("lower", "upper", "left", "right")          # the order apply_boundary visits them (:76)
@@ -37,7 +38,8 @@ def laplace(f, dx=0.01, dy=0.01):
     return diff
 
 
-class NavierStokes2D:
+class NavierStokes2D(StateDictMixin):
+    _STATE_TENSORS = ('u', 'v', 'p', '_obs', 'time_index', '_reward', '_terminated', '_truncated', '_valid')
     def __init__(self, reset_init_condition_func=None, boundary_condition: dict = None, U_ref=None, action_ref=None,
                  viscosity: float = 0.1, density: float = 1.0, maximum_pressure_iteration: float = 2000,
                  stable_factor: float = 0.5,

@@ -18,13 +18,15 @@ import torch
 from . import _lib
 from .rewards import TrafficARZReward
 from .spaces import Box
+from .checkpoint import StateDictMixin
 
 _TYPES = {"inlet": 0, "outlet": 1, "both": 2, "outlet-train": 3}
 F_TIME, F_RS, F_VS, F_QS, NF64 = 0, 1, 2, 3, 4
 _RS_VALUES = (0.115, 0.12, 0.125)            # traffic_arz_env.py:66-68
 
 
-class TrafficPDE1D:
+class TrafficPDE1D(StateDictMixin):
+    _STATE_TENSORS = ('_ry', '_obs', '_fenv', '_reward', '_terminated', '_truncated')
     def __init__(self, simulation_type: str = "inlet", v_steady: float = 10, ro_steady: float = 0.12,
                  v_max: float = 40, ro_max: float = 0.16, tau: float = 60,
                  limit_pde_state_size: bool = False, control_freq: int = 1,

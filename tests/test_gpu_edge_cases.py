@@ -75,3 +75,38 @@ def test_navier_stokes_autoreset(cuda_device):
     assert te.all() and torch.equal(o, o0) and (ns.time_index == 0).all()
     o, r, te, tr, info = ns.step(np.full(2, 3.0))
     assert info["valid"].all() and not te.any()
+
+
+def test_state_dict_roundtrip_all_envs(cuda_device):
+    """Checkpoint / restore: stepping after load_state_dict() reproduces the original continuation bit for bit."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    rng = np.random.default_rng(0)
+    xs = np.linspace(0, 200, 201)
+    z = rng.uniform(-1, 1, (3, 21, 21))
+    cases = [
+        (lambda: pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=3, device=cuda_device, T=0.02, dt=1e-5, X=1, dx=5e-3,
+                          control_sample_rate=1e-3, normalize=True, reward_class=pcg.TunedReward1D(2000)),
+         lambda e: e.reset(options={"init_condition": rng.uniform(1, 2, (3, 201)), "beta": np.linspace(0, 9, 201)}),
+         lambda k: torch.full((3,), 0.1 * k, device=cuda_device)),
+        (lambda: pcg.make("PDEControlGym-TrafficPDE1D", num_envs=3, device=cuda_device, simulation_type="both", T=20, dt=0.25, X=500, dx=10),
+         lambda e: e.reset(), lambda k: torch.full((3, 2), 1.2 + 0.01 * k, dtype=torch.float64, device=cuda_device)),
+        (lambda: pcg.make("PDEControlGym-BrainTumor1D", num_envs=3, device=cuda_device, total_dosage=61.2, T=600, dt=1, X=200, dx=1),
+         lambda e: e.reset(options={"init_condition": 0.8e5 * np.exp(-0.25 * xs ** 2)}), lambda k: torch.full((3,), 0.02, dtype=torch.float64, device=cuda_device)),
+        (lambda: pcg.make("PDEControlGym-NavierStokes2D", num_envs=3, device=cuda_device, boundary_condition=BC, U_ref=np.zeros((200, 21, 21, 2)),
+                          action_ref=np.ones(1000), reward_class=pcg.NSReward(), maximum_pressure_iteration=30, T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05),
+         lambda e: e.reset(options={"init": (z, z * 0.5, z * 0.1)}), lambda k: torch.full((3,), 3.0 - 0.1 * k, dtype=torch.float64, device=cuda_device)),
+    ]
+    for make, reset, act in cases:
+        env = make()
+        reset(env)
+        for k in range(3):
+            env.step(act(k))
+        sd = env.state_dict()
+        want = [env.step(act(3 + k))[:4] for k in range(3)]
+        for k in range(2):
+            env.step(act(9))                       # wander off
+        env.load_state_dict(sd)
+        got = [env.step(act(3 + k))[:4] for k in range(3)]
+        for w, g in zip(want, got):
+            assert all(torch.equal(a, b) for a, b in zip(w, g))
