@@ -74,3 +74,30 @@ class SB3VecEnvAdapter:
 
     def seed(self, seed=None):
         return [seed] * self.num_envs
+
+
+class TrajectoryRecorder:
+    """Keeps the observations of the last `max_steps` steps on the device -- the batched stand-in for the
+    reference's `env.u[t]` / `env.U[t]` history arrays that its plotting notebooks index
+    (base_env_1d.py:41, base_env_2d.py:50).  `history()` returns [steps_recorded, num_envs, ...]."""
+
+    def __init__(self, env, max_steps: int):
+        self.env, self.max_steps = env, int(max_steps)
+        self._buf, self._n = None, 0
+
+    def reset(self, *args, **kwargs):
+        obs, info = self.env.reset(*args, **kwargs)
+        self._buf = torch.empty((self.max_steps + 1,) + tuple(obs.shape), dtype=obs.dtype, device=obs.device)
+        self._buf[0].copy_(obs)
+        self._n = 1
+        return obs, info
+
+    def step(self, action):
+        out = self.env.step(action)
+        if self._n <= self.max_steps:
+            self._buf[self._n].copy_(out[0])
+            self._n += 1
+        return out
+
+    def history(self):
+        return self._buf[:self._n]
