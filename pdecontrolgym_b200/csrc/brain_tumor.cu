@@ -9,6 +9,12 @@
 // so a multi-day advance costs one HBM round trip of the row instead of one per day.
 #include "pdecg_internal.h"
 
+#ifndef PDECG_BT_MINBLOCKS
+#define PDECG_BT_MINBLOCKS 8   // 64 registers, 32 warps/SM: the single-day launch is latency/HBM-bound (measured best)
+#endif
+#ifndef PDECG_ARZ_MINBLOCKS
+#define PDECG_ARZ_MINBLOCKS 1
+#endif
 namespace pdecg {
 
 struct BtArgs {
@@ -180,7 +186,7 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, BtEnv&
 }
 
 template <int K>
-__global__ void __launch_bounds__(kThreads) bt_run_kernel(const BtArgs a) {
+__global__ void __launch_bounds__(kThreads, PDECG_BT_MINBLOCKS) bt_run_kernel(const BtArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -191,6 +197,10 @@ __global__ void __launch_bounds__(kThreads) bt_run_kernel(const BtArgs a) {
     const int nx = cfg.nx;
     const int j0 = lane * K;
 
+    // start the row load first: the scalar loads and their broadcast then overlap its latency
+    double* urow = a.buf.u + env * nx;
+    double u[K], u_raw[K];
+    load_row_issue<double, double, K>(u_raw, urow, nx, lane);
     // per-env scalars: one coalesced read, broadcast by shuffle
     int* irow = a.buf.ienv + env * PDECG_BT_NINT;
     double* frow = a.buf.fenv + env * PDECG_BT_NF64;
@@ -215,9 +225,7 @@ __global__ void __launch_bounds__(kThreads) bt_run_kernel(const BtArgs a) {
     e.rho = __shfl_sync(kFull, fv, PDECG_BT_F_RHO);
     e.last_dose = __shfl_sync(kFull, fv, PDECG_BT_F_LAST_DOSE);
 
-    double* urow = a.buf.u + env * nx;
-    double u[K];
-    load_row_chunk<double, double, K>(u, urow, nx, sm, lane);
+    load_row_finish<double, K>(u, u_raw, sm, lane);
 
     const BtDivs dv(cfg);
     double reward = 0.0;

@@ -9,6 +9,12 @@
 // between the two cells that use them -- bit-identical to the reference, which evaluates them twice.
 #include "pdecg_internal.h"
 
+#ifndef PDECG_BT_MINBLOCKS
+#define PDECG_BT_MINBLOCKS 1
+#endif
+#ifndef PDECG_ARZ_MINBLOCKS
+#define PDECG_ARZ_MINBLOCKS 10   // 48 registers, 40 warps/SM: latency/HBM-bound launch (measured best)
+#endif
 namespace pdecg {
 
 struct ArzArgs {
@@ -38,7 +44,7 @@ __device__ __forceinline__ double clipd(double v, double lo, double hi) {       
 }
 
 template <int K>
-__global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
+__global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel(const ArzArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -50,6 +56,12 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
     const int j0 = lane * K;
     const ArzCtx ctx(cfg);
 
+    // start the row loads first: the scalar load and its broadcast then overlap their latency
+    double* rrow = a.buf.ry + env * 2 * M;
+    double* yrow = rrow + M;
+    double r[K], y[K], r_raw[K], y_raw[K];
+    load_row_issue<double, double, K>(r_raw, rrow, M, lane);
+    load_row_issue<double, double, K>(y_raw, yrow, M, lane);
     double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
     const double fv = (lane < PDECG_ARZ_NF64) ? frow[lane] : 0.0;
     double time = __shfl_sync(kFull, fv, PDECG_ARZ_F_TIME);
@@ -57,11 +69,8 @@ __global__ void __launch_bounds__(kThreads) arz_step_kernel(const ArzArgs a) {
     const double vs = __shfl_sync(kFull, fv, PDECG_ARZ_F_VS);
     const double qs = __shfl_sync(kFull, fv, PDECG_ARZ_F_QS);
 
-    double* rrow = a.buf.ry + env * 2 * M;
-    double* yrow = rrow + M;
-    double r[K], y[K];
-    load_row_chunk<double, double, K>(r, rrow, M, sm, lane);
-    load_row_chunk<double, double, K>(y, yrow, M, sm, lane);
+    load_row_finish<double, K>(r, r_raw, sm, lane);
+    load_row_finish<double, K>(y, y_raw, sm, lane);
     // padding slots (never stored, never read by valid points) hold (rho, y) = (1, 1) so that the divisions
     // evaluated there stay on the fast path instead of div.rn's slow 0/0 path
 #pragma unroll
