@@ -44,9 +44,9 @@ __host__ __device__ inline int ring_len_for(int substeps) {
 // ---- per-point updates -----------------------------------------------------------------------
 // ReactionDiffusion, parabolic.py:143-144:
 //   n_j = (p_j + F*((p_{j-1} - 2 p_j) + p_{j+1})) + ((dt*beta_j) * p_j)          c = dt*beta_j (hoisted)
-// FUSED2 (float64 only): (p_{j-1} - 2 p_j) as ONE fma(-2, p_j, p_{j-1}).  2*p_j is exact, so the fma rounds
-// the same exact value as sub(p_{j-1}, mul(2, p_j)) -- bit-identical -- unless 2*p_j overflows.  The kernel
-// enables it per env only when a rigorous growth bound keeps |u| < 2^1000 for the whole control step.
+// FUSED2: (p_{j-1} - 2 p_j) as ONE fma(-2, p_j, p_{j-1}).  2*p_j is exact, so the fma rounds the same exact
+// value as sub(p_{j-1}, mul(2, p_j)) -- bit-identical -- unless 2*p_j overflows.  The kernel enables it per env
+// only over spans of substeps for which a rigorous growth bound keeps |u| far below the overflow threshold.
 template <class M, bool FUSED2 = false>
 __device__ __forceinline__ typename M::S rd_point(typename M::S pl, typename M::S p, typename M::S pr,
                                                    typename M::S F, typename M::C c) {
@@ -55,12 +55,15 @@ __device__ __forceinline__ typename M::S rd_point(typename M::S pl, typename M::
     if constexpr (M::kFast) {
         S lap = (pl - S(2) * p) + pr;
         return fmaf(c, p, fmaf(F, lap, p));
-    } else if constexpr (FUSED2) {
-        S lap = Strict<S>::add(__fma_rn(S(-2), p, pl), pr);
-        S diff = Strict<S>::add(p, Strict<S>::mul(F, lap));
-        return Strict<S>::add(diff, Strict<S>::mul(c, p));
     } else {
-        S lap = Strict<S>::add(Strict<S>::sub(pl, Strict<S>::mul(S(2), p)), pr);
+        S lap0;
+        if constexpr (FUSED2) {
+            if constexpr (sizeof(S) == 8) lap0 = __fma_rn(S(-2), p, pl);
+            else lap0 = __fmaf_rn(S(-2), p, pl);
+        } else {
+            lap0 = Strict<S>::sub(pl, Strict<S>::mul(S(2), p));
+        }
+        S lap = Strict<S>::add(lap0, pr);
         S diff = Strict<S>::add(p, Strict<S>::mul(F, lap));
         // f32 state with f64 beta: the reaction product and the final sum are evaluated in f64
         C react = Strict<C>::mul(c, static_cast<C>(p));
@@ -221,7 +224,8 @@ struct Integrator {
             for (int k = 0; k < K; ++k) u[k] = v[k];
         }
     }
-    static constexpr bool kCanFuse = (ENV == PDECG_ENV_REACTION_DIFFUSION) && !M::kFast && (sizeof(S) == 8) && (sizeof(C) == 8);
+    // float64 only: for float32 states the re-checks every ~70 substeps cost more than the saved FMUL (measured)
+    static constexpr bool kCanFuse = (ENV == PDECG_ENV_REACTION_DIFFUSION) && !M::kFast && (sizeof(S) == 8);
     bool fuse2;     // warp-uniform, set per env per control step (see rd_point)
     __device__ __forceinline__ void advance(const Bc1dArgs& a, int64_t env, int cnt) {
         if constexpr (kCanFuse) {
@@ -313,27 +317,34 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
 
     I.g = actuate<S>(a, env, S(0));               // constant over the step unless kVarDyn
     I.fuse2 = false;
+    // |n_j| <= (1 + 4F + max|c|) * max(|p|, |g|) =: rho * m, so after s substeps |u| <= m * rho^s.  A span of substeps
+    // may use the fused form while m * rho^s stays below 2^kFuseLimit (2*u_j can then never overflow).
+    constexpr double kFuseLimit = (sizeof(S) == 8) ? 1000.0 : 100.0;
+    double fuse_log2_rho = 1.0;
+    int fuse_left = 0;                             // substeps still covered by the current bound
     if constexpr (Integrator<ENV, M, K, VAR, LPE>::kCanFuse) {
-        // |n_j| <= (1 + 4F + max|c|) * max(|p|, |g|): after nsub substeps |u| <= m * rho^nsub.  Require that to
-        // stay below 2^1000 so that 2*u_j can never overflow inside this control step.
-        if (VAR != kVarDyn) {
-            double m = fabs(static_cast<double>(I.g)), cm = 0.0;
+        double cm = 0.0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                m = fmax(m, fabs(static_cast<double>(I.u[k])));      // fmax drops NaN -> checked below
-                cm = fmax(cm, fabs(static_cast<double>(I.coef[k])));
-            }
-            bool finite = true;
-#pragma unroll
-            for (int k = 0; k < K; ++k) finite = finite & (fabs(static_cast<double>(I.u[k])) < 1.0e300);
-            m = seg_max<LPE>(m, mask);
-            cm = seg_max<LPE>(cm, mask);
-            finite = __all_sync(mask, finite);
-            const double rho = 1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm;
-            const double lg = log2(fmax(m, 1.0)) + static_cast<double>(nsub) * log2(rho) * 1.0000001 + 1.0;
-            I.fuse2 = finite && (lg < 1000.0);
-        }
+        for (int k = 0; k < K; ++k) cm = fmax(cm, fabs(static_cast<double>(I.coef[k])));
+        cm = seg_max<LPE>(cm, mask);
+        fuse_log2_rho = log2(1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm) * 1.0000001 + 1e-9;
     }
+    auto fuse_span = [&]() -> int {                // substeps for which the fused form is provably exact from here
+        double m = fabs(static_cast<double>(I.g));
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double v = fabs(static_cast<double>(I.u[k]));
+            m = fmax(m, v);                        // fmax drops NaN -> caught by `finite`
+            finite = finite & (v < 1.0e300);
+        }
+        m = seg_max<LPE>(m, mask);
+        finite = __all_sync(mask, finite) && (m < 1.0e300);
+        if (!finite) return 0;
+        const double room = kFuseLimit - 1.0 - log2(fmax(m, 1.0));
+        const double span = room / fuse_log2_rho;
+        return span > 1.0e6 ? 1000000 : (span < 0.0 ? 0 : static_cast<int>(span));
+    };
 
     // reward bookkeeping that needs mid-step rows (uniform over the warp)
     const bool tuned = cfg.reward_kind == PDECG_REWARD_TUNED1D;
@@ -375,6 +386,17 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         if (want_hor) {
             int h = hor_from > done + 1 ? hor_from : done + 1;
             if (h < next) next = h;
+        }
+        if constexpr (Integrator<ENV, M, K, VAR, LPE>::kCanFuse) {
+            if (VAR != kVarDyn) {
+                if (fuse_left <= 0) {
+                    const int span = fuse_span();
+                    I.fuse2 = span >= 8;
+                    fuse_left = I.fuse2 ? span : 16;      // too close to the limit: 16 strict substeps, then re-check
+                }
+                if (done + fuse_left < next) next = done + fuse_left;
+                fuse_left -= next - done;
+            }
         }
         I.advance(a, env, next - done);
         done = next;
