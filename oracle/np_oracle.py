@@ -25,7 +25,6 @@ Differences from the reference, all deliberate:
 from __future__ import annotations
 
 import collections
-import math
 
 import numpy as np
 

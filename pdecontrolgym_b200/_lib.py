@@ -163,3 +163,12 @@ def check(rc):
 
 def launch_count() -> int:
     return int(lib().pdecg_launch_count())
+
+
+def current_raw_stream(device_index: int) -> int:
+    """cudaStream_t of torch's current stream on `device_index` (the fast private accessor when available)."""
+    import torch
+    try:
+        return torch._C._cuda_getCurrentRawStream(device_index)
+    except AttributeError:  # pragma: no cover - older/newer torch
+        return torch.cuda.current_stream(device_index).cuda_stream

@@ -178,7 +178,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return _lib.current_raw_stream(self.device.index)
 
     def _call_callback(self, fn, what):
         """Reference callbacks take `nx` and return one row; a batched callback may instead accept

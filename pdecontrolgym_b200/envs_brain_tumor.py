@@ -106,7 +106,7 @@ class BrainTumor1D(StateDictMixin):
 
     # -- plumbing ------------------------------------------------------------------------------
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return _lib.current_raw_stream(self.device.index)
 
     def _run(self, mode, action=None):
         a = self._zero_action if action is None else action

@@ -126,7 +126,7 @@ class NavierStokes2D(StateDictMixin):
         self.action_space = Box(low=-1.0, high=1.0, shape=(N, action_dim), dtype=np.float32)
 
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return _lib.current_raw_stream(self.device.index)
 
     def _field(self, x, what):
         t = x.to(self.device, torch.float64) if isinstance(x, torch.Tensor) else torch.from_numpy(

@@ -139,7 +139,7 @@ class TrafficPDE1D(StateDictMixin):
             self._fenv[mask, F_RS:F_QS + 1] = vals[mask]
 
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return _lib.current_raw_stream(self.device.index)
 
     def _reset_kernel(self, mask_t):
         with torch.cuda.device(self.device):

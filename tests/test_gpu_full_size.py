@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as O
-from tests.helpers import bc1d_case, make_ics
+from tests.helpers import make_ics
 
 pytestmark = pytest.mark.gpu
 
