@@ -327,7 +327,9 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
 #pragma unroll
         for (int k = 0; k < K; ++k) cm = fmax(cm, fabs(static_cast<double>(I.coef[k])));
         cm = seg_max<LPE>(cm, mask);
-        fuse_log2_rho = log2(1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm) * 1.0000001 + 1e-9;
+        // upper bound of log2(rho) from the exponent field (no log2() call): rho in [2^e, 2^(e+1)) -> e + 1
+        const double rho = 1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm;
+        fuse_log2_rho = static_cast<double>(static_cast<int>((static_cast<unsigned>(__double2hiint(rho)) >> 20) & 0x7ffu) - 1022);
     }
     auto fuse_span = [&]() -> int {                // substeps for which the fused form is provably exact from here
         double m = fabs(static_cast<double>(I.g));
@@ -341,8 +343,9 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         m = seg_max<LPE>(m, mask);
         finite = __all_sync(mask, finite) && (m < 1.0e300);
         if (!finite) return 0;
-        const double room = kFuseLimit - 1.0 - log2(fmax(m, 1.0));
-        const double span = room / fuse_log2_rho;
+        // log2(max(m, 1)) < (exponent of max(m, 1)) + 1, again from the exponent field
+        const int e_m = static_cast<int>((static_cast<unsigned>(__double2hiint(fmax(m, 1.0))) >> 20) & 0x7ffu) - 1022;
+        const double span = (kFuseLimit - 1.0 - static_cast<double>(e_m)) / fuse_log2_rho;
         return span > 1.0e6 ? 1000000 : (span < 0.0 ? 0 : static_cast<int>(span));
     };
 
