@@ -371,6 +371,23 @@ def run_ours(args):
         cpu_baseline = {"value": cpu_rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                         "sample": f"numpy oracle (port of the reference numpy path): {cores} worker processes x 4 envs, 400 lockstep "
                                   f"control steps over pipes (AsyncVectorEnv-equivalent), {cpu_dt:.1f} s wall"}
+        # the same integrator as compiled C with OpenMP on all host cores (oracle/c/pdecg_oracle.c): bounded sample
+        try:
+            from oracle.c_oracle import Bc1dCOracle
+            n_c, steps_c = 16384, 40
+            co = Bc1dCOracle("rd", precision="fp64", T=RD_KW["T"], dt=RD_KW["dt"], X=RD_KW["X"], dx=RD_KW["dx"],
+                             control_sample_rate=RD_KW["control_sample_rate"], normalize=True, max_control_value=20)
+            rng = np.random.default_rng(0)
+            co.reset(rng.uniform(1, 10, (n_c, 1)) * np.ones((n_c, NX_PTS)), beta_fn())
+            co.step(rng.uniform(-1, 1, n_c).astype(np.float32))
+            t0 = time.perf_counter()
+            for _ in range(steps_c):
+                co.step(rng.uniform(-1, 1, n_c).astype(np.float32))
+            dt_c = time.perf_counter() - t0
+            cpu_baseline["c_port"] = {"value": n_c * steps_c / dt_c, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                      "sample": f"oracle/c/pdecg_oracle.c (gcc -O3 -mavx2 -fopenmp, no contraction; state integrator only), {n_c} envs x {steps_c} control steps, {dt_c:.2f} s wall"}
+        except Exception as exc:  # noqa: BLE001
+            cpu_baseline["c_port"] = {"unavailable": str(exc)[:200]}
     else:
         cpu_baseline = None
 

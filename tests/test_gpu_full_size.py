@@ -118,3 +118,42 @@ def test_navier_stokes_full_batch(cuda_device):
         o_g, r_g, te_g, _, _ = genv.step(torch.from_numpy(np.tile(a, N // R)))
         assert np.array_equal(_check_tiled(o_g.cpu().numpy(), R), o_r), f"step {k}"
         np.testing.assert_allclose(_check_tiled(r_g.cpu().numpy(), R), r_r, rtol=1e-12)
+
+
+@pytest.mark.parametrize("env,N,precision", [("rd", 65536, "fp64"), ("rd", 65536, "ref"), ("tr", 1 << 18, "ref")])
+def test_bc1d_full_batch_all_distinct_vs_c_oracle(cuda_device, env, N, precision):
+    """Every env of the full-size batch has its own initial condition, beta row and action; states are compared
+    bit for bit with the plain-C oracle (oracle/c/pdecg_oracle.c, itself pinned to the numpy oracle and through
+    it to the live reference)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    from oracle.c_oracle import Bc1dCOracle
+    if env == "rd":
+        kw = dict(T=1.0, dt=1e-5, X=1.0, dx=5e-3, control_sample_rate=1e-3)
+        npts, nt_r, steps = 201, 100000, 2
+        eid = "PDEControlGym-ReactionDiffusionPDE1D"
+        base = 50 * np.cos(8 * np.arccos(np.linspace(0, 1, npts)))
+    else:
+        kw = dict(T=5.0, dt=1e-4, X=1.0, dx=1e-2, control_sample_rate=0.1)
+        npts, nt_r, steps = 100, 50000, 1
+        eid = "PDEControlGym-TransportPDE1D"
+        base = 5 * np.cos(7.35 * np.arccos(np.linspace(0, 1, npts)))
+    rng = np.random.default_rng(5)
+    bdt = np.float64 if precision == "fp64" else np.float32
+    ics = (rng.uniform(1, 10, (N, 1)) * np.ones((N, npts)) + 0.05 * rng.standard_normal((N, npts))).astype(np.float64)
+    beta = (base[None, :] * rng.uniform(0.9, 1.1, (N, 1))).astype(bdt)
+    common = dict(normalize=True, max_control_value=20, **kw)
+    genv = pcg.make(eid, num_envs=N, device=cuda_device, precision=precision, reward_class=pcg.NormReward(nt_r), copy_obs=False, **common)
+    corc = Bc1dCOracle(env, precision=precision, **common)
+    genv.reset(options={"init_condition": ics, "beta": beta})
+    corc.reset(ics, beta)
+    for k in range(steps):
+        a = rng.uniform(-1, 1, N).astype(np.float32)
+        corc.step(a)
+        o_g, r_g, te_g, tr_g, _ = genv.step(torch.from_numpy(a))
+        got = o_g.cpu().numpy()
+        assert np.array_equal(got, corc.u), f"step {k}: {np.count_nonzero((got != corc.u).any(axis=1))} of {N} envs differ"
+        # NormReward (temporal, L2) from the oracle's rows
+        want_r = -np.sqrt((corc.u.astype(np.float64) ** 2).sum(axis=1))
+        np.testing.assert_allclose(r_g.cpu().numpy(), want_r, rtol=1e-12 if precision == "fp64" else 2e-6)
+    assert (genv.time_index.cpu().numpy() == corc.t).all()
