@@ -201,21 +201,26 @@ namespace {
 struct HostPipe {
     cudaStream_t s[2] = {nullptr, nullptr};
     cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
-    int device = -1;
+    bool ready = false;
 };
-thread_local HostPipe g_pipe;
+constexpr int kMaxDevices = 64;
+thread_local HostPipe g_pipes[kMaxDevices];     // one pair of streams per (host thread, device), created on first use
 
-int ensure_pipe() {
+int ensure_pipe(HostPipe** out) {
     int dev = -1;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
-    if (g_pipe.device == dev) return PDECG_OK;
-    for (int i = 0; i < 2; ++i) {
-        if ((e = cudaStreamCreateWithFlags(&g_pipe.s[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
-        if ((e = cudaEventCreateWithFlags(&g_pipe.done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    if (dev < 0 || dev >= kMaxDevices) return fail(PDECG_ERR_UNSUPPORTED, "device index %d out of range", dev);
+    HostPipe& p = g_pipes[dev];
+    if (!p.ready) {
+        for (int i = 0; i < 2; ++i) {
+            if ((e = cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+            if ((e = cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+        }
+        if ((e = cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+        p.ready = true;
     }
-    if ((e = cudaEventCreateWithFlags(&g_pipe.start, cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
-    g_pipe.device = dev;
+    *out = &p;
     return PDECG_OK;
 }
 }  // namespace
@@ -228,7 +233,9 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
     if (rc != PDECG_OK) return rc;
     if (buf->n_envs == 0) return PDECG_OK;
     if (!action_host || !buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
-    if ((rc = ensure_pipe()) != PDECG_OK) return rc;
+    HostPipe* pipe = nullptr;
+    if ((rc = ensure_pipe(&pipe)) != PDECG_OK) return rc;
+    HostPipe& g_pipe = *pipe;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     const int64_t n = buf->n_envs;
     const size_t asz = cfg->action_dtype == PDECG_F32 ? 4 : 8;
