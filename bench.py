@@ -405,7 +405,7 @@ def run_ours(args):
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / fp64_peak_tflops, "traffic": traffic,
                      "traffic_source": "profiles/r1_rd_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full launch)",
-                     "kernel": "bc1d_step_kernel<RD, fp64, K=7>", "kernel_ms": k_ms,
+                     "kernel": "bc1d_step_kernel<RD, ModeFp64, K=13, fast, 16 lanes/env>", "kernel_ms": k_ms,
                      "kernel_share_of_step": k_ms * K / ms_total,
                      "flops_per_launch": flops_per_launch,
                      "peak_source": "in-process non-FMA DADD/DMUL issue probe (pdecg_probe_fp_issue)",
