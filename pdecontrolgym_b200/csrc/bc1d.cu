@@ -94,13 +94,7 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     if (cfg->action_dtype != PDECG_F32 && cfg->action_dtype != PDECG_F64) return fail(PDECG_ERR_INVALID, "bad action_dtype");
     if (cfg->precision == PDECG_PREC_REF && cfg->beta_dtype != PDECG_F32 && cfg->beta_dtype != PDECG_F64) return fail(PDECG_ERR_INVALID, "bad beta_dtype");
     if (cfg->reward_kind == PDECG_REWARD_TUNED1D) {
-        // O(1) replacement of the history look-back needs the row t-100 to sit on a step boundary or
-        // inside the current step
-        const int S = cfg->substeps;
-        if (S >= 1 && S < kLookback && kLookback % S != 0)
-            return fail(PDECG_ERR_UNSUPPORTED, "TunedReward1D: substeps per control step (%d) must divide 100 or be >= 100", S);
-        if (S >= 1 && (cfg->nt - 1) % S != 0)
-            return fail(PDECG_ERR_UNSUPPORTED, "TunedReward1D: (nt-1)=%d must be a multiple of substeps=%d", cfg->nt - 1, S);
+        // the look-back row t-100 wraps onto an already written row when nt <= 100: not representable without history
         if (cfg->nt <= kLookback) return fail(PDECG_ERR_UNSUPPORTED, "TunedReward1D: nt must exceed 100");
     } else if (cfg->reward_kind == PDECG_REWARD_NORM) {
         if (cfg->norm_ord < PDECG_NORM_L1 || cfg->norm_ord > PDECG_NORM_LINF) return fail(PDECG_ERR_INVALID, "NormReward: norm must be 1, 2 or inf");
@@ -118,7 +112,8 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     out->cfg = *cfg;
     out->buf = *buf;
     out->npts = pdecg_bc1d_npts(cfg);
-    out->ring_len = ring_len_for(cfg->substeps);
+    out->tuned_general = (cfg->reward_kind == PDECG_REWARD_TUNED1D && tuned_needs_general_ring(cfg->substeps, cfg->nt)) ? 1 : 0;
+    out->ring_len = out->tuned_general ? kLookback + 1 : ring_len_for(cfg->substeps);
     out->carry_len = 1 + out->ring_len;
     if ((out->npts + 31) / 32 > 8) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", out->npts);
     return PDECG_OK;
@@ -143,6 +138,7 @@ extern "C" int32_t pdecg_bc1d_npts(const pdecg_bc1d_cfg* cfg) {
 
 extern "C" int32_t pdecg_bc1d_carry_len(const pdecg_bc1d_cfg* cfg) {
     if (!cfg) return 0;
+    if (cfg->reward_kind == PDECG_REWARD_TUNED1D && tuned_needs_general_ring(cfg->substeps, cfg->nt)) return 1 + kLookback + 1;
     return 1 + ring_len_for(cfg->substeps);
 }
 

@@ -27,6 +27,7 @@ struct Bc1dArgs {
     int npts;
     int carry_len;
     int ring_len;   // TunedReward1D look-back ring (entries) -- see carry layout below
+    int tuned_general;   // 1: ring of the last 101 per-SUBSTEP norms (any substep count; slow path)
 };
 
 // carry layout (doubles, per env):
@@ -39,6 +40,14 @@ constexpr int kLookback = 100;
 
 __host__ __device__ inline int ring_len_for(int substeps) {
     return (substeps >= 1 && substeps <= kLookback && kLookback % substeps == 0) ? kLookback / substeps : 1;
+}
+// TunedReward1D needs ||u[t-100]||.  Fast layouts exist when row t-100 is a step boundary (substeps | 100) or lies
+// inside the current step (substeps >= 100) and episodes end on a step boundary; every other configuration keeps
+// the norms of the last 101 substeps in the carry and recomputes the norm after EVERY substep (general, slow).
+__host__ __device__ inline bool tuned_needs_general_ring(int substeps, int nt) {
+    if (substeps < 1) return false;
+    if (substeps < kLookback && kLookback % substeps != 0) return true;
+    return (nt - 1) % substeps != 0;
 }
 
 // ---- per-point updates -----------------------------------------------------------------------
@@ -351,7 +360,8 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
 
     // reward bookkeeping that needs mid-step rows (uniform over the warp)
     const bool tuned = cfg.reward_kind == PDECG_REWARD_TUNED1D;
-    const int snap_at = (tuned && cfg.substeps > kLookback) ? nsub - kLookback : -1;   // substeps done when row t-100 is live
+    const bool ring_every = tuned && a.tuned_general;
+    const int snap_at = (tuned && !ring_every && cfg.substeps > kLookback) ? nsub - kLookback : -1;   // substeps done when row t-100 is live
     const bool want_diff = !tuned && cfg.horizon == PDECG_HORIZON_DIFFERENTIAL && nsub > 0;
     const bool want_hor = !tuned && cfg.horizon == PDECG_HORIZON_T;
     const int hor_m = t_end > cfg.t_horizon_length ? cfg.t_horizon_length : t_end;   // norm_reward.py:65-72
@@ -368,6 +378,10 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         // ---- events at the current row (after `done` substeps) ----
         if (VAR == kVarFast && done == 1) I.fix_boundaries();
         if (done == snap_at) lb_norm = sqrt(chunk_sumsq<S, K, LPE>(I.u, j0, npts, mask));
+        if (ring_every && done >= 1) {             // general look-back: norm of every row, ring indexed by t mod 101
+            const double nrm = static_cast<double>(static_cast<S>(sqrt(chunk_sumsq<S, K, LPE>(I.u, j0, npts, mask))));
+            if (lane == 0) carry[1 + (t0 + done) % (kLookback + 1)] = nrm;
+        }
         if (want_hor && done >= hor_from && done >= 1)
             hor_acc += static_cast<double>(static_cast<S>(chunk_norm<S, K, LPE>(I.u, j0, npts, cfg.norm_ord, mask)));
         if (want_diff && done == nsub) {
@@ -385,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         int next = nsub;
         if (VAR == kVarFast && done == 0) next = 1;
         if (snap_at > done && snap_at < next) next = snap_at;
+        if (ring_every) next = done + 1;
         if (want_diff && nsub - 1 > done && nsub - 1 < next) next = nsub - 1;
         if (want_hor) {
             int h = hor_from > done + 1 ? hor_from : done + 1;
@@ -423,7 +438,10 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     double reward;
     if (tuned) {
         // look-back norm from the ring when the row t-100 sits on an earlier step boundary
-        if (cfg.substeps <= kLookback && cfg.substeps >= 1) {
+        if (ring_every) {
+            __syncwarp(mask);
+            lb_norm = (t_end - kLookback >= 0) ? carry[1 + (t_end - kLookback) % (kLookback + 1)] : 0.0;
+        } else if (cfg.substeps <= kLookback && cfg.substeps >= 1) {
             const int slot = 1 + ((t_end / cfg.substeps) % a.ring_len);
             lb_norm = carry[slot];
             __syncwarp(mask);

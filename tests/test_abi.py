@@ -74,8 +74,11 @@ def test_invalid_configs_are_rejected_without_a_gpu(lib):
     cfg.abi_version = lib.ABI_VERSION
     cfg.env, cfg.nx, cfg.nt, cfg.substeps, cfg.dt, cfg.dx = 0, 100, 10001, 30, 1e-4, 1e-2
     cfg.reward_kind, cfg.reward_nt = 0, 10000
-    assert L.pdecg_bc1d_step(ctypes.byref(cfg), ctypes.byref(buf), None) == lib.ERR_UNSUPPORTED  # 30 does not divide 100
+    assert lib.lib().pdecg_bc1d_carry_len(ctypes.byref(cfg)) == 102      # 30 does not divide 100: general 101-entry ring
+    cfg.nt = 50
+    assert L.pdecg_bc1d_step(ctypes.byref(cfg), ctypes.byref(buf), None) == lib.ERR_UNSUPPORTED  # look-back wraps onto written rows
     assert b"TunedReward1D" in L.pdecg_last_error()
+    cfg.nt = 10001
     cfg.substeps = 1000
     cfg.nx = 400
     assert L.pdecg_bc1d_step(ctypes.byref(cfg), ctypes.byref(buf), None) == lib.ERR_UNSUPPORTED

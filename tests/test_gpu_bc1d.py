@@ -179,3 +179,40 @@ def test_step_host_matches_device_step(cuda_device, N):
         assert np.array_equal(r.cpu().numpy(), rew_h.numpy())
         assert np.array_equal(te.cpu().numpy(), te_h.numpy().astype(bool)) and np.array_equal(tr.cpu().numpy(), tr_h.numpy().astype(bool))
     assert te_h.all()
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("sub,steps,extra", [(30, 6, 0), (7, 20, 3), (100, 3, 40), (150, 2, 77), (64, 4, 0)])
+def test_tuned_reward_any_substep_count(cuda_device, env, sub, steps, extra):
+    """TunedReward1D look-back (||u[t-100]||) for substep counts that neither divide 100 nor exceed it, and for
+    episodes whose last control step is cut short (nt-1 not a multiple of substeps): general 101-entry ring."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    nx = 40
+    dx = 1.0 / nx
+    dt = 0.4 * dx * dx if env == "rd" else dx / 100
+    npts = nx + 1 if env == "rd" else nx
+    n_sub_total = sub * steps + extra
+    T = dt * n_sub_total
+    nt = int(round(T / dt) + 1)
+    assert nt - 1 == n_sub_total and nt > 100
+    kw = dict(T=T, dt=dt, X=1, dx=dx, control_sample_rate=dt * sub, normalize=True, max_control_value=20)
+    rng = np.random.default_rng(sub)
+    B = 4
+    ics = make_ics(rng, B, npts)
+    beta = np.cos(np.linspace(0, 3, npts)).astype(np.float32)
+    Orc = O.ReactionDiffusionOracle if env == "rd" else O.TransportOracle
+    oenv = Orc(B, reward=O.TunedReward1DSpec(nt - 1, -1e3, 3e2), **kw)
+    eid = "PDEControlGym-ReactionDiffusionPDE1D" if env == "rd" else "PDEControlGym-TransportPDE1D"
+    genv = pcg.make(eid, num_envs=B, device=cuda_device, reward_class=pcg.TunedReward1D(nt - 1, -1e3, 3e2), **kw)
+    oenv.reset(ics, beta)
+    genv.reset(options={"init_condition": ics, "beta": beta})
+    n_calls = steps + (1 if extra else 0)
+    for k in range(n_calls):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        o_r, r_r, te_r, tr_r = oenv.step(a)
+        o_g, r_g, te_g, tr_g, _ = genv.step(torch.from_numpy(a))
+        assert np.array_equal(o_g.cpu().numpy(), o_r) and np.array_equal(te_g.cpu().numpy(), te_r)
+        scale = 2 * np.sqrt((oenv.u.astype(np.float64) ** 2).sum(axis=1)) + np.abs(r_r)
+        assert_rewards_close(r_g.cpu().numpy(), r_r, scale, TOL_F32_REDUCTION, f"call {k}")
+    assert te_r.all()

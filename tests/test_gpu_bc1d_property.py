@@ -19,7 +19,7 @@ def configs(draw):
     env = draw(st.sampled_from(["rd", "tr"]))
     nx = draw(st.integers(4, 254))
     reward = draw(st.sampled_from(["tuned", "temporal1", "temporal2", "temporalinf", "differential2"]))
-    sub = draw(st.sampled_from(SUBSTEPS_TUNED)) if reward == "tuned" else draw(st.integers(1, 130))
+    sub = draw(st.sampled_from(SUBSTEPS_TUNED + [3, 7, 30, 33, 64, 99, 101, 130])) if reward == "tuned" else draw(st.integers(1, 130))
     steps = draw(st.integers(2, 5))
     if reward == "tuned" and sub * steps <= 100:
         steps = 100 // sub + 2                 # the oracle needs nt > 100
