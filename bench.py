@@ -289,7 +289,7 @@ def run_ours(args):
     ms_total = start.elapsed_time(stop)
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     gaps = [ev[i][1].elapsed_time(ev[i + 1][0]) for i in range(K - 1)]   # non-kernel time between step kernels
-    if rank == 0:
+    if rank == 0 and gaps:
         gs = sorted(gaps)
         print(f"[bench] step-kernel ms: median {np.median(kern_ms):.4f} max {max(kern_ms):.4f}; inter-kernel gap ms: "
               f"median {gs[len(gs)//2]:.4f} p90 {gs[int(0.9*len(gs))]:.4f} max {gs[-1]:.4f} sum {sum(gs):.2f}; "
