@@ -115,7 +115,7 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     out->tuned_general = (cfg->reward_kind == PDECG_REWARD_TUNED1D && tuned_needs_general_ring(cfg->substeps, cfg->nt)) ? 1 : 0;
     out->ring_len = out->tuned_general ? kLookback + 1 : ring_len_for(cfg->substeps);
     out->carry_len = 1 + out->ring_len;
-    if ((out->npts + 31) / 32 > 8) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", out->npts);
+    if (out->npts > 512) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 512 points per env", out->npts);
     return PDECG_OK;
 }
 

@@ -508,7 +508,7 @@ inline void pick_variant(const Bc1dArgs& a, int* LPE, int* K, int* var) {
     const int k32 = (a.npts + 31) / 32, k16 = (a.npts + 15) / 16;
     const bool half = !dyn && (k16 == 7 || k16 == 13) && (k16 < 2 * k32) && !getenv("PDECG_BC1D_NO_HALFWARP");
     *LPE = half ? 16 : 32;
-    *K = half ? k16 : k32;
+    *K = half ? k16 : (k32 <= 8 ? k32 : ((k32 + 1) / 2) * 2);     // 257..512 points: even K in {10, 12, 14, 16}
     // the frozen-slot variant zeroes the halos of the segment's edge lanes, so it is valid for every npts <= LPE*K
     *var = dyn ? kVarDyn : (getenv("PDECG_BC1D_SAFE") ? kVarSafe : kVarFast);
 }
@@ -529,6 +529,7 @@ inline int launch_k(const Bc1dArgs& a, int LPE, int K, cudaStream_t st) {
         switch (K) {
 #define PDECG_CASE(KK) case KK: bc1d_step_kernel<ENV, M, KK, VAR, 32><<<grid, kThreads, 0, st>>>(a); break;
             PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
+            PDECG_CASE(10) PDECG_CASE(12) PDECG_CASE(14) PDECG_CASE(16)
 #undef PDECG_CASE
             default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
         }

@@ -80,7 +80,7 @@ def test_invalid_configs_are_rejected_without_a_gpu(lib):
     assert b"TunedReward1D" in L.pdecg_last_error()
     cfg.nt = 10001
     cfg.substeps = 1000
-    cfg.nx = 400
+    cfg.nx = 600
     assert L.pdecg_bc1d_step(ctypes.byref(cfg), ctypes.byref(buf), None) == lib.ERR_UNSUPPORTED
     assert b"register-resident" in L.pdecg_last_error()
     acfg = lib.ArzCfg()

@@ -86,11 +86,9 @@ def test_reward_kinds(cuda_device, env, rk):
 
 
 @pytest.mark.parametrize("env", ["rd", "tr"])
-@pytest.mark.parametrize("nx", [8, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 160, 191, 192, 200, 223, 224, 255])
+@pytest.mark.parametrize("nx", [8, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 160, 191, 192, 200, 223, 224, 255, 256, 300, 384, 447, 511])
 def test_grid_sizes(cuda_device, env, nx):
-    """Every points-per-lane instantiation (K = 1..8), incl. sizes that are not multiples of 32."""
-    if env == "rd" and nx + 1 > 256:
-        pytest.skip("exceeds register-resident limit")
+    """Every points-per-lane instantiation (K = 1..8, 10, 12, 14, 16), incl. sizes that are not multiples of 32."""
     for precision, bd in (("ref", np.float32), ("ref", np.float64), ("fp64", np.float64)):
         run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), False, bd, np.float32, "tuned",
                  nx=nx, B=3, steps=4)
@@ -146,11 +144,11 @@ def test_empty_batch_and_errors(cuda_device):
         pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=1, device=cuda_device, sensing_loc="opposite",
                  sensing_type="Dirchilet", reward_class=pcg.TunedReward1D(nt - 1), **kw)
     kw2 = dict(kw)
-    kw2["dx"] = 1.0 / 400
+    kw2["dx"] = 1.0 / 600
     big = pcg.make("PDEControlGym-TransportPDE1D", num_envs=1, device=cuda_device,
                    reward_class=pcg.NormReward(nt - 1), **kw2)
     with pytest.raises(PdecgError, match="register-resident"):
-        big.reset(options={"init_condition": np.zeros(400), "beta": np.zeros(400)})
+        big.reset(options={"init_condition": np.zeros(600), "beta": np.zeros(600)})
 
 
 @pytest.mark.parametrize("N", [3, 4099, 20001])

@@ -17,7 +17,7 @@ SUBSTEPS_TUNED = [1, 2, 4, 5, 10, 20, 25, 50, 100, 150, 300]
 @st.composite
 def configs(draw):
     env = draw(st.sampled_from(["rd", "tr"]))
-    nx = draw(st.integers(4, 254))
+    nx = draw(st.one_of(st.integers(4, 254), st.integers(255, 510)))
     reward = draw(st.sampled_from(["tuned", "temporal1", "temporal2", "temporalinf", "differential2"]))
     sub = draw(st.sampled_from(SUBSTEPS_TUNED + [3, 7, 30, 33, 64, 99, 101, 130])) if reward == "tuned" else draw(st.integers(1, 130))
     steps = draw(st.integers(2, 5))
