@@ -105,6 +105,8 @@ typedef struct {
     int32_t* time_index;     /* [n_envs] -- substeps done this episode (the reference's self.time_index) */
     double* carry;           /* [n_envs, pdecg_bc1d_carry_len(cfg)] -- O(1) replacement of the u[nt,nx]
                                 history the reference rewards index into                    */
+    void* obs_copy;          /* optional [n_envs, npts] S: the step / reset kernels also store the new state here,
+                                so a caller gets a private full-state observation without a separate device copy */
 } pdecg_bc1d_buffers;
 
 /* Number of doubles of reward carry per env for this configuration. */

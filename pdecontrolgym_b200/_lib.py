@@ -43,7 +43,7 @@ class Bc1dBuffers(C.Structure):
         ("n_envs", C.c_int64), ("u", C.c_void_p), ("beta", C.c_void_p), ("beta_env_stride", C.c_int64),
         ("action", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
         ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("time_index", C.c_void_p),
-        ("carry", C.c_void_p),
+        ("carry", C.c_void_p), ("obs_copy", C.c_void_p),
     ]
 
 

@@ -40,9 +40,11 @@ __global__ void __launch_bounds__(kThreads) bc1d_reset_kernel(const Bc1dArgs a, 
     };
     double ss = 0.0;
     S last = S(0), first = S(0), second = S(0), blast = S(0);
+    S* crow = a.buf.obs_copy ? static_cast<S*>(a.buf.obs_copy) + env * npts : nullptr;
     for (int j = lane; j < npts; j += 32) {
         S v = ic(j);
         urow[j] = v;
+        if (crow) crow[j] = v;
         double dv = static_cast<double>(v);
         ss += dv * dv;
     }
@@ -261,6 +263,7 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
         b.truncated = buf->truncated + lo;
         b.time_index = buf->time_index + lo;
         b.carry = buf->carry + lo * a.carry_len;
+        b.obs_copy = nullptr;                                  // the host path copies straight from the state
         if ((e = cudaMemcpyAsync(const_cast<void*>(b.action), off(action_host, lo * asz), cnt * asz, cudaMemcpyHostToDevice, st)) != cudaSuccess)
             return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
         if ((rc = pdecg_bc1d_step(cfg, &b, st)) != PDECG_OK) return rc;

@@ -162,8 +162,12 @@ struct Integrator {
 
     __device__ __forceinline__ explicit Integrator(S dx) : by_dx(dx) {}
 
-    template <bool FUSED2>
+    // WIDE: both envs of a half-warp pair run this loop in lock step (see `wide` in the kernel), so the shuffles
+    // may name the whole warp with a compile-time mask -- a run-time member mask costs ~6 extra instructions
+    // per substep (MATCH/REDUX/VOTE convergence check emitted by the compiler).
+    template <bool FUSED2, bool WIDE>
     __device__ __forceinline__ void substep(const Bc1dArgs& a, int64_t env, const S (&p)[K], S (&n)[K]) {
+        const unsigned mask = WIDE ? kFull : this->mask;
         if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
             if constexpr (VAR == kVarDyn) {
                 g = actuate<S>(a, env, row_value<S, K, LPE>(p, jb - 1, mask));
@@ -192,6 +196,7 @@ struct Integrator {
             // per substep; operands outside the window (zero, denormal, inf, ...) redo the chunk exactly
             S x[K], dq[K];
             bool ok = true;
+            [[maybe_unused]] float xmin = 0x1p100f, xmax = 0.0f;  // float states: min/max |x| (3-input FMNMX3), one test
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const S pr = (k == K - 1) ? hr : p[k < K - 1 ? k + 1 : K - 1];
@@ -200,9 +205,15 @@ struct Integrator {
                 } else {
                     x[k] = Strict<S>::sub(pr, p[k]);
                     dq[k] = by_dx.fast(x[k]);
-                    ok = ok & by_dx.in_range(x[k]);
+                    if constexpr (sizeof(S) == 4) {
+                        xmin = fminf(xmin, fabsf(x[k]));     // NaNs drop out here: the fast tail maps NaN -> NaN
+                        xmax = fmaxf(xmax, fabsf(x[k]));     // (canonical) exactly like the division does
+                    } else {
+                        ok = ok & by_dx.in_range(x[k]);
+                    }
                 }
             }
+            if constexpr (!M::kFast && sizeof(S) == 4) ok = by_dx.in_range_minmax(xmin, xmax);
             if constexpr (!M::kFast) {
                 if (!ok) {
 #pragma unroll
@@ -219,28 +230,37 @@ struct Integrator {
     }
 
     // `cnt` substeps in place (register ping-pong: no copies in the steady state)
-    template <bool FUSED2>
+    template <bool FUSED2, bool WIDE>
     __device__ __forceinline__ void advance_t(const Bc1dArgs& a, int64_t env, int cnt) {
         S v[K];
         int i = 0;
         for (; i + 2 <= cnt; i += 2) {
-            substep<FUSED2>(a, env, u, v);
-            substep<FUSED2>(a, env, v, u);
+            substep<FUSED2, WIDE>(a, env, u, v);
+            substep<FUSED2, WIDE>(a, env, v, u);
         }
         if (i < cnt) {
-            substep<FUSED2>(a, env, u, v);
+            substep<FUSED2, WIDE>(a, env, u, v);
 #pragma unroll
             for (int k = 0; k < K; ++k) u[k] = v[k];
         }
     }
     // float64 only: for float32 states the re-checks every ~70 substeps cost more than the saved FMUL (measured)
     static constexpr bool kCanFuse = (ENV == PDECG_ENV_REACTION_DIFFUSION) && !M::kFast && (sizeof(S) == 8);
+    static constexpr bool kCanWide = (LPE == 16);   // LPE == 32: the member mask is already a constant
     bool fuse2;     // warp-uniform, set per env per control step (see rd_point)
-    __device__ __forceinline__ void advance(const Bc1dArgs& a, int64_t env, int cnt) {
+    bool wide;      // warp-uniform: the warp's two envs take identical control flow this step
+    template <bool WIDE>
+    __device__ __forceinline__ void advance_w(const Bc1dArgs& a, int64_t env, int cnt) {
         if constexpr (kCanFuse) {
-            if (fuse2) { advance_t<true>(a, env, cnt); return; }
+            if (fuse2) { advance_t<true, WIDE>(a, env, cnt); return; }
         }
-        advance_t<false>(a, env, cnt);
+        advance_t<false, WIDE>(a, env, cnt);
+    }
+    __device__ __forceinline__ void advance(const Bc1dArgs& a, int64_t env, int cnt) {
+        if constexpr (kCanWide) {
+            if (wide) { advance_w<true>(a, env, cnt); return; }
+        }
+        advance_w<false>(a, env, cnt);
     }
 
     // write the boundary values the reference assigns explicitly
@@ -321,6 +341,15 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
     nsub = nsub < 0 ? 0 : (nsub > cfg.substeps ? cfg.substeps : nsub);
     const int t_end = t0 + nsub;
 
+    // Half-warp pairs: when both envs exist and sit at the same time index, everything that steers the substep
+    // loop below is identical for the two segments (the configuration is uniform over the batch and the fused-form
+    // spans are then evaluated over the whole warp), so the loop runs in lock step and may use full-warp masks.
+    I.wide = false;
+    if constexpr (Integrator<ENV, M, K, VAR, LPE>::kCanWide) {
+        if ((env | 1) < a.buf.n_envs)                 // warp-uniform: both envs of this warp exist -> 32 lanes here
+            I.wide = __all_sync(kFull, t0 == __shfl_xor_sync(kFull, t0, 16));
+    }
+
     double* carry = a.buf.carry + env * a.carry_len;
     double bsum = carry[0];
 
@@ -349,8 +378,13 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
             m = fmax(m, v);                        // fmax drops NaN -> caught by `finite`
             finite = finite & (v < 1.0e300);
         }
-        m = seg_max<LPE>(m, mask);
-        finite = __all_sync(mask, finite) && (m < 1.0e300);
+        if (I.wide) {                               // one (conservative) bound for both envs keeps them in lock step
+            m = seg_max<32>(m, kFull);
+            finite = __all_sync(kFull, finite) && (m < 1.0e300);
+        } else {
+            m = seg_max<LPE>(m, mask);
+            finite = __all_sync(mask, finite) && (m < 1.0e300);
+        }
         if (!finite) return 0;
         // log2(max(m, 1)) < (exponent of max(m, 1)) + 1, again from the exponent field
         const int e_m = static_cast<int>((static_cast<unsigned>(__double2hiint(fmax(m, 1.0))) >> 20) & 0x7ffu) - 1022;
@@ -427,6 +461,8 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         if constexpr (VAR == kVarFast) I.fix_boundaries();   // frozen slots may have absorbed a NaN/inf neighbour
         store_row_chunk<S, K, LPE>(I.u, urow, npts, sm, lane, mask);
     }
+    if (a.buf.obs_copy != nullptr)                           // private observation for the caller (no separate device copy)
+        store_row_chunk<S, K, LPE>(I.u, static_cast<S*>(a.buf.obs_copy) + env * npts, npts, sm, lane, mask);
     S (&u)[K] = I.u;
 
     const double sumsq = chunk_sumsq<S, K, LPE>(u, j0, npts, mask);

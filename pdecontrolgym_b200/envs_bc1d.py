@@ -97,7 +97,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         self.max_control_value = max_control_value
         self.control_sample_rate = control_sample_rate
         self.autoreset = bool(autoreset)
-        self.copy_obs = bool(copy_obs)   # False: full-state observations are zero-copy views of the live state
+        self.copy_obs = bool(copy_obs)   # False: step outputs are zero-copy views of live buffers (overwritten by the next step)
         self.env_id_offset = int(env_id_offset)   # global index of env 0 (multi-GPU sharding)
         self._seed, self._random_ic = 0, None
         # same messages as hyperbolic.py:60-62,87-89,122-124 / parabolic.py:85,114
@@ -320,20 +320,42 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         a = self._prep_action(action)
         self._cfg.action_dtype = _lib.F64 if a.dtype == torch.float64 else _lib.F32
         self._buf.action = a.data_ptr()
+        # full-state observation copies are written by the kernels themselves into a fresh tensor (no clone launch)
+        obs_out = None
+        if self.copy_obs and self.sensing_loc == "full":
+            obs_out = torch.empty_like(self.u)
+            self._buf.obs_copy = obs_out.data_ptr()
+        reward, term_u8, trunc_u8 = self._reward, self._terminated, self._truncated
+        if self.copy_obs:
+            # the kernel writes reward / flags straight into fresh tensors handed to the caller (no clone launches)
+            reward, term_u8, trunc_u8 = torch.empty_like(reward), torch.empty_like(term_u8), torch.empty_like(trunc_u8)
+            self._buf.reward, self._buf.terminated, self._buf.truncated = reward.data_ptr(), term_u8.data_ptr(), trunc_u8.data_ptr()
         ke = self._kernel_events          # optional (start, stop) CUDA events bracketing only the step kernel
-        with torch.cuda.device(self.device):
-            if ke is not None:
-                ke[0].record()
-            _lib.check(self._L.pdecg_bc1d_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
-            if ke is not None:
-                ke[1].record()
-        terminated = self._terminated.bool()
-        truncated = self._truncated.bool()
-        reward = self._reward.clone()
-        info = {}
-        if self.autoreset:
-            torch.bitwise_or(self._terminated, self._truncated, out=self._done)
-            self._reset_kernel(self._done)   # same-step autoreset: finished envs restart from their IC
+        try:
+            with torch.cuda.device(self.device):
+                if ke is not None:
+                    ke[0].record()
+                _lib.check(self._L.pdecg_bc1d_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
+                if ke is not None:
+                    ke[1].record()
+            # the auto-reset below clears reward / flags of the envs it restarts: point it at the internal buffers
+            self._buf.reward, self._buf.terminated, self._buf.truncated = (
+                self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr())
+            # copy_obs: fresh tensors (above); otherwise zero-copy views the next step overwrites
+            terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
+            info = {}
+            if self.autoreset:
+                torch.bitwise_or(term_u8, trunc_u8, out=self._done)
+                if not self.copy_obs:       # the reset would clear the views being returned
+                    terminated, truncated, reward = terminated.clone(), truncated.clone(), reward.clone()
+                self._reset_kernel(self._done)   # same-step autoreset: finished envs restart from their IC
+        finally:
+            self._buf.obs_copy = None            # never leave a pointer to a caller-owned tensor behind
+            self._buf.reward, self._buf.terminated, self._buf.truncated = (
+                self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr())
+        if obs_out is not None:
+            obs = obs_out if self.sensing_noise_func is None else self.sensing_noise_func(obs_out)
+            return obs, reward, terminated, truncated, info
         return self._sense(), reward, terminated, truncated, info
 
     def step_host(self, action_host, obs_host=None, reward_host=None, terminated_host=None, truncated_host=None):
