@@ -135,6 +135,24 @@ int pdecg_bc1d_reset_random(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers*
  * tuned_reward_1d.py:25-40, norm_reward.py:29-73) for all n_envs in one launch. */
 int pdecg_bc1d_step(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, pdecg_stream_t stream);
 
+/* Same-step auto-reset fused into the step launch (the vector-env convention of gymnasium's AsyncVectorEnv
+ * NextStep/SameStep wrappers around the reference envs): envs that come out of this step terminated or
+ * truncated are re-initialised exactly as pdecg_bc1d_reset (random == 0) / pdecg_bc1d_reset_random
+ * (random != 0) with mask = terminated | truncated would do right after it -- state row, obs / obs_copy,
+ * carry, time_index, episode counter -- while reward / terminated / truncated keep the step's values. */
+typedef struct pdecg_bc1d_autoreset {
+    const void* init;        /* [n_envs or 1, npts] initial rows (random == 0) or the [1, npts] profile (random != 0) */
+    int32_t init_dtype;      /* PDECG_F32 / PDECG_F64 */
+    int32_t random;
+    int64_t init_env_stride; /* elements between env rows of `init` (0 = shared row); ignored when random != 0   */
+    double lo, hi;           /* random != 0: c_env ~ U(lo, hi)                                                   */
+    uint64_t seed;
+    int64_t env_id_offset;
+    int32_t* episode;        /* random != 0: [n_envs] episode counters                                           */
+} pdecg_bc1d_autoreset;
+int pdecg_bc1d_step_autoreset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
+                              const pdecg_bc1d_autoreset* autoreset, pdecg_stream_t stream);
+
 /* Same step, but `action_host` ([n_envs], cfg.action_dtype) and the outputs are HOST buffers:
  * H2D(actions) -> kernel -> D2H(obs, reward, flags), all on `stream`, then stream-synchronised.
  * obs_host is [n_envs, npts] S for FULL sensing, [n_envs] S otherwise; any output pointer may be

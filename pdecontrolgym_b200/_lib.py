@@ -47,6 +47,14 @@ class Bc1dBuffers(C.Structure):
     ]
 
 
+class Bc1dAutoReset(C.Structure):
+    _fields_ = [
+        ("init", C.c_void_p), ("init_dtype", C.c_int32), ("random", C.c_int32), ("init_env_stride", C.c_int64),
+        ("lo", C.c_double), ("hi", C.c_double), ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
+        ("episode", C.c_void_p),
+    ]
+
+
 class BtCfg(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("nx", C.c_int32), ("nt", C.c_int32), ("weekends", C.c_int32),
@@ -121,6 +129,8 @@ def lib():
     L.pdecg_bc1d_carry_len.restype = C.c_int32
     L.pdecg_bc1d_step.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.c_void_p]
     L.pdecg_bc1d_step.restype = C.c_int
+    L.pdecg_bc1d_step_autoreset.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.POINTER(Bc1dAutoReset), C.c_void_p]
+    L.pdecg_bc1d_step_autoreset.restype = C.c_int
     L.pdecg_bc1d_reset.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.c_void_p, C.c_int32,
                                    C.c_int64, C.c_void_p, C.c_void_p]
     L.pdecg_bc1d_reset.restype = C.c_int

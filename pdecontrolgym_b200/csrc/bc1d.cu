@@ -8,14 +8,6 @@
 namespace pdecg {
 
 // ---- reset -------------------------------------------------------------------------------------
-struct RandomIc {          // optional: u <- c * profile with c ~ U(lo, hi) from Philox (pdecg_bc1d_reset_random)
-    int enabled;
-    double lo, hi;
-    uint64_t seed;
-    int64_t env_id_offset;
-    int32_t* episode;
-};
-
 template <typename S, typename I>
 __global__ void __launch_bounds__(kThreads) bc1d_reset_kernel(const Bc1dArgs a, const I* __restrict__ init,
                                                              int64_t init_stride, const uint8_t* __restrict__ mask,
@@ -24,55 +16,7 @@ __global__ void __launch_bounds__(kThreads) bc1d_reset_kernel(const Bc1dArgs a, 
     const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
     if (env >= a.buf.n_envs) return;
     if (mask != nullptr && mask[env] == 0) return;
-    const int npts = a.npts;
-    S* urow = static_cast<S*>(a.buf.u) + env * npts;
-    const I* irow = init + env * init_stride;
-    double scale = 1.0;
-    if (rnd.enabled) {
-        const int ep = rnd.episode[env];
-        const double u01 = Philox4x32::uniform53(rnd.seed, static_cast<uint64_t>(rnd.env_id_offset + env), static_cast<uint32_t>(ep));
-        scale = __dadd_rn(rnd.lo, __dmul_rn(__dsub_rn(rnd.hi, rnd.lo), u01));
-        __syncwarp();
-        if (lane == 0) rnd.episode[env] = ep + 1;
-    }
-    auto ic = [&](int j) -> S {                        // `u[0] = init_condition` casts to the state dtype
-        return rnd.enabled ? static_cast<S>(__dmul_rn(scale, static_cast<double>(irow[j]))) : static_cast<S>(irow[j]);
-    };
-    double ss = 0.0;
-    S last = S(0), first = S(0), second = S(0), blast = S(0);
-    S* crow = a.buf.obs_copy ? static_cast<S*>(a.buf.obs_copy) + env * npts : nullptr;
-    for (int j = lane; j < npts; j += 32) {
-        S v = ic(j);
-        urow[j] = v;
-        if (crow) crow[j] = v;
-        double dv = static_cast<double>(v);
-        ss += dv * dv;
-    }
-    ss = warp_sum(ss);
-    if (npts >= 1) last = ic(npts - 1);
-    if (npts >= 2) blast = ic(npts - 2);
-    first = ic(0);
-    if (npts >= 2) second = ic(1);
-    if (lane == 0) {
-        double* carry = a.buf.carry + env * a.carry_len;
-        carry[0] = fabs(static_cast<double>(last));    // row 0 of uVec[:, -1]
-        for (int i = 1; i < a.carry_len; ++i) carry[i] = 0.0;
-        carry[1] = static_cast<double>(static_cast<S>(sqrt(ss)));   // ||u_0||: ring slot of step 0
-        a.buf.time_index[env] = 0;
-        a.buf.reward[env] = 0.0;
-        a.buf.terminated[env] = 0;
-        a.buf.truncated[env] = 0;
-        const pdecg_bc1d_cfg& c = a.cfg;
-        if (c.sensing_loc != PDECG_SENSE_FULL) {
-            const S dxs = static_cast<S>(c.dx);
-            S o;
-            if (c.sensing_loc == PDECG_SENSE_COLLOCATED)
-                o = (c.control_type == PDECG_CONTROL_NEUMANN) ? last : Strict<S>::div(Strict<S>::sub(last, blast), dxs);
-            else
-                o = (c.sensing_type == PDECG_SENSETYPE_NEUMANN) ? Strict<S>::div(Strict<S>::sub(second, first), dxs) : first;
-            static_cast<S*>(a.buf.obs)[env] = o;
-        }
-    }
+    reset_env<S, I, 32>(a, init, init_stride, rnd, env, lane, kFull, false);
 }
 
 // ---- host-side dispatch --------------------------------------------------------------------------
@@ -117,6 +61,7 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     out->tuned_general = (cfg->reward_kind == PDECG_REWARD_TUNED1D && tuned_needs_general_ring(cfg->substeps, cfg->nt)) ? 1 : 0;
     out->ring_len = out->tuned_general ? kLookback + 1 : ring_len_for(cfg->substeps);
     out->carry_len = 1 + out->ring_len;
+    out->ar = AutoReset{};
     if (out->npts > 512) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 512 points per env", out->npts);
     return PDECG_OK;
 }
@@ -153,6 +98,26 @@ extern "C" int pdecg_bc1d_step(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffe
     if (!buf->beta) return fail(PDECG_ERR_INVALID, "null beta buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return launch_mode(a, st);
+}
+
+extern "C" int pdecg_bc1d_step_autoreset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
+                                         const pdecg_bc1d_autoreset* ar, pdecg_stream_t stream) {
+    Bc1dArgs a;
+    int rc = validate(cfg, buf, &a);
+    if (rc != PDECG_OK) return rc;
+    if (!ar) return fail(PDECG_ERR_INVALID, "null autoreset descriptor");
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
+    if (!buf->beta) return fail(PDECG_ERR_INVALID, "null beta buffer");
+    if (!ar->init) return fail(PDECG_ERR_INVALID, "null init buffer");
+    if (ar->init_dtype != PDECG_F32 && ar->init_dtype != PDECG_F64) return fail(PDECG_ERR_INVALID, "bad init_dtype");
+    if (ar->random && !ar->episode) return fail(PDECG_ERR_INVALID, "null episode counter buffer");
+    a.ar.enabled = 1;
+    a.ar.init_dtype = ar->init_dtype;
+    a.ar.init = ar->init;
+    a.ar.init_stride = ar->random ? 0 : ar->init_env_stride;
+    a.ar.rnd = ar->random ? RandomIc{1, ar->lo, ar->hi, ar->seed, ar->env_id_offset, ar->episode} : RandomIc{};
+    return launch_mode(a, static_cast<cudaStream_t>(stream));
 }
 
 static int reset_impl(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, const void* init, int32_t init_dtype,

@@ -21,6 +21,22 @@ struct ModeRefB64 { using S = float;  using C = double; static constexpr bool kF
 struct ModeFp64   { using S = double; using C = double; static constexpr bool kFast = false; };
 struct ModeFp32   { using S = float;  using C = float;  static constexpr bool kFast = true;  };
 
+struct RandomIc {          // optional: u <- c * profile with c ~ U(lo, hi) from Philox (pdecg_bc1d_reset_random)
+    int enabled;
+    double lo, hi;
+    uint64_t seed;
+    int64_t env_id_offset;
+    int32_t* episode;
+};
+
+struct AutoReset {         // pdecg_bc1d_step_autoreset: finished envs restart inside the step launch
+    int enabled;
+    int init_dtype;
+    const void* init;
+    int64_t init_stride;
+    RandomIc rnd;
+};
+
 struct Bc1dArgs {
     pdecg_bc1d_cfg cfg;
     pdecg_bc1d_buffers buf;
@@ -28,6 +44,7 @@ struct Bc1dArgs {
     int carry_len;
     int ring_len;   // TunedReward1D look-back ring (entries) -- see carry layout below
     int tuned_general;   // 1: ring of the last 101 per-SUBSTEP norms (any substep count; slow path)
+    AutoReset ar;
 };
 
 // carry layout (doubles, per env):
@@ -273,8 +290,84 @@ struct Integrator {
     }
 };
 
+// ---- (re)initialise one env: `reset` of hyperbolic.py:198-227 / parabolic.py:192-221 --------------------------
+// Executed by the LPE lanes of the env's segment.  `keep_outputs`: leave reward / flags alone (fused auto-reset).
+template <typename S, typename I, int LPE>
+__device__ __forceinline__ void reset_env(const Bc1dArgs& a, const I* __restrict__ init, int64_t init_stride,
+                                          const RandomIc& rnd, int64_t env, int lane, unsigned mask, bool keep_outputs) {
+    const int npts = a.npts;
+    S* urow = static_cast<S*>(a.buf.u) + env * npts;
+    const I* irow = init + env * init_stride;
+    double scale = 1.0;
+    if (rnd.enabled) {
+        const int ep = rnd.episode[env];
+        const double u01 = Philox4x32::uniform53(rnd.seed, static_cast<uint64_t>(rnd.env_id_offset + env), static_cast<uint32_t>(ep));
+        scale = __dadd_rn(rnd.lo, __dmul_rn(__dsub_rn(rnd.hi, rnd.lo), u01));
+        __syncwarp(mask);
+        if (lane == 0) rnd.episode[env] = ep + 1;
+    }
+    auto ic = [&](int j) -> S {                        // `u[0] = init_condition` casts to the state dtype
+        return rnd.enabled ? static_cast<S>(__dmul_rn(scale, static_cast<double>(irow[j]))) : static_cast<S>(irow[j]);
+    };
+    double ss = 0.0;
+    S last = S(0), first = S(0), second = S(0), blast = S(0);
+    S* crow = a.buf.obs_copy ? static_cast<S*>(a.buf.obs_copy) + env * npts : nullptr;
+    // ||u_0||^2 in the summation order of a 32-lane warp (32 strided partial sums, xor tree 16-8-4-2-1) whatever
+    // LPE is: a half-warp segment carries two of the partial sums per lane, so both reset paths agree bit for bit
+    static_assert(LPE == 32 || LPE == 16, "reset_env: 32 or 16 lanes per env");
+#pragma unroll
+    for (int r = 0; r < 32 / LPE; ++r) {
+        double part = 0.0;
+        for (int j = lane + r * LPE; j < npts; j += 32) {
+            S v = ic(j);
+            urow[j] = v;
+            if (crow) crow[j] = v;
+            double dv = static_cast<double>(v);
+            part += dv * dv;
+        }
+        ss = (r == 0) ? part : ss + part;
+    }
+    ss = seg_sum<LPE>(ss, mask);
+    if (npts >= 1) last = ic(npts - 1);
+    if (npts >= 2) blast = ic(npts - 2);
+    first = ic(0);
+    if (npts >= 2) second = ic(1);
+    if (lane == 0) {
+        double* carry = a.buf.carry + env * a.carry_len;
+        carry[0] = fabs(static_cast<double>(last));    // row 0 of uVec[:, -1]
+        for (int i = 1; i < a.carry_len; ++i) carry[i] = 0.0;
+        carry[1] = static_cast<double>(static_cast<S>(sqrt(ss)));   // ||u_0||: ring slot of step 0
+        a.buf.time_index[env] = 0;
+        if (!keep_outputs) {
+            a.buf.reward[env] = 0.0;
+            a.buf.terminated[env] = 0;
+            a.buf.truncated[env] = 0;
+        }
+        const pdecg_bc1d_cfg& c = a.cfg;
+        if (c.sensing_loc != PDECG_SENSE_FULL) {
+            const S dxs = static_cast<S>(c.dx);
+            S o;
+            if (c.sensing_loc == PDECG_SENSE_COLLOCATED)
+                o = (c.control_type == PDECG_CONTROL_NEUMANN) ? last : Strict<S>::div(Strict<S>::sub(last, blast), dxs);
+            else
+                o = (c.sensing_type == PDECG_SENSETYPE_NEUMANN) ? Strict<S>::div(Strict<S>::sub(second, first), dxs) : first;
+            static_cast<S*>(a.buf.obs)[env] = o;
+        }
+    }
+}
+
+// fused same-step auto-reset: out of line so the (rare) restart does not weigh on the step kernel's registers
+template <typename S, int LPE>
+__device__ __noinline__ void autoreset_env(const Bc1dArgs& a, int64_t env, int lane, unsigned mask) {
+    __syncwarp(mask);                                  // the step's own row / carry stores come first
+    if (a.ar.init_dtype == PDECG_F32)
+        reset_env<S, float, LPE>(a, static_cast<const float*>(a.ar.init), a.ar.init_stride, a.ar.rnd, env, lane, mask, true);
+    else
+        reset_env<S, double, LPE>(a, static_cast<const double*>(a.ar.init), a.ar.init_stride, a.ar.rnd, env, lane, mask, true);
+}
+
 template <int ENV, class M, int K, int VAR, int LPE = 32>
-__global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const Bc1dArgs a) {
+__global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
     using S = typename M::S;
     using C = typename M::C;
     constexpr int EPW = 32 / LPE;                      // envs per warp
@@ -533,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kern
         a.buf.terminated[env] = terminated ? 1 : 0;
         a.buf.truncated[env] = truncated ? 1 : 0;
     }
+    if (a.ar.enabled && (terminated || truncated)) autoreset_env<S, LPE>(a, env, lane, mask);
 }
 
 // Lanes per env, points per lane and kernel variant for this configuration (uniform over the batch).

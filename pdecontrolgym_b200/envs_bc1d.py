@@ -294,6 +294,18 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                 _lib.F64 if self._ic.dtype == torch.float64 else _lib.F32, self._ic_stride,
                 None if mask_t is None else mask_t.data_ptr(), self._stream()))
 
+    def _autoreset_desc(self):
+        ar = _lib.Bc1dAutoReset()
+        ar.init = self._ic.data_ptr()
+        ar.init_dtype = _lib.F64 if self._ic.dtype == torch.float64 else _lib.F32
+        r = self._random_ic
+        if r is not None:
+            ar.random, ar.lo, ar.hi = 1, r.lo, r.hi
+            ar.seed, ar.env_id_offset, ar.episode = self._seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset, self._episode.data_ptr()
+        else:
+            ar.random, ar.init_env_stride = 0, self._ic_stride
+        return ar
+
     def _prep_action(self, action):
         if isinstance(action, torch.Tensor):
             a = action
@@ -335,20 +347,16 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             with torch.cuda.device(self.device):
                 if ke is not None:
                     ke[0].record()
-                _lib.check(self._L.pdecg_bc1d_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
+                if self.autoreset:          # same-step auto-reset inside the step launch: finished envs restart from their IC
+                    _lib.check(self._L.pdecg_bc1d_step_autoreset(C.byref(self._cfg), C.byref(self._buf),
+                                                                 C.byref(self._autoreset_desc()), self._stream()))
+                else:
+                    _lib.check(self._L.pdecg_bc1d_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
                 if ke is not None:
                     ke[1].record()
-            # the auto-reset below clears reward / flags of the envs it restarts: point it at the internal buffers
-            self._buf.reward, self._buf.terminated, self._buf.truncated = (
-                self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr())
             # copy_obs: fresh tensors (above); otherwise zero-copy views the next step overwrites
             terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
             info = {}
-            if self.autoreset:
-                torch.bitwise_or(term_u8, trunc_u8, out=self._done)
-                if not self.copy_obs:       # the reset would clear the views being returned
-                    terminated, truncated, reward = terminated.clone(), truncated.clone(), reward.clone()
-                self._reset_kernel(self._done)   # same-step autoreset: finished envs restart from their IC
         finally:
             self._buf.obs_copy = None            # never leave a pointer to a caller-owned tensor behind
             self._buf.reward, self._buf.terminated, self._buf.truncated = (

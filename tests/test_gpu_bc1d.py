@@ -214,3 +214,48 @@ def test_tuned_reward_any_substep_count(cuda_device, env, sub, steps, extra):
         scale = 2 * np.sqrt((oenv.u.astype(np.float64) ** 2).sum(axis=1)) + np.abs(r_r)
         assert_rewards_close(r_g.cpu().numpy(), r_r, scale, TOL_F32_REDUCTION, f"call {k}")
     assert te_r.all()
+
+
+@pytest.mark.parametrize("env,precision", [("rd", "fp64"), ("rd", "ref"), ("tr", "ref"), ("tr", "fp64")])
+@pytest.mark.parametrize("rk", ["tuned", ("temporal", 2)])
+def test_staggered_time_indices_within_a_warp(cuda_device, env, precision, rk):
+    """Two envs share a warp on the default grids (16 lanes each).  Envs of a pair that sit at different time
+    indices (masked reset) or finish at different steps must not disturb each other; odd batch -> a lone env."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    steps, B = 6, 5
+    kw, npts, beta, nt = bc1d_case(env, None, steps)
+    ospec, prew = reward_pair(rk, nt - 1)
+    common = dict(normalize=True, sensing_loc="full", control_type="Dirchilet", sensing_type=None,
+                  limit_pde_state_size=False, max_state_value=1e10, max_control_value=20, **kw)
+    rng = np.random.default_rng(11)
+    ics, ics2 = make_ics(rng, B, npts), make_ics(rng, B, npts)
+    bdt = np.float64 if precision == "fp64" else np.float32
+    beta = beta.astype(bdt)
+    Orc = O.ReactionDiffusionOracle if env == "rd" else O.TransportOracle
+    oprec = "fp64" if precision == "fp64" else "ref"
+    old, new = Orc(B, reward=ospec, precision=oprec, **common), Orc(B, reward=reward_pair(rk, nt - 1)[0], precision=oprec, **common)
+    old.reset(ics, beta)
+    eid = "PDEControlGym-ReactionDiffusionPDE1D" if env == "rd" else "PDEControlGym-TransportPDE1D"
+    genv = pcg.make(eid, num_envs=B, device=cuda_device, precision=precision, reward_class=prew, **common)
+    genv.reset(options={"init_condition": ics, "beta": beta})
+    for k in range(2):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        old.step(a)
+        genv.step(torch.from_numpy(a))
+    mask = np.array([False, True, True, False, False])
+    genv.reset(options={"init_condition": ics2, "beta": beta, "mask": mask})
+    new.reset(ics2, beta)
+    tol = TOL_F64_REDUCTION if precision == "fp64" else TOL_F32_REDUCTION
+    for k in range(steps + 1):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        o_old, r_old, te_old, _ = old.step(a)
+        o_new, r_new, te_new, _ = new.step(a)
+        o_gpu, r_gpu, te_gpu, _, _ = genv.step(torch.from_numpy(a))
+        o_ref = np.where(mask[:, None], o_new, o_old)
+        assert np.array_equal(o_gpu.cpu().numpy(), o_ref), f"step {k}: state not bit-identical"
+        assert np.array_equal(te_gpu.cpu().numpy(), np.where(mask, te_new, te_old)), f"step {k}: terminated"
+        live = np.where(mask, k < steps, k < steps - 2)         # rewards of finished envs are not compared
+        r_ref = np.where(mask, r_new, r_old)
+        scale = 2 * np.sqrt((o_ref.astype(np.float64) ** 2).sum(axis=1)) + np.abs(r_ref)
+        assert_rewards_close(r_gpu.cpu().numpy()[live], r_ref[live], scale[live], tol, f"step {k}")

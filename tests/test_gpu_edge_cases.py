@@ -141,3 +141,50 @@ def test_bc1d_masked_reset_and_recorder(cuda_device):
     o1, *_ = env.step(a)
     o2, *_ = fresh.step(a)
     assert torch.equal(o1[torch.from_numpy(mask)], o2[torch.from_numpy(mask)])
+
+
+@pytest.mark.parametrize("env_id,precision", [("PDEControlGym-ReactionDiffusionPDE1D", "fp64"), ("PDEControlGym-TransportPDE1D", "ref")])
+@pytest.mark.parametrize("random_ic", [False, True])
+@pytest.mark.parametrize("sensing_loc", ["full", "collocated"])
+def test_bc1d_fused_autoreset_equals_step_then_masked_reset(cuda_device, env_id, precision, random_ic, sensing_loc):
+    """pdecg_bc1d_step_autoreset == pdecg_bc1d_step followed by pdecg_bc1d_reset[_random] on the finished envs."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    rd = "Reaction" in env_id
+    N, steps = 7, 4
+    if rd:
+        kw = dict(T=steps * 100 * 1e-5, dt=1e-5, X=1, dx=5e-3, control_sample_rate=1e-3)
+        npts = 201
+    else:
+        kw = dict(T=steps * 300 * 1e-4, dt=1e-4, X=1, dx=1e-2, control_sample_rate=3e-2)
+        npts = 100
+    kw.update(normalize=True, sensing_loc=sensing_loc, precision=precision, limit_pde_state_size=True, max_state_value=1e10,
+              reward_class=pcg.TunedReward1D(int(round(kw["T"] / kw["dt"])), -1e3, 3e2))
+    rng = np.random.default_rng(9)
+    beta = rng.uniform(-3, 3, (N, npts)).astype(np.float64 if precision == "fp64" else np.float32)
+    ic = pcg.UniformScaleIC(1.0, 10.0) if random_ic else rng.uniform(1, 2, (N, npts))
+    fused = pcg.make(env_id, num_envs=N, device=cuda_device, autoreset=True, **kw)
+    manual = pcg.make(env_id, num_envs=N, device=cuda_device, autoreset=False, **kw)
+    o1, _ = fused.reset(seed=5, options={"init_condition": ic, "beta": beta})
+    o2, _ = manual.reset(seed=5, options={"init_condition": ic, "beta": beta})
+    assert torch.equal(o1, o2)
+    # stagger the episodes so that only some envs finish at a time
+    stag = np.array([True, False, False, True, True, False, True])
+    a0 = torch.zeros(N, device=cuda_device)
+    fused.step(a0), manual.step(a0)
+    fused.reset(options={"mask": stag}), manual.reset(options={"mask": stag})
+    n_done = 0
+    for k in range(2 * steps + 2):
+        a = torch.from_numpy(rng.uniform(-1, 1, N).astype(np.float32))
+        o1, r1, te1, tr1, _ = fused.step(a)
+        o2, r2, te2, tr2, _ = manual.step(a)
+        done = te2 | tr2
+        if done.any():
+            o2, _ = manual.reset(options={"mask": done})
+            n_done += int(done.sum())
+        assert torch.equal(te1, te2) and torch.equal(tr1, tr2) and torch.equal(r1, r2), f"step {k}: outputs"
+        assert torch.equal(o1, o2), f"step {k}: observation"
+        for name in ("u", "time_index", "_carry", "_episode"):
+            x, y = getattr(fused, name), getattr(manual, name)
+            assert torch.equal(x, y), f"step {k}: {name} differs at {(x != y).nonzero()[:6].tolist()} done={done.tolist()} fused={x[x != y][:6].tolist()} manual={y[x != y][:6].tolist()}"
+    assert n_done >= N
