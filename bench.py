@@ -144,6 +144,8 @@ def _cpu_worker(conn, k_envs, seed):
         out = []
         for e, a in zip(envs, msg):
             o, r, te, tr = e.step(np.array([a], dtype=np.float32))
+            if te[0] or tr[0]:         # same-step auto-reset like the vector env (a finished env would step for free)
+                o = e.reset(np.ones(NX_PTS) * rng.uniform(1, 10), beta_fn())
             out.append((o, float(r[0]), bool(te[0]), bool(tr[0])))
         conn.send(out)
 
@@ -352,8 +354,9 @@ def run_ours(args):
     fp64_peak_tflops = ops.value / (ms.value * 1e-3) / 1e12
     k_ms = float(np.mean(kern_ms))
     flops_per_launch = E * INTERIOR * SUBSTEPS * FLOPS_PER_POINT
-    # algorithmic HBM bytes per launch: state row in + out, action, reward, 2 flags, time_index r/w, carry r/w (2 doubles)
-    bytes_per_env = 2 * NX_PTS * 8 + 4 + 8 + 2 + 8 + 2 * 2 * 8
+    # algorithmic HBM bytes per launch: state row in + out, the caller's private observation row out (obs_copy),
+    # action, reward, 2 flags, time_index r/w, carry r/w (2 doubles)
+    bytes_per_env = 3 * NX_PTS * 8 + 4 + 8 + 2 + 8 + 2 * 2 * 8
     bytes_per_launch = E * bytes_per_env + NX_PTS * 8
     traffic = None                # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
     try:

@@ -157,10 +157,12 @@ int pdecg_bc1d_step_autoreset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffer
  * H2D(actions) -> kernel -> D2H(obs, reward, flags), all on `stream`, then stream-synchronised.
  * obs_host is [n_envs, npts] S for FULL sensing, [n_envs] S otherwise; any output pointer may be
  * NULL to skip that copy.  Device buffers in `buf` are still the caller's (buf->action is the
- * device staging buffer for the actions). */
+ * device staging buffer for the actions).  `autoreset` (may be NULL) fuses the same-step auto-reset as in
+ * pdecg_bc1d_step_autoreset; the observation copied out for a restarted env is then its new initial row. */
 int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
                          const void* action_host, void* obs_host, double* reward_host,
-                         uint8_t* terminated_host, uint8_t* truncated_host, pdecg_stream_t stream);
+                         uint8_t* terminated_host, uint8_t* truncated_host,
+                         const pdecg_bc1d_autoreset* autoreset, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Family 2: BrainTumor1D (+ TherapyWrapper semantics)           -- all float64

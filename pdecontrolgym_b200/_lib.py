@@ -138,7 +138,7 @@ def lib():
                                           C.c_double, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_bc1d_reset_random.restype = C.c_int
     L.pdecg_bc1d_step_host.argtypes = [C.POINTER(Bc1dCfg), C.POINTER(Bc1dBuffers), C.c_void_p, C.c_void_p,
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Bc1dAutoReset), C.c_void_p]
     L.pdecg_bc1d_step_host.restype = C.c_int
     L.pdecg_bt_reset.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.pdecg_bt_reset.restype = C.c_int

@@ -190,7 +190,8 @@ int ensure_pipe(HostPipe** out) {
 
 extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
                                     const void* action_host, void* obs_host, double* reward_host,
-                                    uint8_t* terminated_host, uint8_t* truncated_host, pdecg_stream_t stream) {
+                                    uint8_t* terminated_host, uint8_t* truncated_host,
+                                    const pdecg_bc1d_autoreset* autoreset, pdecg_stream_t stream) {
     Bc1dArgs a;
     int rc = validate(cfg, buf, &a);
     if (rc != PDECG_OK) return rc;
@@ -231,7 +232,17 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
         b.obs_copy = nullptr;                                  // the host path copies straight from the state
         if ((e = cudaMemcpyAsync(const_cast<void*>(b.action), off(action_host, lo * asz), cnt * asz, cudaMemcpyHostToDevice, st)) != cudaSuccess)
             return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
-        if ((rc = pdecg_bc1d_step(cfg, &b, st)) != PDECG_OK) return rc;
+        if (autoreset) {
+            pdecg_bc1d_autoreset ar = *autoreset;
+            const size_t isz = ar.init_dtype == PDECG_F64 ? 8 : 4;
+            if (!ar.random) ar.init = off(ar.init, lo * ar.init_env_stride * isz);
+            ar.env_id_offset += lo;
+            if (ar.episode) ar.episode += lo;
+            rc = pdecg_bc1d_step_autoreset(cfg, &b, &ar, st);
+        } else {
+            rc = pdecg_bc1d_step(cfg, &b, st);
+        }
+        if (rc != PDECG_OK) return rc;
         if (obs_host) {
             const void* src = full ? static_cast<const void*>(b.u) : static_cast<const void*>(b.obs);
             if ((e = cudaMemcpyAsync(static_cast<char*>(obs_host) + lo * obs_row, src, cnt * obs_row, cudaMemcpyDeviceToHost, st)) != cudaSuccess)

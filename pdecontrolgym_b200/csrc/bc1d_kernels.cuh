@@ -52,7 +52,7 @@ struct Bc1dArgs {
 //   [1 .. ring]    ring of step-end L2 norms    (tuned_reward_1d.py:40: norm(uVec[t-100]))
 constexpr int kLookback = 100;
 #ifndef PDECG_BC1D_MINBLOCKS
-#define PDECG_BC1D_MINBLOCKS 3   // <= 170 registers: 3 CTAs (12 warps) per SM; measured best for the fp64 two-envs-per-warp kernel
+#define PDECG_BC1D_MINBLOCKS 12  // x PDECG_BC1D_WARPS (1) = 12 warps per SM, <= 170 registers: measured best for the fp64 two-envs-per-warp kernel
 #endif
 
 __host__ __device__ inline int ring_len_for(int substeps) {
@@ -366,16 +366,25 @@ __device__ __noinline__ void autoreset_env(const Bc1dArgs& a, int64_t env, int l
         reset_env<S, double, LPE>(a, static_cast<const double*>(a.ar.init), a.ar.init_stride, a.ar.rnd, env, lane, mask, true);
 }
 
+// Warps of a block never cooperate (one env or env pair per warp, private smem slice), so the block size only
+// sets the scheduling granularity of the tail wave (measured on the headline config: 4 warps 0.5333 ms,
+// 2 warps 0.5327 ms, 1 warp 0.5304 ms per launch, always 12 warps resident per SM).
+#ifndef PDECG_BC1D_WARPS
+#define PDECG_BC1D_WARPS 1
+#endif
+constexpr int kStepWarps = PDECG_BC1D_WARPS;
+constexpr int kStepThreads = kStepWarps * 32;
+
 template <int ENV, class M, int K, int VAR, int LPE = 32>
-__global__ void __launch_bounds__(kThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
+__global__ void __launch_bounds__(kStepThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
     using S = typename M::S;
     using C = typename M::C;
     constexpr int EPW = 32 / LPE;                      // envs per warp
-    __shared__ S sm_all[kWarpsPerBlock * EPW][LPE * K];
+    __shared__ S sm_all[kStepWarps * EPW][LPE * K];
     const int lane = threadIdx.x & (LPE - 1);          // lane inside the env's segment
     const int seg = (threadIdx.x >> 5) * EPW + ((threadIdx.x & 31) / LPE);
     const unsigned mask = seg_mask<LPE>(threadIdx.x & 31);
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * (kWarpsPerBlock * EPW) + seg;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * (kStepWarps * EPW) + seg;
     if (env >= a.buf.n_envs) return;
     S* sm = sm_all[seg];
     const pdecg_bc1d_cfg& cfg = a.cfg;
@@ -645,19 +654,19 @@ inline void pick_variant(const Bc1dArgs& a, int* LPE, int* K, int* var) {
 
 template <int ENV, class M, int VAR>
 inline int launch_k(const Bc1dArgs& a, int LPE, int K, cudaStream_t st) {
-    const int64_t per_block = (LPE == 16) ? 2 * kWarpsPerBlock : kWarpsPerBlock;
+    const int64_t per_block = (LPE == 16) ? 2 * kStepWarps : kStepWarps;
     const unsigned grid = static_cast<unsigned>((a.buf.n_envs + per_block - 1) / per_block);
     if (LPE == 16) {
         if constexpr (VAR == kVarFast) {
-            if (K == 7) bc1d_step_kernel<ENV, M, 7, VAR, 16><<<grid, kThreads, 0, st>>>(a);
-            else if (K == 13) bc1d_step_kernel<ENV, M, 13, VAR, 16><<<grid, kThreads, 0, st>>>(a);
+            if (K == 7) bc1d_step_kernel<ENV, M, 7, VAR, 16><<<grid, kStepThreads, 0, st>>>(a);
+            else if (K == 13) bc1d_step_kernel<ENV, M, 13, VAR, 16><<<grid, kStepThreads, 0, st>>>(a);
             else return fail(PDECG_ERR_UNSUPPORTED, "unsupported half-warp points-per-lane %d", K);
         } else {
             return fail(PDECG_ERR_UNSUPPORTED, "half-warp mapping only exists for the fast variant");
         }
     } else {
         switch (K) {
-#define PDECG_CASE(KK) case KK: bc1d_step_kernel<ENV, M, KK, VAR, 32><<<grid, kThreads, 0, st>>>(a); break;
+#define PDECG_CASE(KK) case KK: bc1d_step_kernel<ENV, M, KK, VAR, 32><<<grid, kStepThreads, 0, st>>>(a); break;
             PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
             PDECG_CASE(10) PDECG_CASE(12) PDECG_CASE(14) PDECG_CASE(16)
 #undef PDECG_CASE

@@ -397,10 +397,8 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                 ptr(obs_host, self.state_dtype, obs_n, "obs_host"),
                 ptr(reward_host, torch.float64, self.num_envs, "reward_host"),
                 ptr(terminated_host, torch.uint8, self.num_envs, "terminated_host"),
-                ptr(truncated_host, torch.uint8, self.num_envs, "truncated_host"), self._stream()))
-            if self.autoreset:
-                torch.bitwise_or(self._terminated, self._truncated, out=self._done)
-                self._reset_kernel(self._done)
+                ptr(truncated_host, torch.uint8, self.num_envs, "truncated_host"),
+                C.byref(self._autoreset_desc()) if self.autoreset else None, self._stream()))
         return obs_host, reward_host, terminated_host, truncated_host, {}
 
     # compatibility attributes read by the reference's examples

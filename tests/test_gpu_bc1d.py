@@ -151,16 +151,18 @@ def test_empty_batch_and_errors(cuda_device):
         big.reset(options={"init_condition": np.zeros(600), "beta": np.zeros(600)})
 
 
+@pytest.mark.parametrize("autoreset", [False, True])
 @pytest.mark.parametrize("N", [3, 4099, 20001])
-def test_step_host_matches_device_step(cuda_device, N):
-    """pdecg_bc1d_step_host (H2D -> chunked, two-stream pipelined kernels -> D2H) == pdecg_bc1d_step."""
+def test_step_host_matches_device_step(cuda_device, N, autoreset):
+    """pdecg_bc1d_step_host (H2D -> chunked, two-stream pipelined kernels -> D2H) == pdecg_bc1d_step, with and
+    without the fused same-step auto-reset (per-env initial rows: the chunk offsets matter)."""
     import torch
     import pdecontrolgym_b200 as pcg
     kw, npts, beta, nt = bc1d_case("rd", None, 3)
     rng = np.random.default_rng(N)
     ics = make_ics(rng, N, npts)
     mk = lambda: pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=N, device=cuda_device, precision="fp64",  # noqa: E731
-                          reward_class=pcg.NormReward(nt - 1), normalize=True, **kw)
+                          reward_class=pcg.NormReward(nt - 1), normalize=True, autoreset=autoreset, **kw)
     e1, e2 = mk(), mk()
     for e in (e1, e2):
         e.reset(options={"init_condition": ics, "beta": np.tile(beta, (N, 1)) * rng.uniform(0.9, 1.1)})
@@ -169,14 +171,16 @@ def test_step_host_matches_device_step(cuda_device, N):
     rew_h = torch.empty(N, dtype=torch.float64).pin_memory()
     te_h = torch.empty(N, dtype=torch.uint8).pin_memory()
     tr_h = torch.empty(N, dtype=torch.uint8).pin_memory()
-    for k in range(3):
+    for k in range(7 if autoreset else 3):
         a = rng.uniform(-1, 1, N).astype(np.float32)
         o, r, te, tr, _ = e1.step(torch.from_numpy(a))
         e2.step_host(torch.from_numpy(a).pin_memory(), obs_h, rew_h, te_h, tr_h)
         assert np.array_equal(o.cpu().numpy(), obs_h.numpy())
         assert np.array_equal(r.cpu().numpy(), rew_h.numpy())
         assert np.array_equal(te.cpu().numpy(), te_h.numpy().astype(bool)) and np.array_equal(tr.cpu().numpy(), tr_h.numpy().astype(bool))
-    assert te_h.all()
+        assert bool(te_h.all()) == (k % 3 == 2)
+        if autoreset and k % 3 == 2:
+            assert np.array_equal(obs_h.numpy(), ics) and torch.equal(e1.time_index, e2.time_index) and int(e2.time_index.max()) == 0
 
 
 @pytest.mark.parametrize("env", ["rd", "tr"])
