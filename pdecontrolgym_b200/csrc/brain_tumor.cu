@@ -10,7 +10,10 @@
 #include "pdecg_internal.h"
 
 #ifndef PDECG_BT_MINBLOCKS
-#define PDECG_BT_MINBLOCKS 8   // 64 registers, 32 warps/SM: the single-day launch is latency/HBM-bound (measured best)
+#define PDECG_BT_MINBLOCKS 6   // 80 registers, 24 warps/SM: the single-day launch is latency/HBM-bound (measured: 8 -> 0.264, 6 -> 0.252, 5 -> 0.268, 4 -> 0.285 ms at 262k envs)
+#endif
+#ifndef PDECG_BT_MINBLOCKS_MULTI
+#define PDECG_BT_MINBLOCKS_MULTI 4   // 128 registers: the multi-day (TherapyWrapper) launches are instruction-bound
 #endif
 #ifndef PDECG_ARZ_MINBLOCKS
 #define PDECG_ARZ_MINBLOCKS 1
@@ -42,62 +45,89 @@ __device__ __forceinline__ int rightmost_ge(const double (&c)[K], int j0, int nx
     return warp_max_i(best);
 }
 
-// _update_fd (:221-245).  rin < 0 encodes "R is None"; treat_to = number of leading points with
+// _update_fd (:221-245).  HASR == false encodes "R is None"; treat_to = number of leading points with
 // xScale <= treatmentRadius (they receive R = rin, the others R = 1 - exp(-alpha*0) = 0).
 struct BtDivs {      // the two loop-invariant divisors of _update_fd (:236-237)
     ConstDiv<double> by_dx2, by_k;
     unsigned tiny_hi;   // high word of the largest power of two <= k*2^-60
+    unsigned om_limit;  // |u_c| with a high word below this takes the 3-instruction quotient (0: never)
+    unsigned k_hi;      // high word of k: 0 <= v < k for sure when hiword(v) < k_hi (as unsigned)
+    bool dx2_one;       // dx**2 == 1 (the reference's grid): the division by it is the identity
     __device__ __forceinline__ explicit BtDivs(const pdecg_bt_cfg& cfg) : by_dx2(cfg.dx * cfg.dx), by_k(cfg.k) {   // self.dx ** 2 (one rounded multiply)
         const unsigned khi = static_cast<unsigned>(__double2hiint(cfg.k)) & 0x7ff00000u;    // 2^floor(log2 k)
         tiny_hi = (khi > (61u << 20)) ? khi - (60u << 20) : 0u;
+        // ConstDiv<double>::in_range is 0x07b00000 <= hi < 0x78300000; everything below tiny_hi is fine too (see
+        // bt_fd), so one unsigned compare covers both whenever the two windows overlap
+        om_limit = (by_k.d_ok && tiny_hi >= 0x07b00000u) ? 0x78300000u : 0u;
+        k_hi = static_cast<unsigned>(__double2hiint(cfg.k));
+        dx2_one = (by_dx2.d == 1.0);
     }
 };
 
-template <int K>
+template <int K, bool DX2ONE, bool HASR>
 __device__ __forceinline__ void bt_fd(const pdecg_bt_cfg& cfg, const BtDivs& dv, const double (&c)[K], double (&n)[K], int lane, int j0,
-                                       double D, double rho, bool has_r, double rin, int treat_to) {
+                                       double D, double rho, double rin, int treat_to) {
     const int nx = cfg.nx;
     const double hl = __shfl_up_sync(kFull, c[K - 1], 1);
     const double hr = __shfl_down_sync(kFull, c[0], 1);
+    // (1.0 - u_c/k): the quotient comes from the 3-instruction exact tail for the whole chunk with ONE window test
+    // per lane.  For |u_c| < k*2^-60 the quotient is below 2^-60 whatever its low bits are and the difference
+    // rounds to exactly 1.0, so the far field (zeros, denormals) needs neither a test nor div.rn's slow path.
+    double diff[K], q[K];
+    bool ok = true;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double cl = (k == 0) ? hl : c[k > 0 ? k - 1 : 0];
         const double cr = (k == K - 1) ? hr : c[k < K - 1 ? k + 1 : K - 1];
         const double cc = c[k];
         // diffusion = D * (((u_r - 2.0*u_c) + u_l) / dx**2)
-        const double lap = dv.by_dx2(__dadd_rn(__dsub_rn(cr, __dmul_rn(2.0, cc)), cl));
-        const double diff = __dmul_rn(D, lap);
-        // proliferation = (rho*u_c) * (1.0 - u_c/k)
-        // (1.0 - u_c/k): for |u_c| < k*2^-60 the quotient is below 2^-60 and the difference rounds to exactly
-        // 1.0 whatever its low bits are -- skip the division there (the far field is full of denormals, which
-        // would otherwise take div.rn's slow path every day).
+        const double s = __dadd_rn(__dsub_rn(cr, __dmul_rn(2.0, cc)), cl);
+        diff[k] = __dmul_rn(D, DX2ONE ? s : dv.by_dx2(s));
         const unsigned cc_hi = static_cast<unsigned>(__double2hiint(cc)) & 0x7fffffffu;
-        const double om = (cc_hi < dv.tiny_hi) ? 1.0 : __dsub_rn(1.0, dv.by_k(cc));
-        const double pro = __dmul_rn(__dmul_rn(rho, cc), om);
-        double acc = __dadd_rn(diff, pro);
-        if (has_r) {
-            const double rj = (j0 + k < treat_to) ? rin : 0.0;
-            acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(rj, cc), om));
-        } else {
-            acc = __dsub_rn(acc, 0.0);                      // `- radiation` with radiation = 0.0
-        }
-        n[k] = __dadd_rn(cc, __dmul_rn(cfg.dt, acc));
+        ok = ok & (cc_hi < dv.om_limit);
+        q[k] = dv.by_k.fast(cc);
     }
-    // nextU[0] = nextU[1]; nextU[-1] = nextU[-2]  (mirrored ends), then clip to [0, k]
-    const double from_left = __shfl_up_sync(kFull, n[K - 1], 1);
-    const double from_right = __shfl_down_sync(kFull, n[0], 1);
-    double m[K];
+    if (!ok) {                                             // huge / NaN densities or an exotic k: exact division
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const unsigned cc_hi = static_cast<unsigned>(__double2hiint(c[k])) & 0x7fffffffu;
+            q[k] = (cc_hi < dv.tiny_hi) ? 0.0 : dv.by_k(c[k]);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int j = j0 + k;
-        double v = n[k];
-        if (j == 0) v = (K > 1) ? n[K > 1 ? 1 : 0] : from_right;
-        if (j == nx - 1) v = (k > 0) ? n[k > 0 ? k - 1 : 0] : from_left;
-        v = (v < 0.0) ? 0.0 : ((v > cfg.k) ? cfg.k : v);   // np.clip keeps NaN
-        m[k] = (j < nx) ? v : 0.0;
+        const double cc = c[k];
+        // proliferation = (rho*u_c) * (1.0 - u_c/k)
+        const double om = __dsub_rn(1.0, q[k]);
+        const double pro = __dmul_rn(__dmul_rn(rho, cc), om);
+        double acc = __dadd_rn(diff[k], pro);
+        if constexpr (HASR) {
+            const double rj = (j0 + k < treat_to) ? rin : 0.0;
+            acc = __dsub_rn(acc, __dmul_rn(__dmul_rn(rj, cc), om));
+        }                                                   // else `- 0.0`: the identity for every double
+        n[k] = __dadd_rn(cc, __dmul_rn(cfg.dt, acc));
     }
+    // nextU[0] = nextU[1]; nextU[-1] = nextU[-2]  (mirrored ends), then clip to [0, k].  Padding slots (j >= nx) are
+    // left to evolve: valid points never read them (u[nx-1] is the mirror of u[nx-2]), the radius scans mask them,
+    // the clip keeps them finite and the store drops them.
+    const double from_left = __shfl_up_sync(kFull, n[K - 1], 1);
+    const double from_right = __shfl_down_sync(kFull, n[0], 1);
+    bool inside = true;
 #pragma unroll
-    for (int k = 0; k < K; ++k) n[k] = m[k];
+    for (int k = 0; k < K; ++k) {
+        double v = n[k];
+        if (k == 0) v = (lane == 0) ? ((K > 1) ? n[K > 1 ? 1 : 0] : from_right) : v;
+        if (j0 + k == nx - 1) v = (k > 0) ? n[k > 0 ? k - 1 : 0] : from_left;
+        inside = inside & (static_cast<unsigned>(__double2hiint(v)) < dv.k_hi);   // 0 <= v < k for sure
+        n[k] = v;
+    }
+    if (!inside) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double v = n[k];
+            n[k] = (v < 0.0) ? 0.0 : ((v > cfg.k) ? cfg.k : v);   // np.clip keeps NaN
+        }
+    }
 }
 
 __device__ __forceinline__ void bt_book(BtEnv& e) {
@@ -136,9 +166,11 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, BtEnv&
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
         const double bed = __dadd_rn(applied, __ddiv_rn(__dmul_rn(applied, applied), cfg.alpha_beta_ratio));
         const double rin = __dsub_rn(1.0, exp(__dmul_rn(-cfg.alpha, bed)));
-        bt_fd<K>(cfg, dv, u, n, lane, j0, e.D, e.rho, true, rin, cnt);
+        if (dv.dx2_one) bt_fd<K, true, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, rin, cnt);
+        else bt_fd<K, false, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, rin, cnt);
     } else {
-        bt_fd<K>(cfg, dv, u, n, lane, j0, e.D, e.rho, false, 0.0, 0);
+        if (dv.dx2_one) bt_fd<K, true, false>(cfg, dv, u, n, lane, j0, e.D, e.rho, 0.0, 0);
+        else bt_fd<K, false, false>(cfg, dv, u, n, lane, j0, e.D, e.rho, 0.0, 0);
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) u[k] = n[k];
@@ -185,8 +217,9 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, BtEnv&
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads, PDECG_BT_MINBLOCKS) bt_run_kernel(const BtArgs a) {
+// MULTI = false: PDECG_BT_RAW_STEP only (one day per launch); MULTI = true: the TherapyWrapper modes.
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(kThreads, MULTI ? PDECG_BT_MINBLOCKS_MULTI : PDECG_BT_MINBLOCKS) bt_run_kernel(const BtArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -232,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, PDECG_BT_MINBLOCKS) bt_run_kernel(co
     bool term = false, trunc = false, valid = true, wrote_obs = false;
     const int last = cfg.nt - 1;
 
-    if (a.mode == PDECG_BT_RAW_STEP) {
+    if constexpr (!MULTI) {
         if (e.t < last) {
             bt_day<K>(a, dv, e, u, lane, j0, a.buf.action[env], reward, term, trunc);
         } else {
@@ -390,7 +423,11 @@ extern "C" int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int K = (cfg->nx + 31) / 32;
     switch (K) {
-#define PDECG_CASE(KK) case KK: bt_run_kernel<KK><<<grid, kThreads, 0, st>>>(a); break;
+#define PDECG_CASE(KK)                                                                   \
+    case KK:                                                                             \
+        if (mode == PDECG_BT_RAW_STEP) bt_run_kernel<KK, false><<<grid, kThreads, 0, st>>>(a); \
+        else bt_run_kernel<KK, true><<<grid, kThreads, 0, st>>>(a);                      \
+        break;
         PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
 #undef PDECG_CASE
         default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);

@@ -50,7 +50,7 @@ def bench_bc1d(env_id, name, N, precision, kw, npts, beta, reward, pts, steps=30
     del env
 
 
-def main():
+def bench_transport():
     # ---- Transport: config 1 (single env, latency) and the PPO-rollout shape (2^18 envs per GPU) ----
     tkw = dict(T=1.0, dt=1e-4, X=1.0, dx=1e-2, control_sample_rate=0.1, normalize=True, max_control_value=20)
     tbeta = 5 * np.cos(7.35 * np.arccos(np.linspace(0, 1, 100)))
@@ -59,6 +59,9 @@ def main():
                    pcg.TunedReward1D(10000, -1e3, 3e2), 99 * 1000, steps=8 if N > 1000 else 20)
     bench_bc1d("PDEControlGym-TransportPDE1D", "TransportPDE1D fp64 x65536", 65536, "fp64", tkw, 100, tbeta,
                pcg.TunedReward1D(10000, -1e3, 3e2), 99 * 1000, steps=6, beta_dtype=np.float64)
+
+
+def bench_rd():
     # ---- ReactionDiffusion in the reference's own precision (f32 state) ----
     rkw = dict(T=1.0, dt=1e-5, X=1.0, dx=5e-3, control_sample_rate=1e-3, normalize=True, max_control_value=20)
     rbeta = 50 * np.cos(8 * np.arccos(np.linspace(0, 1, 201)))
@@ -69,6 +72,8 @@ def main():
     bench_bc1d("PDEControlGym-ReactionDiffusionPDE1D", "ReactionDiffusionPDE1D fp64 x65536 (TunedReward1D)", 65536, "fp64", rkw, 201, rbeta,
                pcg.TunedReward1D(100000, -1e3, 3e2), 199 * 100, beta_dtype=np.float64)
 
+
+def bench_arz():
     # ---- Traffic ARZ x16,384 (config 3) ----
     N = 16384
     env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=dev, simulation_type="outlet", reward_class=pcg.TrafficARZReward(),
@@ -91,6 +96,8 @@ def main():
     report("TrafficPDE1D outlet x262144 (control_freq=1)", N, ms, 49, {"hbm_gbs": N * (2 * 51 * 8 * 2 + 102 * 8 + 40) / (ms * 1e-3) / 1e9})
     del env
 
+
+def bench_bt():
     # ---- BrainTumor x16,384 (config 3) ----
     def bt_ic(X, nx, n=None):
         xs = np.linspace(0, X, nx)
@@ -121,6 +128,8 @@ def main():
         report(f"BrainTumor1D TherapyWrapper.benchmark()+reset() x{N} (~{days:.0f} days/env in 2 launches)", N, dt * 1e3 / days, 199)
         del env, w
 
+
+def bench_ns():
     # ---- NavierStokes2D x1,024 (config 4) ----
     bc = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
     for N in ([1024] if QUICK else [1024, 8192]):
@@ -133,6 +142,14 @@ def main():
         ms = timed(lambda i: env.step(acts[i % 32]), 20, warmup=3)
         report(f"NavierStokes2D 21x21, 2000 Jacobi sweeps x{N}", N, ms, 361 * 2000)
         del env
+
+
+def main():
+    """All families, or only those named in PDECG_BENCH_ONLY (comma list of: transport, rd, arz, bt, ns)."""
+    only = [t for t in os.environ.get("PDECG_BENCH_ONLY", "").split(",") if t]
+    for name, fn in (("transport", bench_transport), ("rd", bench_rd), ("arz", bench_arz), ("bt", bench_bt), ("ns", bench_ns)):
+        if not only or name in only:
+            fn()
 
 
 if __name__ == "__main__":
