@@ -13,7 +13,7 @@
 #define PDECG_BT_MINBLOCKS 1
 #endif
 #ifndef PDECG_ARZ_MINBLOCKS
-#define PDECG_ARZ_MINBLOCKS 10   // 48 registers, 40 warps/SM: latency/HBM-bound launch (measured best)
+#define PDECG_ARZ_MINBLOCKS 8    // 64 registers, 32 warps/SM (measured at 262k envs: 12 -> 0.285, 10 -> 0.262, 8 -> 0.254, 6 -> 0.297 ms)
 #endif
 namespace pdecg {
 
@@ -43,6 +43,39 @@ __device__ __forceinline__ double clipd(double v, double lo, double hi) {       
     return (v > hi) ? hi : v;
 }
 
+// Row <-> register-chunk transfers.  With K <= 2 points per lane the chunk is read / written directly (lane L touches
+// the 8K bytes at offset 8KL: every 32-byte sector is consumed by at most two adjacent lanes, and the second access
+// of a line hits L1), which drops the shared-memory staging and its two warp barriers per row; wider chunks go through
+// the staged, fully coalesced path.
+template <int K>
+__device__ __forceinline__ void arz_load_issue(double (&tmp)[K], const double* __restrict__ g, int npts, int lane) {
+    if constexpr (K <= 2) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) tmp[k] = (lane * K + k < npts) ? g[lane * K + k] : 0.0;
+    } else {
+        load_row_issue<double, double, K>(tmp, g, npts, lane);
+    }
+}
+template <int K>
+__device__ __forceinline__ void arz_load_finish(double (&r)[K], const double (&tmp)[K], double* sm, int lane) {
+    if constexpr (K <= 2) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = tmp[k];
+    } else {
+        load_row_finish<double, K>(r, tmp, sm, lane);
+    }
+}
+template <int K>
+__device__ __forceinline__ void arz_store(const double (&r)[K], double* __restrict__ g, int npts, double* sm, int lane) {
+    if constexpr (K <= 2) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (lane * K + k < npts) g[lane * K + k] = r[k];
+    } else {
+        store_row_chunk<double, K>(r, g, npts, sm, lane);
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel(const ArzArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
@@ -60,8 +93,8 @@ __global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel
     double* rrow = a.buf.ry + env * 2 * M;
     double* yrow = rrow + M;
     double r[K], y[K], r_raw[K], y_raw[K];
-    load_row_issue<double, double, K>(r_raw, rrow, M, lane);
-    load_row_issue<double, double, K>(y_raw, yrow, M, lane);
+    arz_load_issue<K>(r_raw, rrow, M, lane);
+    arz_load_issue<K>(y_raw, yrow, M, lane);
     double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
     const double fv = (lane < PDECG_ARZ_NF64) ? frow[lane] : 0.0;
     double time = __shfl_sync(kFull, fv, PDECG_ARZ_F_TIME);
@@ -69,8 +102,8 @@ __global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel
     const double vs = __shfl_sync(kFull, fv, PDECG_ARZ_F_VS);
     const double qs = __shfl_sync(kFull, fv, PDECG_ARZ_F_QS);
 
-    load_row_finish<double, K>(r, r_raw, sm, lane);
-    load_row_finish<double, K>(y, y_raw, sm, lane);
+    arz_load_finish<K>(r, r_raw, sm, lane);
+    arz_load_finish<K>(y, y_raw, sm, lane);
     // padding slots (never stored, never read by valid points) hold (rho, y) = (1, 1) so that the divisions
     // evaluated there stay on the fast path instead of div.rn's slow 0/0 path
 #pragma unroll
@@ -175,8 +208,8 @@ __global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel
     const bool trunc = (cfg.limit_pde_state_size && over) || steady;                  // :122-127
     if (st != PDECG_ARZ_OUTLET_TRAIN) term = term || (reward > -0.00023);             // :233
 
-    store_row_chunk<double, K>(r, rrow, M, sm, lane);
-    store_row_chunk<double, K>(y, yrow, M, sm, lane);
+    arz_store<K>(r, rrow, M, sm, lane);
+    arz_store<K>(y, yrow, M, sm, lane);
     double* orow = a.buf.obs + env * 2 * M;
     if (st == PDECG_ARZ_OUTLET_TRAIN) {                                               // :231
         double rn[K], vn[K];
@@ -185,11 +218,11 @@ __global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel
             rn[k] = D::div(D::sub(r[k], rs), rs);
             vn[k] = D::div(D::sub(v[k], vs), vs);
         }
-        store_row_chunk<double, K>(rn, orow, M, sm, lane);
-        store_row_chunk<double, K>(vn, orow + M, M, sm, lane);
+        arz_store<K>(rn, orow, M, sm, lane);
+        arz_store<K>(vn, orow + M, M, sm, lane);
     } else {
-        store_row_chunk<double, K>(r, orow, M, sm, lane);
-        store_row_chunk<double, K>(v, orow + M, M, sm, lane);
+        arz_store<K>(r, orow, M, sm, lane);
+        arz_store<K>(v, orow + M, M, sm, lane);
     }
     if (lane == 0) {
         frow[PDECG_ARZ_F_TIME] = time;
