@@ -51,6 +51,9 @@ struct Bc1dArgs {
 //   [0]            sum_t |u_t[-1]|              (tuned_reward_1d.py:37: np.sum(abs(uVec[:, -1])))
 //   [1 .. ring]    ring of step-end L2 norms    (tuned_reward_1d.py:40: norm(uVec[t-100]))
 constexpr int kLookback = 100;
+#ifndef PDECG_BC1D_MINBLOCKS_F32
+#define PDECG_BC1D_MINBLOCKS_F32 20  // float32 states: <= 102 registers, 20 warps/SM (measured Transport / RD ref: 12 -> 2.43 / 0.346, 16 -> 2.43 / 0.343, 20 -> 2.36 / 0.338, 24 -> 2.78 / 0.355 ms)
+#endif
 #ifndef PDECG_BC1D_MINBLOCKS
 #define PDECG_BC1D_MINBLOCKS 12  // x PDECG_BC1D_WARPS (1) = 12 warps per SM, <= 170 registers: measured best for the fp64 two-envs-per-warp kernel
 #endif
@@ -376,7 +379,8 @@ constexpr int kStepWarps = PDECG_BC1D_WARPS;
 constexpr int kStepThreads = kStepWarps * 32;
 
 template <int ENV, class M, int K, int VAR, int LPE = 32>
-__global__ void __launch_bounds__(kStepThreads, PDECG_BC1D_MINBLOCKS) bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
+__global__ void __launch_bounds__(kStepThreads, sizeof(typename M::S) == 8 ? PDECG_BC1D_MINBLOCKS : PDECG_BC1D_MINBLOCKS_F32)
+bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
     using S = typename M::S;
     using C = typename M::C;
     constexpr int EPW = 32 / LPE;                      // envs per warp

@@ -17,9 +17,6 @@
 #ifndef PDECG_BT_MINBLOCKS_MULTI
 #define PDECG_BT_MINBLOCKS_MULTI 4   // 128 registers: the multi-day (TherapyWrapper) launches are instruction-bound
 #endif
-#ifndef PDECG_ARZ_MINBLOCKS
-#define PDECG_ARZ_MINBLOCKS 1
-#endif
 namespace pdecg {
 
 struct BtArgs {
