@@ -97,7 +97,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         self.max_control_value = max_control_value
         self.control_sample_rate = control_sample_rate
         self.autoreset = bool(autoreset)
-        self.copy_obs = bool(copy_obs)   # False: step outputs are zero-copy views of live buffers (overwritten by the next step)
+        self.copy_obs = bool(copy_obs)   # False: full-state observations are zero-copy views of the live state
         self.env_id_offset = int(env_id_offset)   # global index of env 0 (multi-GPU sharding)
         self._seed, self._random_ic = 0, None
         # same messages as hyperbolic.py:60-62,87-89,122-124 / parabolic.py:85,114
@@ -337,11 +337,9 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         if self.copy_obs and self.sensing_loc == "full":
             obs_out = torch.empty_like(self.u)
             self._buf.obs_copy = obs_out.data_ptr()
-        reward, term_u8, trunc_u8 = self._reward, self._terminated, self._truncated
-        if self.copy_obs:
-            # the kernel writes reward / flags straight into fresh tensors handed to the caller (no clone launches)
-            reward, term_u8, trunc_u8 = torch.empty_like(reward), torch.empty_like(term_u8), torch.empty_like(trunc_u8)
-            self._buf.reward, self._buf.terminated, self._buf.truncated = reward.data_ptr(), term_u8.data_ptr(), trunc_u8.data_ptr()
+        # the kernel writes reward / flags straight into fresh tensors handed to the caller (no clone launches)
+        reward, term_u8, trunc_u8 = torch.empty_like(self._reward), torch.empty_like(self._terminated), torch.empty_like(self._truncated)
+        self._buf.reward, self._buf.terminated, self._buf.truncated = reward.data_ptr(), term_u8.data_ptr(), trunc_u8.data_ptr()
         ke = self._kernel_events          # optional (start, stop) CUDA events bracketing only the step kernel
         try:
             with torch.cuda.device(self.device):
@@ -354,7 +352,6 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                     _lib.check(self._L.pdecg_bc1d_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
                 if ke is not None:
                     ke[1].record()
-            # copy_obs: fresh tensors (above); otherwise zero-copy views the next step overwrites
             terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
             info = {}
         finally:

@@ -109,12 +109,22 @@ class BrainTumor1D(StateDictMixin):
         return _lib.current_raw_stream(self.device.index)
 
     def _run(self, mode, action=None):
+        """One launch.  The kernel writes reward / flags / valid straight into fresh tensors handed to the caller (no
+        clone launches); returns (reward, terminated_u8, truncated_u8, valid_u8)."""
         a = self._zero_action if action is None else action
-        self._buf.action = a.data_ptr()
+        buf = self._buf
+        buf.action = a.data_ptr()
         # the raw step's observation is the state itself: no second [N, nx] write (HBM-bound launch)
-        self._buf.obs = None if mode == RAW_STEP else self._obs.data_ptr()
-        with torch.cuda.device(self.device):
-            _lib.check(self._L.pdecg_bt_run(C.byref(self._cfg), C.byref(self._buf), mode, self._stream()))
+        buf.obs = None if mode == RAW_STEP else self._obs.data_ptr()
+        outs = tuple(torch.empty_like(t) for t in (self._reward, self._terminated, self._truncated, self._valid))
+        buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pdecg_bt_run(C.byref(self._cfg), C.byref(buf), mode, self._stream()))
+        finally:
+            buf.reward, buf.terminated, buf.truncated, buf.valid = (
+                self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(), self._valid.data_ptr())
+        return outs
 
     def _prep_action(self, action):
         if isinstance(action, torch.Tensor):
@@ -128,10 +138,14 @@ class BrainTumor1D(StateDictMixin):
             raise ValueError(f"action must have {self.num_envs} elements (got {a.numel()})")
         return a.contiguous()
 
-    def _outputs(self, obs_src):
-        obs = obs_src.clone() if self.copy_obs else obs_src
-        return (obs, self._reward.clone(), self._terminated.bool(), self._truncated.bool(),
-                {"stage": self._ienv[:, I_STAGE].clone(), "valid": self._valid.bool()})
+    def _outputs(self, obs_src, outs):
+        return ((obs_src.clone() if self.copy_obs else obs_src),) + self._out_rest(outs)
+
+    def _out_rest(self, outs):
+        """(reward, terminated, truncated, info) from the fresh tensors a launch wrote."""
+        reward, term_u8, trunc_u8, valid_u8 = outs
+        return (reward, term_u8.view(torch.bool), trunc_u8.view(torch.bool),
+                {"stage": self._ienv[:, I_STAGE].clone(), "valid": valid_u8.view(torch.bool)})
 
     # -- gym API -------------------------------------------------------------------------------
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
@@ -173,15 +187,14 @@ class BrainTumor1D(StateDictMixin):
         reference returns None) are left unchanged and flagged in info["valid"]."""
         if self._ic is None:
             raise RuntimeError("call reset() before step()")
-        self._run(RAW_STEP, self._prep_action(control))
-        out = self._outputs(self.u)
+        outs = self._run(RAW_STEP, self._prep_action(control))
+        rest = self._out_rest(outs)
         if self.autoreset:               # same-step auto-reset (the returned observation is the restarted state)
-            done = torch.bitwise_or(self._terminated, self._truncated)
+            done = torch.bitwise_or(outs[1], outs[2])
             with torch.cuda.device(self.device):
                 _lib.check(self._L.pdecg_bt_reset(C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
                                                   0 if self._ic.shape[0] == 1 else self.nx, done.data_ptr(), self._stream()))
-            out = ((self.u.clone() if self.copy_obs else self.u),) + out[1:]
-        return out
+        return ((self.u.clone() if self.copy_obs else self.u),) + rest
 
     # -- reference attributes, as per-env tensors ------------------------------------------------
     def _icol(self, i):
@@ -248,8 +261,8 @@ class TherapyWrapper:
     def step(self, control):
         env = self.env
         env._cfg.weekends = int(bool(self.weekends))
-        env._run(WRAP_STEP, env._prep_action(control))
-        return env._outputs(env._obs)
+        outs = env._run(WRAP_STEP, env._prep_action(control))
+        return env._outputs(env._obs, outs)
 
     def benchmark(self):
         """Runs a zero-dose episode per env, stores its length in `env.t_benchmark`, resets.  Returns the

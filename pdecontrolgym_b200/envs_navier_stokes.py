@@ -176,16 +176,24 @@ class NavierStokes2D(StateDictMixin):
         if a.numel() != self.num_envs:
             raise ValueError(f"action must have {self.num_envs} elements")
         a = a.contiguous()
-        self._buf.action = a.data_ptr()
-        with torch.cuda.device(self.device):
-            _lib.check(self._L.pdecg_ns_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
-        terminated, truncated, reward = self._terminated.bool(), self._truncated.bool(), self._reward.clone()
-        info = {"valid": self._valid.bool()}
+        buf = self._buf
+        buf.action = a.data_ptr()
+        internal = (self._reward, self._terminated, self._truncated, self._valid)
+        # the kernel writes reward / flags / valid straight into fresh tensors handed to the caller (no clone launches)
+        outs = tuple(torch.empty_like(t) for t in internal)
+        buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pdecg_ns_step(C.byref(self._cfg), C.byref(buf), self._stream()))
+        finally:
+            buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in internal)
+        reward, term_u8, trunc_u8, valid_u8 = outs
+        terminated, truncated, info = term_u8.view(torch.bool), trunc_u8.view(torch.bool), {"valid": valid_u8.view(torch.bool)}
         if self.autoreset:               # same-step auto-reset to the last initial fields
             iu, iv, ip = self._init
             with torch.cuda.device(self.device):
-                _lib.check(self._L.pdecg_ns_reset(C.byref(self._cfg), C.byref(self._buf), iu.data_ptr(), iv.data_ptr(), ip.data_ptr(),
-                                                  self.nx * self.ny, self._terminated.data_ptr(), self._stream()))
+                _lib.check(self._L.pdecg_ns_reset(C.byref(self._cfg), C.byref(buf), iu.data_ptr(), iv.data_ptr(), ip.data_ptr(),
+                                                  self.nx * self.ny, term_u8.data_ptr(), self._stream()))
         obs = self._obs.clone() if self.copy_obs else self._obs
         return obs, reward, terminated, truncated, info
 

@@ -176,17 +176,28 @@ class TrafficPDE1D(StateDictMixin):
         if a.numel() != self.num_envs * nact:
             raise ValueError(f"action must have shape ({self.num_envs}, {nact})")
         a = a.reshape(self.num_envs, nact).contiguous()
-        self._buf.action = a.data_ptr()
-        with torch.cuda.device(self.device):
-            _lib.check(self._L.pdecg_arz_step(C.byref(self._cfg), C.byref(self._buf), self._stream()))
-        terminated, truncated, reward = self._terminated.bool(), self._truncated.bool(), self._reward.clone()
-        if self.autoreset:               # same-step auto-reset: finished envs restart from the initial condition
-            done = torch.bitwise_or(self._terminated, self._truncated)
-            if self.simulation_type == "outlet-train":
-                self.reset(options={"mask": done})
-            else:
-                self._reset_kernel(done)
-        obs = self._obs.clone() if self.copy_obs else self._obs
+        buf = self._buf
+        buf.action = a.data_ptr()
+        # the kernels write reward / flags (and, with copy_obs, the observation) straight into fresh tensors handed to
+        # the caller: no clone launches
+        obs = torch.empty_like(self._obs) if self.copy_obs else self._obs
+        reward, term_u8, trunc_u8 = torch.empty_like(self._reward), torch.empty_like(self._terminated), torch.empty_like(self._truncated)
+        buf.obs, buf.reward, buf.terminated, buf.truncated = obs.data_ptr(), reward.data_ptr(), term_u8.data_ptr(), trunc_u8.data_ptr()
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pdecg_arz_step(C.byref(self._cfg), C.byref(buf), self._stream()))
+            terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
+            if self.autoreset:           # same-step auto-reset: finished envs restart from the initial condition
+                done = torch.bitwise_or(term_u8, trunc_u8)
+                # the restart writes the new observation rows where the step wrote; reward / flags go to the internal buffers
+                buf.reward, buf.terminated, buf.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
+                if self.simulation_type == "outlet-train":
+                    self.reset(options={"mask": done})
+                else:
+                    self._reset_kernel(done)
+        finally:
+            buf.obs, buf.reward, buf.terminated, buf.truncated = (self._obs.data_ptr(), self._reward.data_ptr(),
+                                                                  self._terminated.data_ptr(), self._truncated.data_ptr())
         return obs, reward, terminated, truncated, self.info
 
     # reference attributes
