@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, co
     const ArzCtx ctx(cfg);
     const int M = cfg.M;
     const double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
-    const double rs = frow[PDECG_ARZ_F_RS], vs = frow[PDECG_ARZ_F_VS], qs = frow[PDECG_ARZ_F_QS];
+    const double rs = frow[PDECG_ARZ_F_RS], qs = frow[PDECG_ARZ_F_QS];
     double* rrow = a.buf.ry + env * 2 * M;
     double* orow = a.buf.obs + env * 2 * M;
     for (int j = lane; j < M; j += 32) {
@@ -252,13 +252,8 @@ __global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, co
         const double v = D::add(D::div(y, r), veq(ctx, r));
         rrow[j] = r;
         rrow[M + j] = y;
-        if (cfg.simulation_type == PDECG_ARZ_OUTLET_TRAIN && false) {
-            orow[j] = D::div(D::sub(r, rs), rs);
-            orow[M + j] = D::div(D::sub(v, vs), vs);
-        } else {                                   // reset() always returns concat(r, v)  (:263)
-            orow[j] = r;
-            orow[M + j] = v;
-        }
+        orow[j] = r;                               // reset() returns concat(r, v) un-normalised in every mode,
+        orow[M + j] = v;                           // 'outlet-train' included (:263)
     }
     if (lane == 0) {
         a.buf.reward[env] = 0.0;
