@@ -226,6 +226,12 @@ int pdecg_bt_reset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const d
                    int64_t init_env_stride, const uint8_t* mask, pdecg_stream_t stream);
 /* One launch of `mode` (pdecg_bt_mode) for all envs. */
 int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t mode, pdecg_stream_t stream);
+/* PDECG_BT_RAW_STEP with the same-step auto-reset fused into the launch (vector-env convention, as
+ * pdecg_bc1d_step_autoreset): envs that come out of the day terminated or truncated (or were already past
+ * nt-1: valid == 0) are re-initialised exactly as pdecg_bt_reset(init, init_env_stride, mask = terminated |
+ * truncated) would do right after it, while reward / terminated / truncated / valid keep the step's values. */
+int pdecg_bt_step_autoreset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const double* init,
+                            int64_t init_env_stride, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Family 3: TrafficPDE1D (Aw-Rascle-Zhang) + TrafficARZReward      -- all float64
@@ -272,6 +278,13 @@ int pdecg_arz_reset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, cons
                     const uint8_t* mask, pdecg_stream_t stream);
 /* TrafficPDE1D.step (:131-233) + terminate/truncate (:103-127) + TrafficARZReward.reward. */
 int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, pdecg_stream_t stream);
+/* The same step with the same-step auto-reset fused into the launch: envs that come out terminated or truncated
+ * are re-initialised exactly as pdecg_arz_reset(profile, mask = terminated | truncated) would do right after it
+ * (state rows and the observation rows of buf->obs; the float time is left alone, like reset()), while reward /
+ * terminated / truncated keep the step's values.  fenv rows keep their rs / vs / qs ('outlet-train' callers that
+ * re-draw rs per episode use pdecg_arz_step + pdecg_arz_reset instead). */
+int pdecg_arz_step_autoreset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* profile,
+                             pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Family 4: NavierStokes2D (Chorin projection, Jacobi pressure solve) + NSReward   -- all float64
@@ -316,6 +329,13 @@ int pdecg_ns_reset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const d
                    const uint8_t* mask, pdecg_stream_t stream);
 /* NavierStokes2D.step (:118-157) incl. apply_boundary, solve_pressure, terminate and NSReward.reward. */
 int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, pdecg_stream_t stream);
+/* The same step with the same-step auto-reset fused into the launch: envs that come out terminated (or were already
+ * past the last step: valid == 0) are re-initialised exactly as pdecg_ns_reset(init_*, mask = terminated) would do
+ * right after it (u, v, p, obs <- U[0], time_index <- 0), while reward / terminated / truncated / valid keep the
+ * step's values. */
+int pdecg_ns_step_autoreset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* init_u,
+                            const double* init_v, const double* init_p, int64_t init_env_stride,
+                            pdecg_stream_t stream);
 /* NavierStokes2D.solve_pressure (:94-116) alone, for callers such as examples/NavierStokes/NS2Doptimization.py:
  * p <- n_pressure_iters Jacobi sweeps on rhs = density/dt * (d u/dx + d v/dy), warm-started from p. */
 int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v,

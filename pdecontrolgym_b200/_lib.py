@@ -144,15 +144,22 @@ def lib():
     L.pdecg_bt_reset.restype = C.c_int
     L.pdecg_bt_run.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers), C.c_int32, C.c_void_p]
     L.pdecg_bt_run.restype = C.c_int
+    L.pdecg_bt_step_autoreset.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers), C.c_void_p, C.c_int64, C.c_void_p]
+    L.pdecg_bt_step_autoreset.restype = C.c_int
     L.pdecg_arz_reset.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_arz_reset.restype = C.c_int
     L.pdecg_arz_step.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p]
     L.pdecg_arz_step.restype = C.c_int
+    L.pdecg_arz_step_autoreset.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p, C.c_void_p]
+    L.pdecg_arz_step_autoreset.restype = C.c_int
     L.pdecg_ns_reset.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p]
     L.pdecg_ns_reset.restype = C.c_int
     L.pdecg_ns_step.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers), C.c_void_p]
     L.pdecg_ns_step.restype = C.c_int
+    L.pdecg_ns_step_autoreset.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p]
+    L.pdecg_ns_step_autoreset.restype = C.c_int
     L.pdecg_ns_solve_pressure.argtypes = [C.POINTER(NsCfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_ns_solve_pressure.restype = C.c_int
     L.pdecg_selftest_constdiv.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]

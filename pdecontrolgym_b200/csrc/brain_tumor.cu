@@ -23,7 +23,11 @@ struct BtArgs {
     pdecg_bt_cfg cfg;
     pdecg_bt_buffers buf;
     int mode;
+    const double* ar_init;      // pdecg_bt_step_autoreset: finished envs restart inside the RAW_STEP launch (nullptr: off)
+    int64_t ar_stride;
 };
+
+__device__ __noinline__ void bt_autoreset_env(const BtArgs& a, int64_t env, int lane);   // defined after the reset kernel
 
 struct BtEnv {   // the reference's per-env attributes (brain_tumor_env.py:89-101)
     int t, stage, growthDays, therapyDays, postTherapyDays, simulationDays;
@@ -321,7 +325,7 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
 
 // MULTI = false: PDECG_BT_RAW_STEP only (one day per launch); MULTI = true: the TherapyWrapper modes.
 template <int K, bool MULTI>
-__global__ void __launch_bounds__(kThreads, MULTI ? PDECG_BT_MINBLOCKS_MULTI : PDECG_BT_MINBLOCKS) bt_run_kernel(const BtArgs a) {
+__global__ void __launch_bounds__(kThreads, MULTI ? PDECG_BT_MINBLOCKS_MULTI : PDECG_BT_MINBLOCKS) bt_run_kernel(const __grid_constant__ BtArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -455,14 +459,15 @@ __global__ void __launch_bounds__(kThreads, MULTI ? PDECG_BT_MINBLOCKS_MULTI : P
         a.buf.truncated[env] = trunc ? 1 : 0;
         if (a.buf.valid) a.buf.valid[env] = valid ? 1 : 0;
     }
+    if constexpr (!MULTI) {
+        if (a.ar_init != nullptr && (term || trunc)) bt_autoreset_env(a, env, lane);
+    }
 }
 
-__global__ void __launch_bounds__(kThreads) bt_reset_kernel(const BtArgs a, const double* __restrict__ init, int64_t init_stride,
-                                                            const uint8_t* __restrict__ mask) {
-    const int lane = threadIdx.x & 31;
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (env >= a.buf.n_envs) return;
-    if (mask != nullptr && mask[env] == 0) return;
+// BrainTumor1D.reset (:347-384) for one env, executed by its warp.  `keep_outputs`: leave reward / flags / valid alone
+// (fused auto-reset: they keep the step's values).
+__device__ __forceinline__ void bt_reset_env(const BtArgs& a, const double* __restrict__ init, int64_t init_stride, int64_t env,
+                                             int lane, bool keep_outputs) {
     const int nx = a.cfg.nx;
     const double* irow = init + env * init_stride;
     double* urow = a.buf.u + env * nx;
@@ -483,11 +488,28 @@ __global__ void __launch_bounds__(kThreads) bt_reset_kernel(const BtArgs a, cons
         double* fr = a.buf.fenv + env * PDECG_BT_NF64;
         fr[PDECG_BT_F_REMAINING] = a.cfg.total_dosage;
         fr[PDECG_BT_F_LAST_DOSE] = 0.0;
-        a.buf.reward[env] = 0.0;
-        a.buf.terminated[env] = 0;
-        a.buf.truncated[env] = 0;
-        if (a.buf.valid) a.buf.valid[env] = 1;
+        if (!keep_outputs) {
+            a.buf.reward[env] = 0.0;
+            a.buf.terminated[env] = 0;
+            a.buf.truncated[env] = 0;
+            if (a.buf.valid) a.buf.valid[env] = 1;
+        }
     }
+}
+
+// fused same-step auto-reset: out of line so the (rare) restart does not weigh on the step kernel's registers
+__device__ __noinline__ void bt_autoreset_env(const BtArgs& a, int64_t env, int lane) {
+    __syncwarp();                                  // the step's own row / scalar stores come first
+    bt_reset_env(a, a.ar_init, a.ar_stride, env, lane, true);
+}
+
+__global__ void __launch_bounds__(kThreads) bt_reset_kernel(const BtArgs a, const double* __restrict__ init, int64_t init_stride,
+                                                            const uint8_t* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (env >= a.buf.n_envs) return;
+    if (mask != nullptr && mask[env] == 0) return;
+    bt_reset_env(a, init, init_stride, env, lane, false);
 }
 
 static int bt_validate(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf) {
@@ -512,20 +534,21 @@ extern "C" int pdecg_bt_reset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* b
     if (rc != PDECG_OK) return rc;
     if (buf->n_envs == 0) return PDECG_OK;
     if (!init) return fail(PDECG_ERR_INVALID, "null init buffer");
-    BtArgs a{*cfg, *buf, 0};
+    BtArgs a{*cfg, *buf, 0, nullptr, 0};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     bt_reset_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init, init_env_stride, mask);
     count_launch();
     return check_launch("bt_reset_kernel");
 }
 
-extern "C" int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t mode, pdecg_stream_t stream) {
+static int bt_launch(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t mode, const double* ar_init, int64_t ar_stride,
+                     pdecg_stream_t stream) {
     int rc = bt_validate(cfg, buf);
     if (rc != PDECG_OK) return rc;
     if (mode < PDECG_BT_RAW_STEP || mode > PDECG_BT_RUN_TO_END) return fail(PDECG_ERR_INVALID, "bad mode %d", mode);
     if (buf->n_envs == 0) return PDECG_OK;
     if ((mode == PDECG_BT_RAW_STEP || mode == PDECG_BT_WRAP_STEP) && !buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
-    BtArgs a{*cfg, *buf, mode};
+    BtArgs a{*cfg, *buf, mode, ar_init, ar_stride};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int K = (cfg->nx + 31) / 32;
@@ -541,4 +564,14 @@ extern "C" int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf
     }
     count_launch();
     return check_launch("bt_run_kernel");
+}
+
+extern "C" int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t mode, pdecg_stream_t stream) {
+    return bt_launch(cfg, buf, mode, nullptr, 0, stream);
+}
+
+extern "C" int pdecg_bt_step_autoreset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const double* init,
+                                       int64_t init_env_stride, pdecg_stream_t stream) {
+    if (!init) return fail(PDECG_ERR_INVALID, "null init buffer");
+    return bt_launch(cfg, buf, PDECG_BT_RAW_STEP, init, init_env_stride, stream);
 }

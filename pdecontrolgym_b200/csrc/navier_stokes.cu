@@ -27,7 +27,37 @@ struct NsArgs {
     const double* sv;
     double* sp;
     int solve_only;
+    // pdecg_ns_step_autoreset: finished envs restart inside the step launch (ar_u == nullptr: off)
+    const double* ar_u;
+    const double* ar_v;
+    const double* ar_p;
+    int64_t ar_stride;
 };
+
+// NavierStokes2D.reset (:171-194) for one env, executed by `nth` cooperating threads (a CTA or a warp).
+// `keep_outputs`: leave reward / flags / valid alone (fused auto-reset: they keep the step's values).
+__device__ __forceinline__ void ns_reset_env(const NsArgs& a, const double* __restrict__ iu, const double* __restrict__ iv,
+                                             const double* __restrict__ ip, int64_t stride, int64_t env, int tid, int nth,
+                                             bool keep_outputs) {
+    const int npt = a.cfg.nx * a.cfg.ny;
+    for (int q = tid; q < npt; q += nth) {
+        const double un = iu[env * stride + q], vn = iv[env * stride + q];
+        a.buf.u[env * npt + q] = un;
+        a.buf.v[env * npt + q] = vn;
+        a.buf.p[env * npt + q] = ip[env * stride + q];
+        a.buf.obs[(env * npt + q) * 2] = un;
+        a.buf.obs[(env * npt + q) * 2 + 1] = vn;
+    }
+    if (tid == 0) {
+        a.buf.time_index[env] = 0;
+        if (!keep_outputs) {
+            a.buf.reward[env] = 0.0;
+            a.buf.terminated[env] = 0;
+            a.buf.truncated[env] = 0;
+            if (a.buf.valid) a.buf.valid[env] = 1;
+        }
+    }
+}
 
 using D = Strict<double>;
 constexpr int kNsThreads = 256;
@@ -151,6 +181,7 @@ __global__ void __launch_bounds__(kNsThreads) ns_step_kernel(const NsArgs a) {
             a.buf.truncated[env] = 0;
             a.buf.reward[env] = 0.0;
         }
+        if (a.ar_u != nullptr) ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
         return;
     }
     double* gu = a.buf.u + env * npt;
@@ -238,28 +269,17 @@ __global__ void __launch_bounds__(kNsThreads) ns_step_kernel(const NsArgs a) {
         a.buf.truncated[env] = 0;
         if (a.buf.valid) a.buf.valid[env] = 1;
     }
+    if (a.ar_u != nullptr && t1 >= cfg.nt - 1) {          // same-step auto-reset (block-uniform condition)
+        __syncthreads();                                  // the step's own field / observation stores come first
+        ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
+    }
 }
 
 __global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, const double* __restrict__ iu, const double* __restrict__ iv,
                                                               const double* __restrict__ ip, int64_t stride, const uint8_t* __restrict__ mask) {
     const int64_t env = blockIdx.x;
     if (mask != nullptr && mask[env] == 0) return;
-    const int npt = a.cfg.nx * a.cfg.ny;
-    for (int q = threadIdx.x; q < npt; q += blockDim.x) {
-        const double un = iu[env * stride + q], vn = iv[env * stride + q];
-        a.buf.u[env * npt + q] = un;
-        a.buf.v[env * npt + q] = vn;
-        a.buf.p[env * npt + q] = ip[env * stride + q];
-        a.buf.obs[(env * npt + q) * 2] = un;
-        a.buf.obs[(env * npt + q) * 2 + 1] = vn;
-    }
-    if (threadIdx.x == 0) {
-        a.buf.time_index[env] = 0;
-        a.buf.reward[env] = 0.0;
-        a.buf.terminated[env] = 0;
-        a.buf.truncated[env] = 0;
-        if (a.buf.valid) a.buf.valid[env] = 1;
-    }
+    ns_reset_env(a, iu, iv, ip, stride, env, threadIdx.x, blockDim.x, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -295,6 +315,7 @@ __global__ void __launch_bounds__(kThreads) ns_step_warp_kernel(const NsArgs a) 
             a.buf.truncated[env] = 0;
             a.buf.reward[env] = 0.0;
         }
+        if (a.ar_u != nullptr) ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, 32, true);
         return;
     }
     const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
@@ -479,6 +500,10 @@ __global__ void __launch_bounds__(kThreads) ns_step_warp_kernel(const NsArgs a) 
         a.buf.truncated[env] = 0;
         if (a.buf.valid) a.buf.valid[env] = 1;
     }
+    if (a.ar_u != nullptr && t1 >= cfg.nt - 1) {          // same-step auto-reset (warp-uniform condition)
+        __syncwarp();                                     // the step's own field / observation stores come first
+        ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, 32, true);
+    }
 }
 
 static int ns_validate_cfg(const pdecg_ns_cfg* cfg) {
@@ -514,20 +539,21 @@ extern "C" int pdecg_ns_reset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* b
     if (buf->n_envs == 0) return PDECG_OK;
     if (!init_u || !init_v || !init_p || !buf->u || !buf->v || !buf->p || !buf->obs || !buf->time_index || !buf->reward || !buf->terminated || !buf->truncated)
         return fail(PDECG_ERR_INVALID, "null device buffer");
-    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0};
+    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0};
     ns_reset_kernel<<<static_cast<unsigned>(buf->n_envs), kNsThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init_u, init_v, init_p, init_env_stride, mask);
     count_launch();
     return check_launch("ns_reset_kernel");
 }
 
-extern "C" int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, pdecg_stream_t stream) {
+static int ns_launch_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* ar_u, const double* ar_v,
+                          const double* ar_p, int64_t ar_stride, pdecg_stream_t stream) {
     int rc = ns_validate_cfg(cfg);
     if (rc != PDECG_OK) return rc;
     if (!buf || buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "bad buffers");
     if (buf->n_envs == 0) return PDECG_OK;
     if (!buf->u || !buf->v || !buf->p || !buf->obs || !buf->action || !buf->u_ref || !buf->action_ref || !buf->time_index || !buf->reward || !buf->terminated || !buf->truncated)
         return fail(PDECG_ERR_INVALID, "null device buffer");
-    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0};
+    NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0, ar_u, ar_v, ar_p, ar_stride};
     if (cfg->nx == 21 && cfg->ny == 21 && !getenv("PDECG_NS_GENERIC")) {
         // the reference grid (examples/NavierStokes/NS2Dppo.py:29-32): warp-per-env register kernel
         constexpr int kN = 19;
@@ -545,6 +571,16 @@ extern "C" int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* bu
     ns_step_kernel<<<static_cast<unsigned>(buf->n_envs), kNsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     count_launch();
     return check_launch("ns_step_kernel");
+}
+
+extern "C" int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, pdecg_stream_t stream) {
+    return ns_launch_step(cfg, buf, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int pdecg_ns_step_autoreset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* init_u, const double* init_v,
+                                       const double* init_p, int64_t init_env_stride, pdecg_stream_t stream) {
+    if (!init_u || !init_v || !init_p) return fail(PDECG_ERR_INVALID, "null init buffer");
+    return ns_launch_step(cfg, buf, init_u, init_v, init_p, init_env_stride, stream);
 }
 
 extern "C" int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v, double* p,

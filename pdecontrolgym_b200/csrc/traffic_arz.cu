@@ -20,6 +20,7 @@ namespace pdecg {
 struct ArzArgs {
     pdecg_arz_cfg cfg;
     pdecg_arz_buffers buf;
+    const double* ar_profile;   // pdecg_arz_step_autoreset: finished envs restart inside the step launch (nullptr: off)
 };
 
 using D = Strict<double>;
@@ -76,8 +77,10 @@ __device__ __forceinline__ void arz_store(const double (&r)[K], double* __restri
     }
 }
 
+__device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane);   // defined after the reset kernel
+
 template <int K>
-__global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel(const ArzArgs a) {
+__global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel(const __grid_constant__ ArzArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -230,14 +233,13 @@ __global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel
         a.buf.terminated[env] = term ? 1 : 0;
         a.buf.truncated[env] = trunc ? 1 : 0;
     }
+    if (a.ar_profile != nullptr && (term || trunc)) arz_autoreset_env(a, env, lane);
 }
 
-__global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, const double* __restrict__ profile,
-                                                             const uint8_t* __restrict__ mask) {
-    const int lane = threadIdx.x & 31;
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (env >= a.buf.n_envs) return;
-    if (mask != nullptr && mask[env] == 0) return;
+// TrafficPDE1D.reset (:237-267) for one env, executed by its warp.  `keep_outputs`: leave reward / flags alone
+// (fused auto-reset: they keep the step's values).
+__device__ __forceinline__ void arz_reset_env(const ArzArgs& a, const double* __restrict__ profile, int64_t env, int lane,
+                                              bool keep_outputs) {
     const pdecg_arz_cfg& cfg = a.cfg;
     const ArzCtx ctx(cfg);
     const int M = cfg.M;
@@ -255,11 +257,26 @@ __global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, co
         orow[j] = r;                               // reset() returns concat(r, v) un-normalised in every mode,
         orow[M + j] = v;                           // 'outlet-train' included (:263)
     }
-    if (lane == 0) {
+    if (lane == 0 && !keep_outputs) {
         a.buf.reward[env] = 0.0;
         a.buf.terminated[env] = 0;
         a.buf.truncated[env] = 0;
     }
+}
+
+// fused same-step auto-reset: out of line so the (rare) restart does not weigh on the step kernel's registers
+__device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane) {
+    __syncwarp();                                  // the step's own row / observation stores come first
+    arz_reset_env(a, a.ar_profile, env, lane, true);
+}
+
+__global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, const double* __restrict__ profile,
+                                                             const uint8_t* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (env >= a.buf.n_envs) return;
+    if (mask != nullptr && mask[env] == 0) return;
+    arz_reset_env(a, profile, env, lane, false);
 }
 
 static int arz_validate(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf) {
@@ -286,19 +303,19 @@ extern "C" int pdecg_arz_reset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers
     if (rc != PDECG_OK) return rc;
     if (buf->n_envs == 0) return PDECG_OK;
     if (!profile) return fail(PDECG_ERR_INVALID, "null profile buffer");
-    ArzArgs a{*cfg, *buf};
+    ArzArgs a{*cfg, *buf, nullptr};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     arz_reset_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, profile, mask);
     count_launch();
     return check_launch("arz_reset_kernel");
 }
 
-extern "C" int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, pdecg_stream_t stream) {
+static int arz_launch_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* ar_profile, pdecg_stream_t stream) {
     int rc = arz_validate(cfg, buf);
     if (rc != PDECG_OK) return rc;
     if (buf->n_envs == 0) return PDECG_OK;
     if (!buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
-    ArzArgs a{*cfg, *buf};
+    ArzArgs a{*cfg, *buf, ar_profile};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int K = (cfg->M + 31) / 32;
@@ -310,4 +327,14 @@ extern "C" int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers*
     }
     count_launch();
     return check_launch("arz_step_kernel");
+}
+
+extern "C" int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, pdecg_stream_t stream) {
+    return arz_launch_step(cfg, buf, nullptr, stream);
+}
+
+extern "C" int pdecg_arz_step_autoreset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* profile,
+                                        pdecg_stream_t stream) {
+    if (!profile) return fail(PDECG_ERR_INVALID, "null profile buffer");
+    return arz_launch_step(cfg, buf, profile, stream);
 }

@@ -108,9 +108,10 @@ class BrainTumor1D(StateDictMixin):
     def _stream(self):
         return _lib.current_raw_stream(self.device.index)
 
-    def _run(self, mode, action=None):
+    def _run(self, mode, action=None, autoreset=False):
         """One launch.  The kernel writes reward / flags / valid straight into fresh tensors handed to the caller (no
-        clone launches); returns (reward, terminated_u8, truncated_u8, valid_u8)."""
+        clone launches); returns (reward, terminated_u8, truncated_u8, valid_u8).  `autoreset` (RAW_STEP only): envs
+        that finish restart from the last initial condition inside the same launch."""
         a = self._zero_action if action is None else action
         buf = self._buf
         buf.action = a.data_ptr()
@@ -120,7 +121,11 @@ class BrainTumor1D(StateDictMixin):
         buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
         try:
             with torch.cuda.device(self.device):
-                _lib.check(self._L.pdecg_bt_run(C.byref(self._cfg), C.byref(buf), mode, self._stream()))
+                if autoreset:
+                    _lib.check(self._L.pdecg_bt_step_autoreset(C.byref(self._cfg), C.byref(buf), self._ic.data_ptr(),
+                                                               0 if self._ic.shape[0] == 1 else self.nx, self._stream()))
+                else:
+                    _lib.check(self._L.pdecg_bt_run(C.byref(self._cfg), C.byref(buf), mode, self._stream()))
         finally:
             buf.reward, buf.terminated, buf.truncated, buf.valid = (
                 self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(), self._valid.data_ptr())
@@ -187,13 +192,9 @@ class BrainTumor1D(StateDictMixin):
         reference returns None) are left unchanged and flagged in info["valid"]."""
         if self._ic is None:
             raise RuntimeError("call reset() before step()")
-        outs = self._run(RAW_STEP, self._prep_action(control))
+        # same-step auto-reset is part of the step launch (the returned observation is the restarted state)
+        outs = self._run(RAW_STEP, self._prep_action(control), autoreset=self.autoreset)
         rest = self._out_rest(outs)
-        if self.autoreset:               # same-step auto-reset (the returned observation is the restarted state)
-            done = torch.bitwise_or(outs[1], outs[2])
-            with torch.cuda.device(self.device):
-                _lib.check(self._L.pdecg_bt_reset(C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
-                                                  0 if self._ic.shape[0] == 1 else self.nx, done.data_ptr(), self._stream()))
         return ((self.u.clone() if self.copy_obs else self.u),) + rest
 
     # -- reference attributes, as per-env tensors ------------------------------------------------

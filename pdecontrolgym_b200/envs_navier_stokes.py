@@ -184,16 +184,16 @@ class NavierStokes2D(StateDictMixin):
         buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
         try:
             with torch.cuda.device(self.device):
-                _lib.check(self._L.pdecg_ns_step(C.byref(self._cfg), C.byref(buf), self._stream()))
+                if self.autoreset:       # same-step auto-reset to the last initial fields, inside the step launch
+                    iu, iv, ip = self._init
+                    _lib.check(self._L.pdecg_ns_step_autoreset(C.byref(self._cfg), C.byref(buf), iu.data_ptr(), iv.data_ptr(),
+                                                               ip.data_ptr(), self.nx * self.ny, self._stream()))
+                else:
+                    _lib.check(self._L.pdecg_ns_step(C.byref(self._cfg), C.byref(buf), self._stream()))
         finally:
             buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in internal)
         reward, term_u8, trunc_u8, valid_u8 = outs
         terminated, truncated, info = term_u8.view(torch.bool), trunc_u8.view(torch.bool), {"valid": valid_u8.view(torch.bool)}
-        if self.autoreset:               # same-step auto-reset to the last initial fields
-            iu, iv, ip = self._init
-            with torch.cuda.device(self.device):
-                _lib.check(self._L.pdecg_ns_reset(C.byref(self._cfg), C.byref(buf), iu.data_ptr(), iv.data_ptr(), ip.data_ptr(),
-                                                  self.nx * self.ny, term_u8.data_ptr(), self._stream()))
         obs = self._obs.clone() if self.copy_obs else self._obs
         return obs, reward, terminated, truncated, info
 

@@ -183,18 +183,22 @@ class TrafficPDE1D(StateDictMixin):
         obs = torch.empty_like(self._obs) if self.copy_obs else self._obs
         reward, term_u8, trunc_u8 = torch.empty_like(self._reward), torch.empty_like(self._terminated), torch.empty_like(self._truncated)
         buf.obs, buf.reward, buf.terminated, buf.truncated = obs.data_ptr(), reward.data_ptr(), term_u8.data_ptr(), trunc_u8.data_ptr()
+        # same-step auto-reset: finished envs restart from the initial condition inside the step launch (the restart
+        # writes the new observation rows where the step wrote).  'outlet-train' re-draws rs per episode on the host, so
+        # it keeps the step + masked-reset sequence.
+        fused = self.autoreset and self.simulation_type != "outlet-train"
         try:
             with torch.cuda.device(self.device):
-                _lib.check(self._L.pdecg_arz_step(C.byref(self._cfg), C.byref(buf), self._stream()))
-            terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
-            if self.autoreset:           # same-step auto-reset: finished envs restart from the initial condition
-                done = torch.bitwise_or(term_u8, trunc_u8)
-                # the restart writes the new observation rows where the step wrote; reward / flags go to the internal buffers
-                buf.reward, buf.terminated, buf.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
-                if self.simulation_type == "outlet-train":
-                    self.reset(options={"mask": done})
+                if fused:
+                    _lib.check(self._L.pdecg_arz_step_autoreset(C.byref(self._cfg), C.byref(buf), self._profile.data_ptr(), self._stream()))
                 else:
-                    self._reset_kernel(done)
+                    _lib.check(self._L.pdecg_arz_step(C.byref(self._cfg), C.byref(buf), self._stream()))
+            terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
+            if self.autoreset and not fused:
+                done = torch.bitwise_or(term_u8, trunc_u8)
+                # reward / flags of the restart go to the internal buffers
+                buf.reward, buf.terminated, buf.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
+                self.reset(options={"mask": done})
         finally:
             buf.obs, buf.reward, buf.terminated, buf.truncated = (self._obs.data_ptr(), self._reward.data_ptr(),
                                                                   self._terminated.data_ptr(), self._truncated.data_ptr())

@@ -188,3 +188,116 @@ def test_bc1d_fused_autoreset_equals_step_then_masked_reset(cuda_device, env_id,
             x, y = getattr(fused, name), getattr(manual, name)
             assert torch.equal(x, y), f"step {k}: {name} differs at {(x != y).nonzero()[:6].tolist()} done={done.tolist()} fused={x[x != y][:6].tolist()} manual={y[x != y][:6].tolist()}"
     assert n_done >= N
+
+
+def _staggered_pair(fused, manual, reset, act, steps, state_names, stagger):
+    """Step a fused-autoreset env and a manual (step, then masked reset) twin through several staggered episodes and
+    compare every output and every piece of carried state bit for bit."""
+    import torch
+    o1, o2 = reset(fused, None), reset(manual, None)
+    assert torch.equal(o1, o2)
+    stagger(fused), stagger(manual)                     # only some envs finish at a time
+    n_done = 0
+    for k in range(steps):
+        o1, r1, te1, tr1, i1 = fused.step(act(k))
+        o2, r2, te2, tr2, i2 = manual.step(act(k))
+        done = te2 | tr2
+        if done.any():
+            o2r = reset(manual, done)
+            o2 = torch.where(done.reshape((-1,) + (1,) * (o2.dim() - 1)), o2r, o2)
+            n_done += int(done.sum())
+        assert torch.equal(te1, te2) and torch.equal(tr1, tr2) and torch.equal(r1, r2), f"step {k}: outputs"
+        if "valid" in i2:
+            assert torch.equal(i1["valid"], i2["valid"])
+        assert torch.equal(o1, o2), f"step {k}: observation"
+        for name in state_names:
+            assert torch.equal(getattr(fused, name), getattr(manual, name)), f"step {k}: {name}"
+    return n_done
+
+
+def _stagger_by_masked_reset(reset, act, mask):
+    def go(env):
+        for k in range(2):
+            env.step(act(k))
+        reset(env, mask)
+    return go
+
+
+@pytest.mark.parametrize("simulation_type,dx,vm", [("outlet", 10, 40), ("both", 10, 40), ("inlet", 4, 10)])
+def test_arz_fused_autoreset_equals_step_then_masked_reset(cuda_device, simulation_type, dx, vm):
+    """pdecg_arz_step_autoreset == pdecg_arz_step followed by pdecg_arz_reset on the finished envs (dx = 4 -> 126
+    points, K = 4: the staged row path)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    N = 9
+    kw = dict(T=1.5, dt=0.25, X=500, dx=dx, simulation_type=simulation_type, v_max=vm, v_steady=vm * (1 - 0.12 / 0.16))   # 24 steps per episode
+    fused = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=cuda_device, autoreset=True, **kw)
+    manual = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=cuda_device, autoreset=False, **kw)
+    rng = np.random.default_rng(3)
+    nact = 2 if simulation_type == "both" else 1
+    qs = vm * (1 - 0.12 / 0.16) * 0.12
+    acts = [torch.from_numpy(rng.uniform(0.7 * qs, 1.3 * qs, (N, nact))) for _ in range(64)]
+
+    def reset(env, mask):
+        return env.reset(options=None if mask is None else {"mask": mask})[0]
+
+    def stagger(env):        # reset() leaves the float time alone (reference quirk), so offset it directly
+        env._fenv[:, 0] = torch.arange(N, dtype=torch.float64, device=env.device) % 4 * (3 * 0.25)
+
+    n_done = _staggered_pair(fused, manual, reset, lambda k: acts[k], 60, ("_ry", "_fenv"), stagger)
+    assert n_done >= N
+
+
+def test_brain_tumor_fused_autoreset_equals_step_then_masked_reset(cuda_device):
+    """pdecg_bt_step_autoreset == pdecg_bt_run(RAW_STEP) followed by pdecg_bt_reset on the finished envs; per-env
+    parameters make some patients die (truncate) and others reach the last day (terminate)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    N = 8
+    xs = np.linspace(0, 200, 201)
+    rng = np.random.default_rng(5)
+    ic = 0.8e5 * np.exp(-0.25 * xs ** 2)[None, :] * rng.uniform(0.5, 1.5, (N, 1))
+    kw = dict(total_dosage=61.2, T=40, dt=1, X=200, dx=1, D=rng.uniform(0.1, 0.3, N), rho=np.linspace(0.02, 0.5, N),
+              t1_detection_radius=3, t1_death_radius=6)
+    fused = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, autoreset=True, **kw)
+    manual = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, autoreset=False, **kw)
+    acts = [torch.from_numpy(rng.uniform(0, 0.1, N)) for _ in range(130)]
+
+    def reset(env, mask):
+        opts = {"init_condition": ic}
+        if mask is not None:
+            opts["mask"] = mask
+        return env.reset(options=opts)[0]
+
+    stag = np.array([True, False, True, False, False, True, False, True])
+    n_done = _staggered_pair(fused, manual, reset, lambda k: acts[k], 125, ("u", "_ienv", "_fenv"),
+                             _stagger_by_masked_reset(reset, lambda k: acts[k], stag))
+    assert n_done >= N
+
+
+@pytest.mark.parametrize("dx", [0.05, 0.1])
+def test_navier_stokes_fused_autoreset_equals_step_then_masked_reset(cuda_device, dx):
+    """pdecg_ns_step_autoreset == pdecg_ns_step followed by pdecg_ns_reset on the finished envs, for the warp kernel
+    (21 x 21) and the generic shared-memory kernel (11 x 11)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    N = 5
+    n = int(round(1 / dx + 1))
+    rng = np.random.default_rng(7)
+    kw = dict(boundary_condition=BC, U_ref=rng.uniform(-1, 1, (50, n, n, 2)), action_ref=np.ones(100), reward_class=pcg.NSReward(0.1),
+              maximum_pressure_iteration=7, T=0.006, dt=1e-3, X=1, dx=dx, Y=1, dy=dx)
+    fused = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, autoreset=True, **kw)
+    manual = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, autoreset=False, **kw)
+    init = tuple(rng.uniform(-1, 1, (N, n, n)) for _ in range(3))
+    acts = [torch.from_numpy(rng.uniform(2, 4, N)) for _ in range(20)]
+
+    def reset(env, mask):
+        opts = {"init": init}
+        if mask is not None:
+            opts["mask"] = mask
+        return env.reset(options=opts)[0]
+
+    stag = np.array([True, False, True, False, False])
+    n_done = _staggered_pair(fused, manual, reset, lambda k: acts[k], 16, ("u", "v", "p", "time_index"),
+                             _stagger_by_masked_reset(reset, lambda k: acts[k], stag))
+    assert n_done >= N
