@@ -20,6 +20,7 @@ from .envs_navier_stokes import NavierStokes2D, central_difference, laplace
 from .dist import EpisodeStats, shard_range
 from . import adapters, controllers
 from .graph import GraphedStep
+from ._lib import PdecgError
 
 __version__ = "0.1.0"
 
@@ -43,5 +44,5 @@ def make(id: str, num_envs: int = 1, device="cuda", precision: str = "ref", **kw
 
 make_vec = make
 
-__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "EpisodeStats", "shard_range", "UniformScaleIC", "GraphedStep", "BaseReward",
+__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "EpisodeStats", "shard_range", "UniformScaleIC", "GraphedStep", "PdecgError", "BaseReward",
            "NormReward", "TunedReward1D", "NSReward", "TrafficARZReward", "BrainTumorReward"]

@@ -62,7 +62,7 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     out->ring_len = out->tuned_general ? kLookback + 1 : ring_len_for(cfg->substeps);
     out->carry_len = 1 + out->ring_len;
     out->ar = AutoReset{};
-    if (out->npts > 512) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 512 points per env", out->npts);
+    if (out->npts > kCtaMaxPoints) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the shared-memory-resident limit of %d points per env", out->npts, kCtaMaxPoints);
     return PDECG_OK;
 }
 

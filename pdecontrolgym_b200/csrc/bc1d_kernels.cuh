@@ -51,6 +51,7 @@ struct Bc1dArgs {
 //   [0]            sum_t |u_t[-1]|              (tuned_reward_1d.py:37: np.sum(abs(uVec[:, -1])))
 //   [1 .. ring]    ring of step-end L2 norms    (tuned_reward_1d.py:40: norm(uVec[t-100]))
 constexpr int kLookback = 100;
+constexpr int kWarpMaxPoints = 512;      // register-resident warp kernels: 32 lanes x up to 16 points
 #ifndef PDECG_BC1D_MINBLOCKS_F32
 #define PDECG_BC1D_MINBLOCKS_F32 20  // float32 states: <= 102 registers, 20 warps/SM (measured Transport / RD ref: 12 -> 2.43 / 0.346, 16 -> 2.43 / 0.343, 20 -> 2.36 / 0.338, 24 -> 2.78 / 0.355 ms)
 #endif
@@ -682,7 +683,11 @@ inline int launch_k(const Bc1dArgs& a, int LPE, int K, cudaStream_t st) {
 }
 
 template <int ENV, class M>
+inline int launch_cta(const Bc1dArgs& a, cudaStream_t st);       // bc1d_large.cuh
+
+template <int ENV, class M>
 inline int launch_var(const Bc1dArgs& a, cudaStream_t st) {
+    if (a.npts > kWarpMaxPoints) return launch_cta<ENV, M>(a, st);   // beyond the register-resident limit: CTA per env
     int LPE, K, var;
     pick_variant(a, &LPE, &K, &var);
     if (var == kVarFast) return launch_k<ENV, M, kVarFast>(a, LPE, K, st);
@@ -699,3 +704,5 @@ int launch_bc1d_fp64(const Bc1dArgs& a, cudaStream_t st);
 int launch_bc1d_fp32(const Bc1dArgs& a, cudaStream_t st);
 
 }  // namespace pdecg
+
+#include "bc1d_large.cuh"

@@ -1,0 +1,256 @@
+// bc1d_large.cuh -- TransportPDE1D / ReactionDiffusionPDE1D step kernel for grids beyond the register-resident
+// limit of the warp kernels (more than 512 points per env): ONE CTA = ONE ENV.
+//
+// Reference behaviour restated here (no code shared): hyperbolic.py:126-227, parabolic.py:126-221,
+// base_env_1d.py:20-45, tuned_reward_1d.py:25-40, norm_reward.py:29-73 of lukebhan/PDEControlGym.
+//
+// The env's row lives in shared memory (two ping-pong copies + the per-point coefficient row) for all substeps of a
+// control step; thread t updates the points t, t + THREADS, ... (conflict-free shared-memory accesses), one block
+// barrier per substep.  Same arithmetic, operation order and reward / flag semantics as the warp kernels
+// (bc1d_kernels.cuh) -- states are bit-identical to numpy -- and HBM still carries one row in and out per control
+// step.  Included at the end of bc1d_kernels.cuh.
+#pragma once
+
+namespace pdecg {
+
+constexpr int kCtaMaxThreads = 1024;
+constexpr int kCtaMaxPoints = 8192;      // 2 x 8 B state copies + 8 B coefficient per point = 192 KB of the 227 KB per CTA
+
+// Sum / NaN-propagating max over the CTA in a fixed order (warp xor tree, then the warps' partial results in
+// ascending order): deterministic from launch to launch.  `red` holds 32 doubles.  Every thread gets the result.
+__device__ __forceinline__ double cta_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();                                   // protects `red` against the previous reduction's readers
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) tot += red[w];
+    return tot;
+}
+__device__ __forceinline__ double cta_nanmax(double v, double* red) {
+    v = seg_nanmax<32>(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) tot = nanmax(tot, red[w]);
+    return tot;
+}
+
+template <typename S>
+__device__ __forceinline__ double cta_sumsq(const S* row, int npts, double* red) {
+    double s = 0.0;
+    for (int j = threadIdx.x; j < npts; j += blockDim.x) {
+        const double v = static_cast<double>(row[j]);
+        s += v * v;
+    }
+    return cta_sum(s, red);
+}
+
+// ||row||_ord (or ||row - other||_ord when `other` is given; the difference is formed in the state dtype like numpy)
+template <typename S>
+__device__ __forceinline__ double cta_norm(const S* row, const S* other, int npts, int ord, double* red) {
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < npts; j += blockDim.x) {
+        const S d = other ? Strict<S>::sub(row[j], other[j]) : row[j];
+        const double v = static_cast<double>(d);
+        if (ord == kNormL2) acc += v * v;
+        else if (ord == kNormL1) acc += fabs(v);
+        else acc = nanmax(acc, fabs(v));
+    }
+    if (ord == kNormL2) return sqrt(cta_sum(acc, red));
+    if (ord == kNormL1) return cta_sum(acc, red);
+    return cta_nanmax(acc, red);
+}
+
+template <int ENV, class M>
+__global__ void __launch_bounds__(kCtaMaxThreads, 1) bc1d_step_cta_kernel(const __grid_constant__ Bc1dArgs a) {
+    using S = typename M::S;
+    using C = typename M::C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    const pdecg_bc1d_cfg& cfg = a.cfg;
+    const int npts = a.npts;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int64_t env = blockIdx.x;
+    C* coef = reinterpret_cast<C*>(smem_raw);                         // RD: dt*beta_j ; Transport: beta_j
+    S* cur = reinterpret_cast<S*>(coef + npts);
+    S* nxt = cur + npts;
+
+    const S Fs = static_cast<S>(cfg.dt / (cfg.dx * cfg.dx));          // parabolic.py:138 (python float -> S)
+    const S dxs = static_cast<S>(cfg.dx);
+    const C dtc = static_cast<C>(cfg.dt);
+    const ConstDiv<S> by_dx(dxs);
+    const int jb = npts - 1;                                          // actuated point (x = X; ghost point for RD)
+
+    S* urow = static_cast<S*>(a.buf.u) + env * npts;
+    const C* brow = static_cast<const C*>(a.buf.beta) + env * a.buf.beta_env_stride;
+    for (int j = tid; j < npts; j += nth) {
+        cur[j] = urow[j];
+        const C b = brow[j];
+        if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) coef[j] = M::kFast ? dtc * b : Strict<C>::mul(dtc, b);   // parabolic.py:144
+        else coef[j] = b;
+    }
+    __syncthreads();
+
+    const int t0 = a.buf.time_index[env];
+    int nsub = cfg.nt - 1 - t0;
+    nsub = nsub < 0 ? 0 : (nsub > cfg.substeps ? cfg.substeps : nsub);
+    const int t_end = t0 + nsub;
+    double* carry = a.buf.carry + env * a.carry_len;
+
+    const bool dyn = (ENV == PDECG_ENV_REACTION_DIFFUSION) && cfg.control_type == PDECG_CONTROL_NEUMANN;   // parabolic.py:148-150
+    S g = actuate<S>(a, env, S(0));                                   // constant over the step unless `dyn`
+    double bsum_dyn = 0.0;
+
+    // reward bookkeeping that needs mid-step rows (block-uniform; same definitions as the warp kernel)
+    const bool tuned = cfg.reward_kind == PDECG_REWARD_TUNED1D;
+    const bool ring_every = tuned && a.tuned_general;
+    const int snap_at = (tuned && !ring_every && cfg.substeps > kLookback) ? nsub - kLookback : -1;
+    const bool want_diff = !tuned && cfg.horizon == PDECG_HORIZON_DIFFERENTIAL && nsub > 0;
+    const bool want_hor = !tuned && cfg.horizon == PDECG_HORIZON_T;
+    const int hor_m = t_end > cfg.t_horizon_length ? cfg.t_horizon_length : t_end;   // norm_reward.py:65-72
+    const int hor_from = nsub - hor_m + 1;
+    double lb_norm = 0.0, diff_norm = 0.0, hor_acc = 0.0;
+
+    if (snap_at == 0) lb_norm = sqrt(cta_sumsq<S>(cur, npts, red));
+    for (int done = 0; done < nsub;) {
+        if (dyn) {
+            g = actuate<S>(a, env, cur[jb - 1]);
+            bsum_dyn += fabs(static_cast<double>(g));
+        }
+        if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) {
+            for (int j = tid; j < npts; j += nth) {
+                S n;
+                if (j == 0) n = S(0);                                 // parabolic.py:146
+                else if (j == jb) n = g;
+                else n = rd_point<M, false>(cur[j - 1], cur[j], cur[j + 1], Fs, coef[j]);
+                nxt[j] = n;
+            }
+        } else {
+            const S p0 = cur[0];
+            for (int j = tid; j < npts; j += nth) {
+                S n;
+                if (j == jb) {
+                    n = g;                                            // hyperbolic.py:143-145
+                } else {
+                    const S p = cur[j];
+                    S dq;
+                    if constexpr (M::kFast) dq = (cur[j + 1] - p) * by_dx.y;
+                    else dq = by_dx(Strict<S>::sub(cur[j + 1], p));
+                    n = tr_point<M>(p, dq, p0, dtc, coef[j]);
+                }
+                nxt[j] = n;
+            }
+        }
+        __syncthreads();
+        S* t = cur; cur = nxt; nxt = t;
+        ++done;
+        // ---- events at the current row (after `done` substeps) ----
+        if (done == snap_at) lb_norm = sqrt(cta_sumsq<S>(cur, npts, red));
+        if (ring_every) {                          // general look-back: norm of every row, ring indexed by t mod 101
+            const double nrm = static_cast<double>(static_cast<S>(sqrt(cta_sumsq<S>(cur, npts, red))));
+            if (tid == 0) carry[1 + (t0 + done) % (kLookback + 1)] = nrm;
+        }
+        if (want_hor && done >= hor_from)
+            hor_acc += static_cast<double>(static_cast<S>(cta_norm<S>(cur, nullptr, npts, cfg.norm_ord, red)));
+    }
+    if (want_diff) diff_norm = cta_norm<S>(cur, nxt, npts, cfg.norm_ord, red);   // `nxt` still holds row t-1
+
+    // ---- write back state ------------------------------------------------------------------------
+    S* crow = a.buf.obs_copy ? static_cast<S*>(a.buf.obs_copy) + env * npts : nullptr;
+    for (int j = tid; j < npts; j += nth) {
+        const S v = cur[j];
+        if (nsub > 0) urow[j] = v;
+        if (crow) crow[j] = v;
+    }
+    const double sumsq = cta_sumsq<S>(cur, npts, red);
+    const S norm2 = static_cast<S>(sqrt(sumsq));               // np.linalg.norm(u[t]) in the state dtype
+    const bool terminated = t_end >= cfg.nt - 1;                // hyperbolic.py:171-180
+    const bool truncated = cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value));
+    double other_norm = 0.0;                                    // NormReward temporal with p != 2
+    if (!tuned && !terminated && !truncated && (cfg.horizon == PDECG_HORIZON_TEMPORAL || nsub == 0) && cfg.norm_ord != kNormL2)
+        other_norm = cta_norm<S>(cur, nullptr, npts, cfg.norm_ord, red);
+
+    if (tid == 0) {
+        double bsum = carry[0];
+        if (dyn) bsum += bsum_dyn;
+        else bsum += static_cast<double>(nsub) * fabs(static_cast<double>(g));
+        double reward;
+        if (tuned) {
+            if (ring_every) {
+                lb_norm = (t_end - kLookback >= 0) ? carry[1 + (t_end - kLookback) % (kLookback + 1)] : 0.0;
+            } else if (cfg.substeps <= kLookback && cfg.substeps >= 1) {
+                const int slot = 1 + ((t_end / cfg.substeps) % a.ring_len);
+                lb_norm = carry[slot];
+                if (nsub > 0) carry[slot] = static_cast<double>(norm2);
+            }
+            if (terminated && norm2 < S(20)) {
+                // tuned_reward_1d.py:36-37, evaluated in the state dtype like numpy (python floats are weak)
+                S acc = static_cast<S>(bsum);
+                S r = Strict<S>::sub(Strict<S>::sub(static_cast<S>(cfg.terminate_reward), Strict<S>::div(acc, S(1000))), norm2);
+                reward = static_cast<double>(r);
+            } else if (truncated) {
+                reward = cfg.truncate_penalty * static_cast<double>(cfg.reward_nt - t_end);
+            } else {
+                reward = static_cast<double>(Strict<S>::sub(static_cast<S>(lb_norm), norm2));
+            }
+        } else {
+            const S coeff = static_cast<S>(cfg.norm_coeff);
+            if (terminated) {
+                reward = cfg.terminate_reward;
+            } else if (truncated) {
+                reward = cfg.truncate_penalty * static_cast<double>(cfg.reward_nt - t_end);
+            } else if (cfg.horizon == PDECG_HORIZON_TEMPORAL || nsub == 0) {
+                S nn = (cfg.norm_ord == kNormL2) ? norm2 : static_cast<S>(other_norm);
+                reward = static_cast<double>(Strict<S>::div(-nn, coeff));
+            } else if (cfg.horizon == PDECG_HORIZON_DIFFERENTIAL) {
+                reward = static_cast<double>(Strict<S>::div(static_cast<S>(diff_norm), coeff));
+            } else {
+                S mean = Strict<S>::div(static_cast<S>(hor_acc), static_cast<S>(hor_m));
+                reward = static_cast<double>(Strict<S>::div(-mean, coeff));
+            }
+        }
+        // ---- sensing (hyperbolic.py:69-120, parabolic.py:69-118) ----
+        if (cfg.sensing_loc != PDECG_SENSE_FULL) {
+            S o;
+            if (cfg.sensing_loc == PDECG_SENSE_COLLOCATED) {
+                if (cfg.control_type == PDECG_CONTROL_NEUMANN) o = cur[npts - 1];
+                else o = Strict<S>::div(Strict<S>::sub(cur[npts - 1], cur[npts - 2]), dxs);
+            } else {
+                if (cfg.sensing_type == PDECG_SENSETYPE_NEUMANN) o = Strict<S>::div(Strict<S>::sub(cur[1], cur[0]), dxs);
+                else o = cur[0];
+            }
+            static_cast<S*>(a.buf.obs)[env] = o;
+        }
+        carry[0] = bsum;
+        a.buf.time_index[env] = t_end;
+        a.buf.reward[env] = reward;
+        a.buf.terminated[env] = terminated ? 1 : 0;
+        a.buf.truncated[env] = truncated ? 1 : 0;
+    }
+    if (a.ar.enabled && (terminated || truncated)) {
+        __syncthreads();                               // the step's own row / carry stores come first
+        if (tid < 32) autoreset_env<S, 32>(a, env, tid, kFull);   // warp 0 restarts the env exactly like the reset kernel
+    }
+}
+
+template <int ENV, class M>
+inline int launch_cta(const Bc1dArgs& a, cudaStream_t st) {
+    using S = typename M::S;
+    using C = typename M::C;
+    if (a.npts > kCtaMaxPoints)
+        return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the shared-memory-resident limit of %d points per env", a.npts, kCtaMaxPoints);
+    const size_t smem = static_cast<size_t>(a.npts) * (sizeof(C) + 2 * sizeof(S));
+    auto kern = bc1d_step_cta_kernel<ENV, M>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int threads = a.npts <= 1024 ? 256 : (a.npts <= 4096 ? 512 : 1024);
+    kern<<<static_cast<unsigned>(a.buf.n_envs), threads, smem, st>>>(a);
+    count_launch();
+    return check_launch("bc1d_step_cta_kernel");
+}
+
+}  // namespace pdecg

@@ -325,7 +325,7 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
 
 // MULTI = false: PDECG_BT_RAW_STEP only (one day per launch); MULTI = true: the TherapyWrapper modes.
 template <int K, bool MULTI>
-__global__ void __launch_bounds__(kThreads, MULTI ? PDECG_BT_MINBLOCKS_MULTI : PDECG_BT_MINBLOCKS) bt_run_kernel(const __grid_constant__ BtArgs a) {
+__global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLOCKS_MULTI : PDECG_BT_MINBLOCKS)) bt_run_kernel(const __grid_constant__ BtArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -516,7 +516,7 @@ static int bt_validate(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf) {
     if (!cfg || !buf) return fail(PDECG_ERR_INVALID, "null cfg/buffers");
     if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
     if (cfg->nx < 4 || cfg->nt < 2) return fail(PDECG_ERR_INVALID, "need nx >= 4 and nt >= 2");
-    if (cfg->nx > 256) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", cfg->nx);
+    if (cfg->nx > 512) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 512 points per env", cfg->nx);
     if (!(cfg->dt > 0) || !(cfg->dx > 0) || !(cfg->k > 0)) return fail(PDECG_ERR_INVALID, "dt, dx, k must be positive");
     if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (buf->n_envs > 0 && (!buf->u || !buf->ienv || !buf->fenv || !buf->reward || !buf->terminated || !buf->truncated || !buf->x_scale))
@@ -551,7 +551,8 @@ static int bt_launch(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32
     BtArgs a{*cfg, *buf, mode, ar_init, ar_stride};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int K = (cfg->nx + 31) / 32;
+    int K = (cfg->nx + 31) / 32;
+    if (K > 8) K = (K + 1) / 2 * 2;                    // 257..512 points: even K in {10, 12, 14, 16}
     switch (K) {
 #define PDECG_CASE(KK)                                                                   \
     case KK:                                                                             \
@@ -559,6 +560,7 @@ static int bt_launch(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32
         else bt_run_kernel<KK, true><<<grid, kThreads, 0, st>>>(a);                      \
         break;
         PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
+        PDECG_CASE(10) PDECG_CASE(12) PDECG_CASE(14) PDECG_CASE(16)
 #undef PDECG_CASE
         default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
     }

@@ -61,6 +61,7 @@ __device__ __forceinline__ void ns_reset_env(const NsArgs& a, const double* __re
 
 using D = Strict<double>;
 constexpr int kNsThreads = 256;
+constexpr int kNsMaxPoints = 4096;   // 7 fields x 4096 x 8 B = 224 KB of the 227 KB an sm_100a CTA may use
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -106,13 +107,14 @@ __device__ void apply_boundary(const pdecg_ns_cfg& cfg, double* fu, double* fv, 
 
 // N Jacobi sweeps (:104-114) on smem ping-pong buffers pa (current) / pb; returns the buffer holding the result.
 // `b` = (dx*dy) * rhs, per point (only interior entries are read).
-__device__ double* jacobi(const pdecg_ns_cfg& cfg, double* pa, double* pb, const double* b, int tid, int nthreads) {
+template <int PT>
+__device__ __forceinline__ double* jacobi(const pdecg_ns_cfg& cfg, double* pa, double* pb, const double* b, int tid, int nthreads) {
     const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny;
-    // each thread owns up to 2 points (npt <= 2*nthreads is enforced on the host)
-    int idx[2], ci[2];
-    double bb[2];
+    // each thread owns up to PT points (npt <= PT*nthreads is enforced on the host)
+    int idx[PT], ci[PT];
+    double bb[PT];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < PT; ++s) {
         const int q = tid + s * nthreads;
         idx[s] = q < npt ? q : -1;
         const int i = clampi((q < npt ? q : 0) / nx, 1, ny - 2), j = clampi((q < npt ? q : 0) % nx, 1, nx - 2);
@@ -121,7 +123,7 @@ __device__ double* jacobi(const pdecg_ns_cfg& cfg, double* pa, double* pb, const
     }
     for (int it = 0; it < cfg.n_pressure_iters; ++it) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < PT; ++s) {
             if (idx[s] >= 0) {
                 const int c = ci[s];
                 double acc = D::add(pa[c - 1], pa[c - nx]);     // ((left + up) + right) + down
@@ -136,7 +138,10 @@ __device__ double* jacobi(const pdecg_ns_cfg& cfg, double* pa, double* pb, const
     return pa;
 }
 
-__global__ void __launch_bounds__(kNsThreads) ns_step_kernel(const NsArgs a) {
+// THREADS x PT >= nx*ny: (256, 2) up to 512 points, (512, 4) up to 2,048, (1024, 4) up to 4,096 (64 x 64; the seven
+// float64 fields of one env then fill the SM's 227 KB of shared memory)
+template <int THREADS, int PT>
+__global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
     extern __shared__ double smem[];
     const pdecg_ns_cfg& cfg = a.cfg;
     const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny;
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kNsThreads) ns_step_kernel(const NsArgs a) {
     double* sp0 = svs + npt;           // pressure ping
     double* sp1 = sp0 + npt;           // pressure pong
     double* sb = sp1 + npt;            // (dx*dy) * rhs
-    __shared__ double red[kNsThreads / 32];
+    __shared__ double red[THREADS / 32];
 
     const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
     const double dxdy = D::mul(cfg.dx, cfg.dy);
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kNsThreads) ns_step_kernel(const NsArgs a) {
                 sb[q] = D::mul(dxdy, D::mul(rho_dt, D::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
         }
         __syncthreads();
-        double* pf = jacobi(cfg, sp0, sp1, sb, tid, nth);
+        double* pf = jacobi<PT>(cfg, sp0, sp1, sb, tid, nth);
         for (int q = tid; q < npt; q += nth) gp[q] = pf[q];
         return;
     }
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kNsThreads) ns_step_kernel(const NsArgs a) {
         sb[q] = bv;
     }
     __syncthreads();
-    double* pf = jacobi(cfg, sp0, sp1, sb, tid, nth);
+    double* pf = jacobi<PT>(cfg, sp0, sp1, sb, tid, nth);
 
     // ---- corrector (:143-146) ----
     const double dt_rho = D::div(cfg.dt, cfg.density);
@@ -510,7 +515,7 @@ static int ns_validate_cfg(const pdecg_ns_cfg* cfg) {
     if (!cfg) return fail(PDECG_ERR_INVALID, "null cfg");
     if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
     if (cfg->nx < 3 || cfg->ny < 3) return fail(PDECG_ERR_INVALID, "need nx, ny >= 3");
-    if (cfg->nx * cfg->ny > 2 * kNsThreads) return fail(PDECG_ERR_UNSUPPORTED, "grid %dx%d exceeds the shared-memory-resident limit of %d points per env", cfg->nx, cfg->ny, 2 * kNsThreads);
+    if (cfg->nx * cfg->ny > kNsMaxPoints) return fail(PDECG_ERR_UNSUPPORTED, "grid %dx%d exceeds the shared-memory-resident limit of %d points per env", cfg->nx, cfg->ny, kNsMaxPoints);
     if (cfg->n_pressure_iters < 0) return fail(PDECG_ERR_INVALID, "maximum_pressure_iteration < 0");
     if (!(cfg->dt > 0) || !(cfg->dx > 0) || !(cfg->dy > 0)) return fail(PDECG_ERR_INVALID, "dt, dx, dy must be positive");
     for (int s = 0; s < 4; ++s)
@@ -521,10 +526,22 @@ static int ns_validate_cfg(const pdecg_ns_cfg* cfg) {
 
 static size_t ns_smem_bytes(const pdecg_ns_cfg* cfg) { return static_cast<size_t>(7) * cfg->nx * cfg->ny * sizeof(double); }
 
-static int ns_prepare_launch(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(ns_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+// generic (CTA-per-env) kernel: pick the instantiation for this grid, opt in to its shared memory, launch
+template <int THREADS, int PT>
+static int ns_launch_generic_t(const NsArgs& a, int64_t n_envs, size_t smem, cudaStream_t st) {
+    auto kern = ns_step_kernel<THREADS, PT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return PDECG_OK;
+    kern<<<static_cast<unsigned>(n_envs), THREADS, smem, st>>>(a);
+    count_launch();
+    return check_launch("ns_step_kernel");
+}
+static int ns_launch_generic(const NsArgs& a, int64_t n_envs, cudaStream_t st) {
+    const int npt = a.cfg.nx * a.cfg.ny;
+    const size_t smem = ns_smem_bytes(&a.cfg);
+    if (npt <= 2 * 256) return ns_launch_generic_t<256, 2>(a, n_envs, smem, st);
+    if (npt <= 4 * 512) return ns_launch_generic_t<512, 4>(a, n_envs, smem, st);
+    return ns_launch_generic_t<1024, 4>(a, n_envs, smem, st);
 }
 
 }  // namespace pdecg
@@ -566,11 +583,7 @@ static int ns_launch_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, 
         count_launch();
         return check_launch("ns_step_warp_kernel");
     }
-    const size_t smem = ns_smem_bytes(cfg);
-    if ((rc = ns_prepare_launch(smem)) != PDECG_OK) return rc;
-    ns_step_kernel<<<static_cast<unsigned>(buf->n_envs), kNsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
-    count_launch();
-    return check_launch("ns_step_kernel");
+    return ns_launch_generic(a, buf->n_envs, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, pdecg_stream_t stream) {
@@ -590,13 +603,9 @@ extern "C" int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, 
     if (n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (n_envs == 0) return PDECG_OK;
     if (!u || !v || !p) return fail(PDECG_ERR_INVALID, "null device buffer");
-    const size_t smem = ns_smem_bytes(cfg);
-    if ((rc = ns_prepare_launch(smem)) != PDECG_OK) return rc;
     NsArgs a{};
     a.cfg = *cfg;
     a.buf.n_envs = n_envs;
     a.su = u; a.sv = v; a.sp = p; a.solve_only = 1;
-    ns_step_kernel<<<static_cast<unsigned>(n_envs), kNsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
-    count_launch();
-    return check_launch("ns_step_kernel(solve_pressure)");
+    return ns_launch_generic(a, n_envs, static_cast<cudaStream_t>(stream));
 }

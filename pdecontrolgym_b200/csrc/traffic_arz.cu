@@ -80,7 +80,7 @@ __device__ __forceinline__ void arz_store(const double (&r)[K], double* __restri
 __device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane);   // defined after the reset kernel
 
 template <int K>
-__global__ void __launch_bounds__(kThreads, PDECG_ARZ_MINBLOCKS) arz_step_kernel(const __grid_constant__ ArzArgs a) {
+__global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) arz_step_kernel(const __grid_constant__ ArzArgs a) {
     __shared__ double sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -284,7 +284,7 @@ static int arz_validate(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf) 
     if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
     if (cfg->simulation_type < PDECG_ARZ_INLET || cfg->simulation_type > PDECG_ARZ_OUTLET_TRAIN) return fail(PDECG_ERR_INVALID, "Invalid simulation type");
     if (cfg->M < 4) return fail(PDECG_ERR_INVALID, "need at least 4 grid points");
-    if (cfg->M > 256) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 256 points per env", cfg->M);
+    if (cfg->M > 512) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 512 points per env", cfg->M);
     if (cfg->control_freq < 1) return fail(PDECG_ERR_INVALID, "control_freq must be a positive integer (got %d)", cfg->control_freq);
     if (cfg->action_dim != ((cfg->simulation_type == PDECG_ARZ_BOTH) ? 2 : 1)) return fail(PDECG_ERR_INVALID, "action_dim must be 2 for 'both', else 1");
     if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
@@ -318,10 +318,12 @@ static int arz_launch_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* bu
     ArzArgs a{*cfg, *buf, ar_profile};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int K = (cfg->M + 31) / 32;
+    int K = (cfg->M + 31) / 32;
+    if (K > 8) K = (K + 1) / 2 * 2;                    // 257..512 points: even K in {10, 12, 14, 16}
     switch (K) {
 #define PDECG_CASE(KK) case KK: arz_step_kernel<KK><<<grid, kThreads, 0, st>>>(a); break;
         PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
+        PDECG_CASE(10) PDECG_CASE(12) PDECG_CASE(14) PDECG_CASE(16)
 #undef PDECG_CASE
         default: return fail(PDECG_ERR_UNSUPPORTED, "unsupported points-per-lane %d", K);
     }

@@ -80,9 +80,11 @@ def test_invalid_configs_are_rejected_without_a_gpu(lib):
     assert b"TunedReward1D" in L.pdecg_last_error()
     cfg.nt = 10001
     cfg.substeps = 1000
-    cfg.nx = 600
+    cfg.nx = 600                 # beyond the warp kernels' 512 points: served by the CTA-per-env kernel
+    assert L.pdecg_bc1d_step(ctypes.byref(cfg), ctypes.byref(buf), None) == lib.OK               # n_envs == 0: nothing to launch
+    cfg.nx = 8193
     assert L.pdecg_bc1d_step(ctypes.byref(cfg), ctypes.byref(buf), None) == lib.ERR_UNSUPPORTED
-    assert b"register-resident" in L.pdecg_last_error()
+    assert b"shared-memory-resident" in L.pdecg_last_error()
     acfg = lib.ArzCfg()
     acfg.abi_version, acfg.simulation_type, acfg.M, acfg.control_freq, acfg.action_dim = lib.ABI_VERSION, 7, 51, 1, 1
     assert L.pdecg_arz_step(ctypes.byref(acfg), ctypes.byref(lib.ArzBuffers()), None) == lib.ERR_INVALID

@@ -144,11 +144,11 @@ def test_empty_batch_and_errors(cuda_device):
         pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=1, device=cuda_device, sensing_loc="opposite",
                  sensing_type="Dirchilet", reward_class=pcg.TunedReward1D(nt - 1), **kw)
     kw2 = dict(kw)
-    kw2["dx"] = 1.0 / 600
+    kw2["dx"] = 1.0 / 9000
     big = pcg.make("PDEControlGym-TransportPDE1D", num_envs=1, device=cuda_device,
                    reward_class=pcg.NormReward(nt - 1), **kw2)
-    with pytest.raises(PdecgError, match="register-resident"):
-        big.reset(options={"init_condition": np.zeros(600), "beta": np.zeros(600)})
+    with pytest.raises(PdecgError, match="shared-memory-resident"):
+        big.reset(options={"init_condition": np.zeros(9000), "beta": np.zeros(9000)})
 
 
 @pytest.mark.parametrize("autoreset", [False, True])
@@ -263,3 +263,122 @@ def test_staggered_time_indices_within_a_warp(cuda_device, env, precision, rk):
         r_ref = np.where(mask, r_new, r_old)
         scale = 2 * np.sqrt((o_ref.astype(np.float64) ** 2).sum(axis=1)) + np.abs(r_ref)
         assert_rewards_close(r_gpu.cpu().numpy()[live], r_ref[live], scale[live], tol, f"step {k}")
+
+
+# ---- grids beyond 512 points per env: the CTA-per-env shared-memory kernel (bc1d_large.cuh) ----------------------
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("nx", [512, 513, 600, 1024, 1025, 2500, 4097, 8191])
+def test_large_grid_sizes(cuda_device, env, nx):
+    """256-, 512- and 1024-thread launches, sizes that are not multiples of the block size, every precision mode."""
+    steps = 3 if nx <= 1025 else 2
+    for precision, bd in (("ref", np.float32), ("ref", np.float64), ("fp64", np.float64)):
+        run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), False, bd, np.float32, "tuned",
+                 nx=nx, B=3, steps=steps)
+        run_pair(cuda_device, env, precision, "Neumann", ("collocated", None), False, bd, np.float64, ("temporal", 2),
+                 nx=nx, B=3, steps=steps)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+def test_large_grid_all_variants(cuda_device, env):
+    """Control / sensing / normalisation / action-dtype / reward variants and truncation on a 700-point grid."""
+    for control_type, sensing, normalize, act_dtype in itertools.product(
+            ("Dirchilet", "Neumann"), SENSINGS, (False, True), (np.float32, np.float64)):
+        if env == "rd" and sensing == ("opposite", "Dirchilet"):
+            continue
+        steps = 3 if (env == "rd" and control_type == "Neumann" and normalize) else 4
+        run_pair(cuda_device, env, "ref", control_type, sensing, normalize, np.float32, act_dtype, "tuned", nx=700, B=2, steps=steps)
+        run_pair(cuda_device, env, "fp64", control_type, sensing, normalize, np.float64, act_dtype, ("temporal", 2), nx=700, B=2, steps=steps)
+    for rk in [("temporal", 1), ("temporal", np.inf), ("differential", 2), ("differential", 1), ("differential", np.inf), ("t-horizon", 2)]:
+        for precision, bd in (("ref", np.float32), ("fp64", np.float64)):
+            run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), True, bd, np.float32, rk, nx=700, B=2, steps=4)
+    run_pair(cuda_device, env, "ref", "Dirchilet", ("full", None), False, np.float32, np.float32, "tuned", nx=700, B=3, steps=12, limit=True)
+    run_pair(cuda_device, env, "fp64", "Dirchilet", ("full", None), False, np.float64, np.float32, ("temporal", 2), nx=700, B=3, steps=12, limit=True)
+    run_pair(cuda_device, env, "fp32", "Dirchilet", ("full", None), True, np.float32, np.float32, "tuned", nx=700, B=2, steps=3)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("sub,steps,extra", [(30, 5, 0), (150, 2, 77)])
+def test_large_grid_tuned_reward_general_ring(cuda_device, env, sub, steps, extra):
+    """TunedReward1D look-back through the 101-entry per-substep ring on a 640-point grid."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    nx = 640
+    dx = 1.0 / nx
+    dt = 0.4 * dx * dx if env == "rd" else dx / 100
+    npts = nx + 1 if env == "rd" else nx
+    n_sub_total = sub * steps + extra
+    T = dt * n_sub_total
+    nt = int(round(T / dt) + 1)
+    assert nt - 1 == n_sub_total and nt > 100
+    kw = dict(T=T, dt=dt, X=1, dx=dx, control_sample_rate=dt * sub, normalize=True, max_control_value=20)
+    rng = np.random.default_rng(sub)
+    B = 3
+    ics = make_ics(rng, B, npts)
+    beta = np.cos(np.linspace(0, 3, npts)).astype(np.float32)
+    Orc = O.ReactionDiffusionOracle if env == "rd" else O.TransportOracle
+    oenv = Orc(B, reward=O.TunedReward1DSpec(nt - 1, -1e3, 3e2), **kw)
+    eid = "PDEControlGym-ReactionDiffusionPDE1D" if env == "rd" else "PDEControlGym-TransportPDE1D"
+    genv = pcg.make(eid, num_envs=B, device=cuda_device, reward_class=pcg.TunedReward1D(nt - 1, -1e3, 3e2), **kw)
+    oenv.reset(ics, beta)
+    genv.reset(options={"init_condition": ics, "beta": beta})
+    for k in range(steps + (1 if extra else 0)):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        o_r, r_r, te_r, tr_r = oenv.step(a)
+        o_g, r_g, te_g, tr_g, _ = genv.step(torch.from_numpy(a))
+        assert np.array_equal(o_g.cpu().numpy(), o_r) and np.array_equal(te_g.cpu().numpy(), te_r)
+        scale = 2 * np.sqrt((oenv.u.astype(np.float64) ** 2).sum(axis=1)) + np.abs(r_r)
+        assert_rewards_close(r_g.cpu().numpy(), r_r, scale, TOL_F32_REDUCTION, f"call {k}")
+    assert te_r.all()
+
+
+@pytest.mark.parametrize("env_id,precision", [("PDEControlGym-ReactionDiffusionPDE1D", "fp64"), ("PDEControlGym-TransportPDE1D", "ref")])
+@pytest.mark.parametrize("random_ic", [False, True])
+def test_large_grid_fused_autoreset_and_step_host(cuda_device, env_id, precision, random_ic):
+    """On a 900-point grid: fused same-step auto-reset == step + masked reset, and step_host == step."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    rd = "Reaction" in env_id
+    N, steps, nx = 5, 3, 900
+    dx = 1.0 / nx
+    if rd:
+        dt, sub, npts = 0.4 * dx * dx, 100, nx + 1
+    else:
+        dt, sub, npts = dx / 100, 300, nx
+    kw = dict(T=steps * sub * dt, dt=dt, X=1, dx=dx, control_sample_rate=sub * dt, normalize=True, precision=precision,
+              limit_pde_state_size=True, max_state_value=1e10)
+    kw["reward_class"] = pcg.TunedReward1D(int(round(kw["T"] / dt)), -1e3, 3e2)
+    rng = np.random.default_rng(9)
+    beta = rng.uniform(-3, 3, (N, npts)).astype(np.float64 if precision == "fp64" else np.float32)
+    ic = pcg.UniformScaleIC(1.0, 10.0) if random_ic else rng.uniform(1, 2, (N, npts))
+    fused = pcg.make(env_id, num_envs=N, device=cuda_device, autoreset=True, **kw)
+    manual = pcg.make(env_id, num_envs=N, device=cuda_device, autoreset=False, **kw)
+    hosted = pcg.make(env_id, num_envs=N, device=cuda_device, autoreset=True, **kw)
+    for e in (fused, manual, hosted):
+        e.reset(seed=5, options={"init_condition": ic, "beta": beta})
+    stag = np.array([True, False, False, True, True])
+    a0 = torch.zeros(N, device=cuda_device)
+    for e in (fused, manual, hosted):
+        e.step(a0)
+        e.reset(options={"mask": stag})
+    sdt = torch.float64 if precision == "fp64" else torch.float32
+    obs_h = torch.empty(N, npts, dtype=sdt).pin_memory()
+    rew_h = torch.empty(N, dtype=torch.float64).pin_memory()
+    te_h = torch.empty(N, dtype=torch.uint8).pin_memory()
+    tr_h = torch.empty(N, dtype=torch.uint8).pin_memory()
+    n_done = 0
+    for k in range(2 * steps + 2):
+        a = torch.from_numpy(rng.uniform(-1, 1, N).astype(np.float32))
+        o1, r1, te1, tr1, _ = fused.step(a)
+        o2, r2, te2, tr2, _ = manual.step(a)
+        hosted.step_host(a.pin_memory(), obs_h, rew_h, te_h, tr_h)
+        done = te2 | tr2
+        if done.any():
+            o2, _ = manual.reset(options={"mask": done})
+            n_done += int(done.sum())
+        assert torch.equal(te1, te2) and torch.equal(tr1, tr2) and torch.equal(r1, r2), f"step {k}: outputs"
+        assert torch.equal(o1, o2), f"step {k}: observation"
+        assert np.array_equal(o1.cpu().numpy(), obs_h.numpy()) and np.array_equal(r1.cpu().numpy(), rew_h.numpy())
+        assert np.array_equal(te1.cpu().numpy(), te_h.numpy().astype(bool))
+        for name in ("u", "time_index", "_carry", "_episode"):
+            assert torch.equal(getattr(fused, name), getattr(manual, name)), f"step {k}: {name}"
+    assert n_done >= N

@@ -135,7 +135,7 @@ def test_wrapper_random_schedules_with_violations(cuda_device):
         assert int(w.soft_constraint_violations[b]) >= ow.soft_constraint_violations
 
 
-@pytest.mark.parametrize("X", [20, 63, 100, 255])
+@pytest.mark.parametrize("X", [20, 63, 100, 255, 256, 300, 400, 460, 511])
 def test_grid_sizes(cuda_device, X):
     """All points-per-lane instantiations; small domains (tumour reaches the wall)."""
     import torch

@@ -53,7 +53,7 @@ def test_vs_oracle(cuda_device, bc, iters):
         assert np.array_equal(te_g.cpu().numpy(), te_r) and not tr_g.any()
 
 
-@pytest.mark.parametrize("n", [5, 8, 11, 16, 22])
+@pytest.mark.parametrize("n", [5, 8, 11, 16, 22, 23, 41, 45, 46, 64])      # 23..45: 512 threads x 4 points, 46..64: 1024 x 4
 def test_grid_sizes(cuda_device, n):
     import torch
     env, orc, nt = make_pair(cuda_device, 2, BC_MIX, 25, n=n, T=0.02 * (20 / (n - 1)) ** 2)
@@ -111,3 +111,11 @@ def test_k5_target_trajectory(cuda_device):
             np.testing.assert_allclose(o[:, :, 0], want[t][0], rtol=0, atol=1e-12)
             np.testing.assert_allclose(o[:, :, 1], want[t][1], rtol=0, atol=1e-12)
     assert te.all()
+
+
+def test_grid_beyond_shared_memory_is_rejected_loudly(cuda_device):
+    import pdecontrolgym_b200 as pcg
+    env, orc, nt = make_pair(cuda_device, 1, BC_REF, 2, n=65, T=0.002)
+    z = np.zeros((65, 65))
+    with pytest.raises(pcg.PdecgError, match="exceeds the shared-memory-resident limit"):
+        env.reset(options={"init": (z, z, z)})

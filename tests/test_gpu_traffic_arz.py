@@ -49,7 +49,7 @@ def test_outlet_train(cuda_device):
     run(cuda_device, "outlet-train", 2, False, rs=np.array([0.115, 0.12, 0.125, 0.12]))
 
 
-@pytest.mark.parametrize("X,dx", [(100, 10), (310, 10), (640, 10), (500, 4), (500, 2)])
+@pytest.mark.parametrize("X,dx", [(100, 10), (310, 10), (640, 10), (500, 4), (500, 2), (500, 1.75), (500, 1.4), (500, 1.2), (500, 1)])   # ... 251, 287, 358, 418, 501 points
 def test_grid_sizes(cuda_device, X, dx):
     run(cuda_device, "both", 2, True, steps=60, B=3, X=X, dx=dx, dt=0.25 * dx / 10)
 
