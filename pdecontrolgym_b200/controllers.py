@@ -78,3 +78,65 @@ class TrafficARZBackstepping:
         if e.simulation_type == "both":
             return torch.stack((e.qs, q_out), dim=1)
         return q_out.unsqueeze(1)
+
+
+class NavierStokesAdjoint:
+    """Adjoint-based open-loop optimiser of examples/NavierStokes/NS2Doptimization.py:55-107 for a whole batch of
+    `NavierStokes2D` envs: a backward costate sweep over a recorded trajectory (each sweep step projects the costate
+    with the env's Jacobi pressure solve, `pdecg_ns_solve_pressure`, one launch for all envs), then the boundary
+    gradient gives the new action sequence.  Element-wise arithmetic follows the example's operation order."""
+
+    def __init__(self, env, viscosity: float = 0.1, gamma: float = 0.1):
+        self.env = env
+        self.nu, self.gamma = viscosity, gamma
+
+    @staticmethod
+    def _zero_walls(a1, a2):                             # apply_boundary of the example (:55-60)
+        for a in (a1, a2):
+            a[..., :, -1] = 0.
+            a[..., :, 0] = 0.
+            a[..., -1, :] = 0.
+            a[..., 0, :] = 0.
+        return a1, a2
+
+    def costates(self, U, V, u_target, v_target):
+        """U, V: [T, N, ny, nx] recorded velocities (after each of T steps); u_target, v_target: [NT, ny, nx] with
+        NT >= T (indexed from the end like the example).  Returns Lam1, Lam2: [T, N, ny, nx] in forward time order."""
+        from .envs_navier_stokes import central_difference as cd, laplace
+        e = self.env
+        dx, dy, dt = e.dx, e.dy, e.dt
+        dev = e.device
+        U, V = (torch.as_tensor(x, device=dev, dtype=torch.float64) for x in (U, V))
+        ut, vt = (torch.as_tensor(x, device=dev, dtype=torch.float64) for x in (u_target, v_target))
+        T = U.shape[0]
+        lam1, lam2 = torch.zeros_like(U[0]), torch.zeros_like(U[0])
+        pressure = torch.zeros_like(U[0])
+        L1, L2 = [lam1], [lam2]
+        for t in range(T - 1):                           # :85-101
+            u, v = U[-1 - t], V[-1 - t]
+            dl1dx, dl1dy = cd(lam1, "x", dx), cd(lam1, "y", dy)
+            dl2dx, dl2dy = cd(lam2, "x", dx), cd(lam2, "y", dy)
+            lap1, lap2 = laplace(lam1, dx, dy), laplace(lam2, dx, dy)
+            dlam1dt = -2 * dl1dx * u - dl1dy * v - dl2dx * v - self.nu * lap1 + (u - ut[-1 - t])
+            dlam2dt = -2 * dl2dy * v - dl1dy * u - dl2dx * u - self.nu * lap2 + (v - vt[-1 - t])
+            lam1 = lam1 - dt * dlam1dt
+            lam2 = lam2 - dt * dlam2dt
+            lam1, lam2 = self._zero_walls(lam1, lam2)
+            pressure = e.solve_pressure(lam1, lam2, pressure)
+            lam1 = lam1 - dt * cd(pressure, "x", dx)
+            lam2 = lam2 - dt * cd(pressure, "y", dy)
+            lam1, lam2 = self._zero_walls(lam1, lam2)
+            L1.append(lam1)
+            L2.append(lam2)
+        return torch.stack(L1[::-1]), torch.stack(L2[::-1])
+
+    def actions(self, U, V, u_target, v_target, action_ref=2.0):
+        """New action sequence [T, N] (:103-106): a_t = a_ref,t - nu/gamma * sum_x(d lam1 / dy at the row below the
+        controlled wall) * 5 * dx."""
+        from .envs_navier_stokes import central_difference as cd
+        L1, _ = self.costates(U, V, u_target, v_target)
+        T = L1.shape[0]
+        aref = torch.as_tensor(action_ref, device=L1.device, dtype=torch.float64)
+        aref = aref.expand(T) if aref.dim() == 0 else aref[:T]
+        g = cd(L1, "y", self.env.dy)[..., -2, :].sum(dim=-1)          # [T, N]
+        return aref[:, None] - self.nu / self.gamma * g * 5 * self.env.dx

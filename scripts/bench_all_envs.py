@@ -87,6 +87,13 @@ def bench_arz():
     ms = timed(lambda i: g.step(acts[i % 64]), 200)
     report("TrafficPDE1D outlet x16384 (control_freq=1), CUDA-graph replay", N, ms, 49, {"hbm_gbs": N * (2 * 51 * 8 * 2 + 102 * 8 + 40) / (ms * 1e-3) / 1e9})
     del env, g
+    # rollout-style stepping: private observation copies + same-step auto-reset, all inside the one step launch
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=dev, simulation_type="outlet", reward_class=pcg.TrafficARZReward(),
+                   T=240, dt=0.25, X=500, dx=10, copy_obs=True, autoreset=True)
+    env.reset()
+    ms = timed(lambda i: env.step(acts[i % 64]), 200)
+    report("TrafficPDE1D outlet x16384 (control_freq=1), autoreset + observation copy (1 launch/step)", N, ms, 49)
+    del env
     N = 262144
     env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=dev, simulation_type="outlet", reward_class=pcg.TrafficARZReward(),
                    T=240, dt=0.25, X=500, dx=10, copy_obs=False)
@@ -111,6 +118,11 @@ def bench_bt():
         ms = timed(lambda i: env.step(acts[i % 16]), 150)
         report(f"BrainTumor1D raw step x{N}", N, ms, 199, {"hbm_gbs": N * (2 * 201 * 8 + 64 + 32 + 12) / (ms * 1e-3) / 1e9})
         if N == 16384:
+            env.autoreset = True        # same-step auto-reset fused into the step launch
+            ms = timed(lambda i: env.step(acts[i % 16]), 150)
+            report(f"BrainTumor1D raw step x{N}, autoreset (1 launch/step)", N, ms, 199)
+            env.autoreset = False
+            env.reset(options={"init_condition": bt_ic(200, 201)})
             g = pcg.GraphedStep(env, acts[0])
             env.reset(options={"init_condition": bt_ic(200, 201)})
             ms = timed(lambda i: g.step(acts[i % 16]), 150)
@@ -144,10 +156,35 @@ def bench_ns():
         del env
 
 
+def bench_large():
+    # ---- grids beyond the reference's: CTA-per-env shared-memory kernels ----
+    for nx, N in ((1000, 16384), (4000, 4096)):
+        dx = 1.0 / nx
+        rkw = dict(T=1.0, dt=0.4 * dx * dx, X=1.0, dx=dx, control_sample_rate=100 * 0.4 * dx * dx, normalize=True, max_control_value=20)
+        rbeta = 50 * np.cos(8 * np.arccos(np.linspace(0, 1, nx + 1)))
+        bench_bc1d("PDEControlGym-ReactionDiffusionPDE1D", f"ReactionDiffusionPDE1D fp64, {nx + 1} points, 100 substeps x{N}", N, "fp64", rkw, nx + 1, rbeta,
+                   pcg.NormReward(int(round(1.0 / rkw["dt"]))), (nx - 1) * 100, steps=10, beta_dtype=np.float64)
+        tkw = dict(T=1.0, dt=dx / 100, X=1.0, dx=dx, control_sample_rate=10 * dx, normalize=True, max_control_value=20)
+        tbeta = 5 * np.cos(7.35 * np.arccos(np.linspace(0, 1, nx)))
+        bench_bc1d("PDEControlGym-TransportPDE1D", f"TransportPDE1D ref(f32), {nx} points, 1000 substeps x{N}", N, "ref", tkw, nx, tbeta,
+                   pcg.TunedReward1D(int(round(1.0 / tkw["dt"])), -1e3, 3e2), (nx - 1) * 1000, steps=4)
+    bc = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
+    for n, N in ((41, 1024), (64, 592)):
+        h = 1.0 / (n - 1)
+        env = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=dev, boundary_condition=bc, U_ref=np.zeros((200, n, n, 2)), action_ref=2.0 * np.ones(1000),
+                       reward_class=pcg.NSReward(0.1), action_dim=1, T=150 * 1e-3 * (h / 0.05) ** 2, dt=1e-3 * (h / 0.05) ** 2, X=1, dx=h, Y=1, dy=h, copy_obs=False)
+        c = torch.empty(3, N, 1, 1, dtype=torch.float64, device=dev).uniform_(-5, 5) * torch.ones(1, n, n, dtype=torch.float64, device=dev)
+        env.reset(options={"init": (c[0], c[1], c[2])})
+        acts = torch.empty(8, N, dtype=torch.float64, device=dev).uniform_(2, 4)
+        ms = timed(lambda i: env.step(acts[i % 8]), 5, warmup=2)
+        report(f"NavierStokes2D {n}x{n}, 2000 Jacobi sweeps x{N}", N, ms, (n - 2) ** 2 * 2000)
+        del env
+
+
 def main():
-    """All families, or only those named in PDECG_BENCH_ONLY (comma list of: transport, rd, arz, bt, ns)."""
+    """All families, or only those named in PDECG_BENCH_ONLY (comma list of: transport, rd, arz, bt, ns, large)."""
     only = [t for t in os.environ.get("PDECG_BENCH_ONLY", "").split(",") if t]
-    for name, fn in (("transport", bench_transport), ("rd", bench_rd), ("arz", bench_arz), ("bt", bench_bt), ("ns", bench_ns)):
+    for name, fn in (("transport", bench_transport), ("rd", bench_rd), ("arz", bench_arz), ("bt", bench_bt), ("ns", bench_ns), ("large", bench_large)):
         if not only or name in only:
             fn()
 

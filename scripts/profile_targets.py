@@ -1,4 +1,4 @@
-"""Tiny drivers for ncu captures of the non-headline kernels:  python scripts/profile_targets.py arz|bt|bt_wrap|ns|transport"""
+"""Tiny drivers for ncu captures of the non-headline kernels:  python scripts/profile_targets.py arz|bt|bt_wrap|ns|transport|rd_large|tr_large|ns_large"""
 import os
 import sys
 
@@ -50,5 +50,33 @@ elif which == "transport":
     env.reset(options={"init_condition": ic, "beta": (5 * np.cos(7.35 * np.arccos(np.linspace(0, 1, 100)))).astype(np.float32)})
     a = torch.empty(N, device=dev).uniform_(-1, 1)
     for _ in range(4):
+        env.step(a)
+elif which in ("rd_large", "tr_large"):
+    # grids beyond 512 points: the CTA-per-env shared-memory kernel (bc1d_large.cuh)
+    N, nx = 8192, 1000
+    dx = 1.0 / nx
+    if which == "rd_large":
+        kw = dict(T=1.0, dt=0.4 * dx * dx, X=1.0, dx=dx, control_sample_rate=100 * 0.4 * dx * dx)
+        npts, eid, prec = nx + 1, "PDEControlGym-ReactionDiffusionPDE1D", "fp64"
+    else:
+        kw = dict(T=1.0, dt=dx / 100, X=1.0, dx=dx, control_sample_rate=10 * dx)
+        npts, eid, prec = nx, "PDEControlGym-TransportPDE1D", "ref"
+    env = pcg.make(eid, num_envs=N, device=dev, precision=prec, reward_class=pcg.NormReward(int(round(kw["T"] / kw["dt"]))), normalize=True,
+                   max_control_value=20, copy_obs=False, **kw)
+    ic = torch.empty(N, 1, dtype=torch.float64, device=dev).uniform_(1, 10) * torch.ones(1, npts, dtype=torch.float64, device=dev)
+    beta = 5 * np.cos(7.35 * np.arccos(np.linspace(0, 1, npts)))
+    env.reset(options={"init_condition": ic, "beta": beta.astype(np.float64 if prec == "fp64" else np.float32)})
+    a = torch.empty(N, device=dev).uniform_(-1, 1)
+    for _ in range(4):
+        env.step(a)
+elif which == "ns_large":
+    N, n = 592, 41
+    bc = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
+    env = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=dev, boundary_condition=bc, U_ref=np.zeros((200, n, n, 2)),
+                   action_ref=2.0 * np.ones(1000), reward_class=pcg.NSReward(0.1), action_dim=1, T=0.05, dt=2.5e-4, X=1, dx=0.025, Y=1, dy=0.025, copy_obs=False)
+    z = torch.zeros(N, n, n, dtype=torch.float64, device=dev)
+    env.reset(options={"init": (z + 1.0, z - 2.0, z + 0.5)})
+    a = torch.empty(N, dtype=torch.float64, device=dev).uniform_(2, 4)
+    for _ in range(3):
         env.step(a)
 torch.cuda.synchronize()
