@@ -118,6 +118,7 @@ def bench_bt():
         ms = timed(lambda i: env.step(acts[i % 16]), 150)
         report(f"BrainTumor1D raw step x{N}", N, ms, 199, {"hbm_gbs": N * (2 * 201 * 8 + 64 + 32 + 12) / (ms * 1e-3) / 1e9})
         if N == 16384:
+            env.reset(options={"init_condition": bt_ic(200, 201)})
             env.autoreset = True        # same-step auto-reset fused into the step launch
             ms = timed(lambda i: env.step(acts[i % 16]), 150)
             report(f"BrainTumor1D raw step x{N}, autoreset (1 launch/step)", N, ms, 199)

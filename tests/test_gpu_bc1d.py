@@ -382,3 +382,16 @@ def test_large_grid_fused_autoreset_and_step_host(cuda_device, env_id, precision
         for name in ("u", "time_index", "_carry", "_episode"):
             assert torch.equal(getattr(fused, name), getattr(manual, name)), f"step {k}: {name}"
     assert n_done >= N
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+def test_large_grid_shared_memory_variant(cuda_device, env, monkeypatch):
+    """The shared-memory CTA kernel (kept for RD + Neumann control, where the actuation changes every substep) on the
+    configurations the register-tiled kernel normally serves."""
+    monkeypatch.setenv("PDECG_BC1D_LARGE_SMEM", "1")
+    for nx in (513, 1500, 4097):
+        for precision, bd in (("ref", np.float32), ("fp64", np.float64)):
+            run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), True, bd, np.float32, "tuned", nx=nx, B=2, steps=2)
+    for rk in [("temporal", 1), ("differential", 2), ("differential", np.inf), ("t-horizon", 2)]:
+        run_pair(cuda_device, env, "fp64", "Dirchilet", ("opposite", "Neumann"), True, np.float64, np.float64, rk, nx=700, B=2, steps=3)
+    run_pair(cuda_device, env, "ref", "Dirchilet", ("full", None), False, np.float32, np.float32, "tuned", nx=700, B=3, steps=12, limit=True)
