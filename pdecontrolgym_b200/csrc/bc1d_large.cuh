@@ -369,19 +369,34 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
         }
     };
 
-    if (snap_at == 0) lb_norm = sqrt(row_sumsq());
     double dacc = 0.0;
-    for (int done = 0; done < nsub;) {
-        if (want_diff && done == nsub - 1) substep(done & 1, std::true_type{}, dacc);
-        else substep(done & 1, std::false_type{}, dacc);
-        ++done;
+    int done = 0;
+    while (true) {
         // ---- events at the current row (after `done` substeps) ----
         if (done == snap_at) lb_norm = sqrt(row_sumsq());
-        if (ring_every) {                          // general look-back: norm of every row, ring indexed by t mod 101
+        if (ring_every && done >= 1) {             // general look-back: norm of every row, ring indexed by t mod 101
             const double nrm = static_cast<double>(static_cast<S>(sqrt(row_sumsq())));
             if (tid == 0) carry[1 + (t0 + done) % (kLookback + 1)] = nrm;
         }
-        if (want_hor && done >= hor_from) hor_acc += static_cast<double>(static_cast<S>(row_norm(cfg.norm_ord)));
+        if (want_hor && done >= hor_from && done >= 1) hor_acc += static_cast<double>(static_cast<S>(row_norm(cfg.norm_ord)));
+        if (done >= nsub) break;
+        if (want_diff && done == nsub - 1) {       // the last substep also accumulates ||u_t - u_{t-1}||
+            substep(done & 1, std::true_type{}, dacc);
+            ++done;
+            continue;
+        }
+        // ---- next stop ----
+        int next = nsub;
+        if (snap_at > done && snap_at < next) next = snap_at;
+        if (ring_every) next = done + 1;
+        if (want_diff && nsub - 1 < next) next = nsub - 1;
+        if (want_hor) {
+            const int h = hor_from > done + 1 ? hor_from : done + 1;
+            if (h < next) next = h;
+        }
+        // plain substeps up to the next stop (tight loop: nothing but the stencil and the halo exchange)
+        for (int s = done; s < next; ++s) substep(s & 1, std::false_type{}, dacc);
+        done = next;
     }
     if (want_diff) {
         if (cfg.norm_ord == kNormL2) diff_norm = sqrt(cta_sum(dacc, red));

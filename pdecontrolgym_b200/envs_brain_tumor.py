@@ -149,8 +149,9 @@ class BrainTumor1D(StateDictMixin):
     def _out_rest(self, outs):
         """(reward, terminated, truncated, info) from the fresh tensors a launch wrote."""
         reward, term_u8, trunc_u8, valid_u8 = outs
+        stage = self._ienv[:, I_STAGE]              # copy_obs=False: a live zero-copy view, like the observation
         return (reward, term_u8.view(torch.bool), trunc_u8.view(torch.bool),
-                {"stage": self._ienv[:, I_STAGE].clone(), "valid": valid_u8.view(torch.bool)})
+                {"stage": stage.clone() if self.copy_obs else stage, "valid": valid_u8.view(torch.bool)})
 
     # -- gym API -------------------------------------------------------------------------------
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
