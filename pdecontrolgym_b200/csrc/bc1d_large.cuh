@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = j0 + k;
-        u[k] = (j < npts) ? urow[j] : S(0);
+        // Transport padding slots (never stored, never read by valid points) hold a ramp instead of zeros so that the
+        // differences formed there are ordinary numbers and stay on the division fast path
+        u[k] = (j < npts) ? urow[j] : ((ENV == PDECG_ENV_TRANSPORT) ? static_cast<S>(j - npts + 1) : S(0));
         const C b = (j < npts) ? brow[j] : C(0);
         if constexpr (ENV == PDECG_ENV_REACTION_DIFFUSION) coef[k] = M::kFast ? dtc * b : Strict<C>::mul(dtc, b);   // parabolic.py:144
         else coef[k] = b;
@@ -349,14 +351,38 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
             }
         } else {
             const S p0 = edge[par][1].first;
+            // (p_{j+1} - p_j) / dx for the whole chunk from the OLD values: 3-instruction exact tail per point and ONE
+            // range test per chunk; operands outside the window (zero, denormal, inf, ...) redo the chunk exactly
+            S x[K], dq[K];
+            bool ok = true;
+            [[maybe_unused]] float xmin = 0x1p100f, xmax = 0.0f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const S pr = (k == K - 1) ? hr : u[k < K - 1 ? k + 1 : K - 1];
+                if constexpr (M::kFast) {
+                    dq[k] = (pr - u[k]) * by_dx.y;
+                } else {
+                    x[k] = Strict<S>::sub(pr, u[k]);
+                    dq[k] = by_dx.fast(x[k]);
+                    if constexpr (sizeof(S) == 4) {
+                        xmin = fminf(xmin, fabsf(x[k]));
+                        xmax = fmaxf(xmax, fabsf(x[k]));
+                    } else {
+                        ok = ok & by_dx.in_range(x[k]);
+                    }
+                }
+            }
+            if constexpr (!M::kFast) {
+                if constexpr (sizeof(S) == 4) ok = by_dx.in_range_minmax(xmin, xmax);
+                if (!ok) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) dq[k] = by_dx.exact(x[k]);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const S old = u[k];
-                const S pr = (k == K - 1) ? hr : u[k < K - 1 ? k + 1 : K - 1];
-                S dq;
-                if constexpr (M::kFast) dq = (pr - old) * by_dx.y;
-                else dq = by_dx(Strict<S>::sub(pr, old));
-                S n = tr_point<M>(old, dq, p0, dtc, coef[k]);
+                S n = tr_point<M>(old, dq[k], p0, dtc, coef[k]);
                 if (owner_warp) n = (j0 + k == jb) ? g : n;            // hyperbolic.py:143-145
                 if constexpr (DIFF) {
                     if (j0 + k < npts) {
