@@ -47,5 +47,42 @@ for n in (21, 12):
     for _ in range(3):
         ns.step(rng.uniform(2, 4, 5))
     ns.solve_pressure(rng.uniform(-1, 1, (5, n, n)), rng.uniform(-1, 1, (5, n, n)), np.zeros((n, n)))
+# grids beyond 512 points: register-tiled and shared-memory CTA kernels, every reward event path, fused auto-reset
+for eid, nx, sub in (("PDEControlGym-TransportPDE1D", 700, 30), ("PDEControlGym-ReactionDiffusionPDE1D", 2500, 30)):
+    dx = 1.0 / nx
+    dt = dx / 100 if "Transport" in eid else 0.4 * dx * dx
+    npts = nx if "Transport" in eid else nx + 1
+    for prec, rew, ct in (("ref", pcg.TunedReward1D(4 * sub), "Dirchilet"), ("fp64", pcg.NormReward(4 * sub, "1", "differential"), "Dirchilet"),
+                          ("fp64", pcg.NormReward(4 * sub, "inf", "t-horizon"), "Neumann"), ("fp32", pcg.NormReward(4 * sub), "Dirchilet")):
+        env = pcg.make(eid, num_envs=3, device=dev, precision=prec, reward_class=rew, control_type=ct, autoreset=True,
+                       T=4 * sub * dt, dt=dt, X=1, dx=dx, control_sample_rate=sub * dt)
+        env.reset(options={"init_condition": rng.uniform(1, 2, (3, npts)), "beta": rng.uniform(-1, 1, npts)})
+        for _ in range(5):
+            env.step(rng.uniform(-1, 1, 3).astype(np.float32))
+os.environ["PDECG_BC1D_LARGE_SMEM"] = "1"
+env = pcg.make("PDEControlGym-TransportPDE1D", num_envs=3, device=dev, reward_class=pcg.TunedReward1D(600), autoreset=True,
+               T=600 * 1e-5, dt=1e-5, X=1, dx=1e-3, control_sample_rate=150 * 1e-5)
+env.reset(options={"init_condition": rng.uniform(1, 2, (3, 1000)), "beta": rng.uniform(-1, 1, 1000)})
+for _ in range(5):
+    env.step(rng.uniform(-1, 1, 3).astype(np.float32))
+del os.environ["PDECG_BC1D_LARGE_SMEM"]
+# fused auto-reset of the other families, larger ARZ / BrainTumor / NavierStokes grids
+env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=5, device=dev, simulation_type="outlet", T=1.5, dt=0.025, X=500, dx=1, autoreset=True)
+env.reset()
+for _ in range(70):
+    env.step(rng.uniform(1.0, 1.4, (5, 1)))
+xs = np.linspace(0, 300, 301)
+bt = pcg.make("PDEControlGym-BrainTumor1D", num_envs=5, device=dev, total_dosage=61.2, T=20, dt=1, X=300, dx=1, autoreset=True)
+bt.reset(options={"init_condition": 0.8e5 * np.exp(-0.25 * xs ** 2)})
+for _ in range(45):
+    bt.step(rng.uniform(0, 0.1, 5))
+for n in (21, 33, 50):
+    h = 1.0 / (n - 1)
+    ns = pcg.make("PDEControlGym-NavierStokes2D", num_envs=3, device=dev, boundary_condition=bc, U_ref=np.zeros((50, n, n, 2)), action_ref=np.ones(100),
+                  reward_class=pcg.NSReward(), action_dim=1, maximum_pressure_iteration=10, T=0.004 * (h / 0.05) ** 2, dt=1e-3 * (h / 0.05) ** 2, X=1, dx=h, Y=1, dy=h,
+                  autoreset=True)
+    ns.reset(options={"init": tuple(rng.uniform(-1, 1, (3, n, n)) for _ in range(3))})
+    for _ in range(7):
+        ns.step(rng.uniform(2, 4, 3))
 torch.cuda.synchronize()
 print("sanitize_smoke: done")
