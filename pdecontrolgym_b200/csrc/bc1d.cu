@@ -20,6 +20,12 @@ __global__ void __launch_bounds__(kThreads) bc1d_reset_kernel(const Bc1dArgs a, 
 }
 
 // ---- host-side dispatch --------------------------------------------------------------------------
+static thread_local int64_t g_map_envs = -1;      // set by pdecg_bc1d_step_host while it launches the chunks of one batch
+struct MapEnvsScope {
+    explicit MapEnvsScope(int64_t n) { g_map_envs = n; }
+    ~MapEnvsScope() { g_map_envs = -1; }
+};
+
 static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc1dArgs* out) {
     if (!cfg || !buf) return fail(PDECG_ERR_INVALID, "null cfg/buffers");
     if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch (got %d, want %d)", cfg->abi_version, PDECG_ABI_VERSION);
@@ -62,6 +68,7 @@ static int validate(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf, Bc
     out->ring_len = out->tuned_general ? kLookback + 1 : ring_len_for(cfg->substeps);
     out->carry_len = 1 + out->ring_len;
     out->ar = AutoReset{};
+    out->map_envs = g_map_envs >= 0 ? g_map_envs : buf->n_envs;
     if (out->npts > kCtaMaxPoints) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the shared-memory-resident limit of %d points per env", out->npts, kCtaMaxPoints);
     return PDECG_OK;
 }
@@ -214,6 +221,7 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
     cudaError_t e = cudaEventRecord(g_pipe.start, user);      // order after whatever the caller queued
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
     for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_pipe.s[i], g_pipe.start, 0);
+    MapEnvsScope map_scope(n);                                // every chunk uses the lane mapping of the whole batch
     auto off = [](const void* p, size_t bytes) { return p ? static_cast<const char*>(p) + bytes : nullptr; };
     for (int c = 0; c * per < n; ++c) {
         const int64_t lo = c * per, cnt = (lo + per <= n) ? per : n - lo;

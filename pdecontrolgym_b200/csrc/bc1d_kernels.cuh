@@ -45,6 +45,7 @@ struct Bc1dArgs {
     int ring_len;   // TunedReward1D look-back ring (entries) -- see carry layout below
     int tuned_general;   // 1: ring of the last 101 per-SUBSTEP norms (any substep count; slow path)
     AutoReset ar;
+    int64_t map_envs;    // batch size the lane mapping is chosen for (the whole batch, also when step_host launches chunks)
 };
 
 // carry layout (doubles, per env):
@@ -647,10 +648,18 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
 // Two envs per warp (LPE = 16) are used for the reference's default grids when that wastes fewer lane-slots:
 // 201 points (RD) -> 16 x 13 = 208 slots instead of 32 x 7 = 224; 100 points (Transport) -> 16 x 7 = 112
 // instead of 32 x 4 = 128.
+// Small batches are latency-bound (one control step is a chain of `substeps` dependent stencil updates per warp), so
+// they use one env per warp with the fewest points per lane: TransportPDE1D x 1 env 0.090 -> 0.059 ms per step.  The
+// choice depends only on the size of the whole batch (`map_envs`), never on how a host-buffer step is chunked, so
+// step() and step_host() reduce the reward norms in the same order.
+inline int64_t halfwarp_min_envs() {
+    const char* e = getenv("PDECG_BC1D_HALFWARP_MIN");
+    return e ? atoll(e) : 4096;
+}
 inline void pick_variant(const Bc1dArgs& a, int* LPE, int* K, int* var) {
     const bool dyn = a.cfg.env == PDECG_ENV_REACTION_DIFFUSION && a.cfg.control_type == PDECG_CONTROL_NEUMANN;
     const int k32 = (a.npts + 31) / 32, k16 = (a.npts + 15) / 16;
-    const bool half = !dyn && (k16 == 7 || k16 == 13) && (k16 < 2 * k32) && !getenv("PDECG_BC1D_NO_HALFWARP");
+    const bool half = !dyn && (k16 == 7 || k16 == 13) && (k16 < 2 * k32) && a.map_envs >= halfwarp_min_envs() && !getenv("PDECG_BC1D_NO_HALFWARP");
     *LPE = half ? 16 : 32;
     *K = half ? k16 : (k32 <= 8 ? k32 : ((k32 + 1) / 2) * 2);     // 257..512 points: even K in {10, 12, 14, 16}
     // the frozen-slot variant zeroes the halos of the segment's edge lanes, so it is valid for every npts <= LPE*K

@@ -395,3 +395,32 @@ def test_large_grid_shared_memory_variant(cuda_device, env, monkeypatch):
     for rk in [("temporal", 1), ("differential", 2), ("differential", np.inf), ("t-horizon", 2)]:
         run_pair(cuda_device, env, "fp64", "Dirchilet", ("opposite", "Neumann"), True, np.float64, np.float64, rk, nx=700, B=2, steps=3)
     run_pair(cuda_device, env, "ref", "Dirchilet", ("full", None), False, np.float32, np.float32, "tuned", nx=700, B=3, steps=12, limit=True)
+
+
+@pytest.mark.parametrize("env", ["rd", "tr"])
+def test_small_batch_latency_mapping(cuda_device, env, monkeypatch):
+    """Default lane mapping of batches below 4,096 envs (one env per warp, fewest points per lane) on the reference
+    grids: same bits as the oracle, and step_host() of a chunked batch agrees with step() bit for bit (rewards included:
+    both use the mapping of the whole batch)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    monkeypatch.delenv("PDECG_BC1D_HALFWARP_MIN")
+    for precision, bd in (("ref", np.float32), ("ref", np.float64), ("fp64", np.float64)):
+        run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), True, bd, np.float32, "tuned", B=5, steps=4)
+        run_pair(cuda_device, env, precision, "Neumann", ("collocated", None), False, bd, np.float64, ("differential", 2), B=3, steps=3)
+    # a batch just above the threshold whose host-step chunks fall below it
+    kw, npts, beta, nt = bc1d_case(env, None, 2)
+    N = 12290                      # 3 chunks of 4100, 4100 and 4090 envs
+    eid = "PDEControlGym-ReactionDiffusionPDE1D" if env == "rd" else "PDEControlGym-TransportPDE1D"
+    rng = np.random.default_rng(1)
+    ics = make_ics(rng, N, npts)
+    mk = lambda: pcg.make(eid, num_envs=N, device=cuda_device, precision="ref", reward_class=pcg.NormReward(nt - 1), normalize=True, **kw)  # noqa: E731
+    e1, e2 = mk(), mk()
+    for e in (e1, e2):
+        e.reset(options={"init_condition": ics, "beta": beta.astype(np.float32)})
+    obs_h = torch.empty(N, npts, dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(N, dtype=torch.float64).pin_memory()
+    a = rng.uniform(-1, 1, N).astype(np.float32)
+    o, r, te, tr, _ = e1.step(torch.from_numpy(a))
+    e2.step_host(torch.from_numpy(a).pin_memory(), obs_h, rew_h, None, None)
+    assert np.array_equal(o.cpu().numpy(), obs_h.numpy()) and np.array_equal(r.cpu().numpy(), rew_h.numpy())

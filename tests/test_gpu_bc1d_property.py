@@ -15,9 +15,9 @@ SUBSTEPS_TUNED = [1, 2, 4, 5, 10, 20, 25, 50, 100, 150, 300]
 
 
 @st.composite
-def configs(draw):
+def configs(draw, large=False):
     env = draw(st.sampled_from(["rd", "tr"]))
-    nx = draw(st.one_of(st.integers(4, 254), st.integers(255, 510)))
+    nx = draw(st.one_of(st.integers(511, 2047), st.integers(2048, 4300))) if large else draw(st.one_of(st.integers(4, 254), st.integers(255, 510)))
     reward = draw(st.sampled_from(["tuned", "temporal1", "temporal2", "temporalinf", "differential2"]))
     sub = draw(st.sampled_from(SUBSTEPS_TUNED + [3, 7, 30, 33, 64, 99, 101, 130])) if reward == "tuned" else draw(st.integers(1, 130))
     steps = draw(st.integers(2, 5))
@@ -35,6 +35,17 @@ def configs(draw):
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow], derandomize=True)
 @given(c=configs())
 def test_random_configurations(cuda_device, c):
+    _check(cuda_device, c)
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow], derandomize=True)
+@given(c=configs(large=True))
+def test_random_configurations_large_grids(cuda_device, c):
+    """The CTA-per-env kernels (more than 512 points per env): register-tiled and, for RD + Neumann, shared-memory."""
+    _check(cuda_device, c)
+
+
+def _check(cuda_device, c):
     import torch
     import pdecontrolgym_b200 as pcg
     env, nx, sub, steps, B = c["env"], c["nx"], c["sub"], c["steps"], c["B"]
