@@ -649,12 +649,13 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
 // 201 points (RD) -> 16 x 13 = 208 slots instead of 32 x 7 = 224; 100 points (Transport) -> 16 x 7 = 112
 // instead of 32 x 4 = 128.
 // Small batches are latency-bound (one control step is a chain of `substeps` dependent stencil updates per warp), so
-// they use one env per warp with the fewest points per lane: TransportPDE1D x 1 env 0.090 -> 0.059 ms per step.  The
+// they use one env per warp with the fewest points per lane: TransportPDE1D x 1 env 0.089 -> 0.059 ms per step, x 256
+// envs 0.078 -> 0.060 ms; from ~1,500 envs on the two-envs-per-warp mapping wins (2,048 envs: 0.108 vs 0.130 ms).  The
 // choice depends only on the size of the whole batch (`map_envs`), never on how a host-buffer step is chunked, so
 // step() and step_host() reduce the reward norms in the same order.
 inline int64_t halfwarp_min_envs() {
     const char* e = getenv("PDECG_BC1D_HALFWARP_MIN");
-    return e ? atoll(e) : 4096;
+    return e ? atoll(e) : 1536;
 }
 inline void pick_variant(const Bc1dArgs& a, int* LPE, int* K, int* var) {
     const bool dyn = a.cfg.env == PDECG_ENV_REACTION_DIFFUSION && a.cfg.control_type == PDECG_CONTROL_NEUMANN;

@@ -298,14 +298,14 @@ __global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, co
 // barrier and no shared-memory traffic inside the 2000-sweep loop: 5 DADD/DMUL per point per sweep.
 // The first sweep reads the true boundary values of the warm-start pressure from shared memory, so an
 // arbitrary initial pressure field is handled exactly.
-template <int N, int BR, int BC, int RG, int CG>
-__global__ void __launch_bounds__(kThreads) ns_step_warp_kernel(const NsArgs a) {
+template <int N, int BR, int BC, int RG, int CG, int WPB>
+__global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) {
     static_assert(RG * CG <= 32 && RG * BR >= N && CG * BC >= N, "bad tiling");
     constexpr int NX = N + 2, NPT = NX * NX;
     extern __shared__ double smem[];
     const pdecg_ns_cfg& cfg = a.cfg;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * WPB + wib;
     if (env >= a.buf.n_envs) return;
     double* f0 = smem + static_cast<size_t>(wib) * 4 * NPT;   // u   -> (dx*dy)*rhs
     double* f1 = f0 + NPT;                                     // v   -> pressure
@@ -573,13 +573,17 @@ static int ns_launch_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, 
     NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0, ar_u, ar_v, ar_p, ar_stride};
     if (cfg->nx == 21 && cfg->ny == 21 && !getenv("PDECG_NS_GENERIC")) {
         // the reference grid (examples/NavierStokes/NS2Dppo.py:29-32): warp-per-env register kernel
+        // Warps never cooperate, so the CTA size only sets the scheduling granularity: small batches (fewer warps than
+        // the GPU can hold at full rate) use one-warp CTAs so that the block scheduler spreads them evenly over the SMs.
         constexpr int kN = 19;
-        const size_t smem_w = static_cast<size_t>(kWarpsPerBlock) * 4 * (kN + 2) * (kN + 2) * sizeof(double);
-        auto kern = ns_step_warp_kernel<kN, 2, 7, 10, 3>;
+        const bool small = buf->n_envs < 148 * 16 && !getenv("PDECG_NS_WPB4");
+        const int wpb = small ? 1 : kWarpsPerBlock;
+        const size_t smem_w = static_cast<size_t>(wpb) * 4 * (kN + 2) * (kN + 2) * sizeof(double);
+        auto kern = small ? ns_step_warp_kernel<kN, 2, 7, 10, 3, 1> : ns_step_warp_kernel<kN, 2, 7, 10, 3, kWarpsPerBlock>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_w));
         if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-        kern<<<grid, kThreads, smem_w, static_cast<cudaStream_t>(stream)>>>(a);
+        const unsigned grid = static_cast<unsigned>((buf->n_envs + wpb - 1) / wpb);
+        kern<<<grid, wpb * 32, smem_w, static_cast<cudaStream_t>(stream)>>>(a);
         count_launch();
         return check_launch("ns_step_warp_kernel");
     }

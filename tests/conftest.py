@@ -22,7 +22,7 @@ def cuda_device():
 
 @pytest.fixture(autouse=True)
 def _two_envs_per_warp_for_small_test_batches(monkeypatch):
-    """Batches below 4,096 envs normally take the latency-optimised one-env-per-warp mapping of the Transport / RD
+    """Batches below 1,536 envs normally take the latency-optimised one-env-per-warp mapping of the Transport / RD
     kernels.  The parity tests run small batches, so by default they force the throughput mapping (two envs per warp on
     the reference grids: the headline kernel); tests of the small-batch mapping override the variable themselves."""
     monkeypatch.setenv("PDECG_BC1D_HALFWARP_MIN", "0")

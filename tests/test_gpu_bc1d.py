@@ -399,7 +399,7 @@ def test_large_grid_shared_memory_variant(cuda_device, env, monkeypatch):
 
 @pytest.mark.parametrize("env", ["rd", "tr"])
 def test_small_batch_latency_mapping(cuda_device, env, monkeypatch):
-    """Default lane mapping of batches below 4,096 envs (one env per warp, fewest points per lane) on the reference
+    """Default lane mapping of batches below 1,536 envs (one env per warp, fewest points per lane) on the reference
     grids: same bits as the oracle, and step_host() of a chunked batch agrees with step() bit for bit (rewards included:
     both use the mapping of the whole batch)."""
     import torch
@@ -408,7 +408,8 @@ def test_small_batch_latency_mapping(cuda_device, env, monkeypatch):
     for precision, bd in (("ref", np.float32), ("ref", np.float64), ("fp64", np.float64)):
         run_pair(cuda_device, env, precision, "Dirchilet", ("full", None), True, bd, np.float32, "tuned", B=5, steps=4)
         run_pair(cuda_device, env, precision, "Neumann", ("collocated", None), False, bd, np.float64, ("differential", 2), B=3, steps=3)
-    # a batch just above the threshold whose host-step chunks fall below it
+    # a batch above the threshold whose host-step chunks fall below it
+    monkeypatch.setenv("PDECG_BC1D_HALFWARP_MIN", "4096")
     kw, npts, beta, nt = bc1d_case(env, None, 2)
     N = 12290                      # 3 chunks of 4100, 4100 and 4090 envs
     eid = "PDEControlGym-ReactionDiffusionPDE1D" if env == "rd" else "PDEControlGym-TransportPDE1D"
