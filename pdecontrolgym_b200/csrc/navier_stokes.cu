@@ -576,7 +576,7 @@ static int ns_launch_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, 
         // Warps never cooperate, so the CTA size only sets the scheduling granularity: small batches (fewer warps than
         // the GPU can hold at full rate) use one-warp CTAs so that the block scheduler spreads them evenly over the SMs.
         constexpr int kN = 19;
-        const bool small = buf->n_envs < 148 * 16 && !getenv("PDECG_NS_WPB4");
+        const bool small = (buf->n_envs < 148 * 16 || getenv("PDECG_NS_WPB1")) && !getenv("PDECG_NS_WPB4");
         const int wpb = small ? 1 : kWarpsPerBlock;
         const size_t smem_w = static_cast<size_t>(wpb) * 4 * (kN + 2) * (kN + 2) * sizeof(double);
         auto kern = small ? ns_step_warp_kernel<kN, 2, 7, 10, 3, 1> : ns_step_warp_kernel<kN, 2, 7, 10, 3, kWarpsPerBlock>;
