@@ -89,6 +89,30 @@ def test_invalid_configs_are_rejected_without_a_gpu(lib):
     acfg.abi_version, acfg.simulation_type, acfg.M, acfg.control_freq, acfg.action_dim = lib.ABI_VERSION, 7, 51, 1, 1
     assert L.pdecg_arz_step(ctypes.byref(acfg), ctypes.byref(lib.ArzBuffers()), None) == lib.ERR_INVALID
     assert b"Invalid simulation type" in L.pdecg_last_error()
+    # fused auto-reset entry points: the restart source is mandatory; grid limits are reported before any launch
+    acfg.simulation_type, acfg.M = 1, 51
+    abuf = lib.ArzBuffers()
+    assert L.pdecg_arz_step_autoreset(ctypes.byref(acfg), ctypes.byref(abuf), None, None) == lib.ERR_INVALID
+    assert b"profile" in L.pdecg_last_error()
+    acfg.M = 513
+    assert L.pdecg_arz_step(ctypes.byref(acfg), ctypes.byref(abuf), None) == lib.ERR_UNSUPPORTED
+    bcfg = lib.BtCfg()
+    bcfg.abi_version, bcfg.nx, bcfg.nt, bcfg.dt, bcfg.dx, bcfg.k = lib.ABI_VERSION, 201, 601, 1.0, 1.0, 1e5
+    assert L.pdecg_bt_step_autoreset(ctypes.byref(bcfg), ctypes.byref(lib.BtBuffers()), None, 0, None) == lib.ERR_INVALID
+    assert b"init" in L.pdecg_last_error()
+    bcfg.nx = 513
+    assert L.pdecg_bt_run(ctypes.byref(bcfg), ctypes.byref(lib.BtBuffers()), 0, None) == lib.ERR_UNSUPPORTED
+    ncfg = lib.NsCfg()
+    ncfg.abi_version, ncfg.nx, ncfg.ny, ncfg.nt, ncfg.n_pressure_iters = lib.ABI_VERSION, 21, 21, 200, 10
+    ncfg.dt, ncfg.dx, ncfg.dy = 1e-3, 0.05, 0.05
+    assert L.pdecg_ns_step_autoreset(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None, None, None, 0, None) == lib.ERR_INVALID
+    assert b"init" in L.pdecg_last_error()
+    assert L.pdecg_ns_step(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None) == lib.OK          # n_envs == 0
+    ncfg.nx = ncfg.ny = 64
+    assert L.pdecg_ns_step(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None) == lib.OK          # 4,096 points still fit
+    ncfg.nx = ncfg.ny = 65
+    assert L.pdecg_ns_step(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None) == lib.ERR_UNSUPPORTED
+    assert b"shared-memory-resident" in L.pdecg_last_error()
 
 
 def test_no_cpu_fallback():
