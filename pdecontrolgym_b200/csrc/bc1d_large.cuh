@@ -1,14 +1,18 @@
-// bc1d_large.cuh -- TransportPDE1D / ReactionDiffusionPDE1D step kernel for grids beyond the register-resident
+// bc1d_large.cuh -- TransportPDE1D / ReactionDiffusionPDE1D step kernels for grids beyond the register-resident
 // limit of the warp kernels (more than 512 points per env): ONE CTA = ONE ENV.
 //
 // Reference behaviour restated here (no code shared): hyperbolic.py:126-227, parabolic.py:126-221,
 // base_env_1d.py:20-45, tuned_reward_1d.py:25-40, norm_reward.py:29-73 of lukebhan/PDEControlGym.
 //
-// The env's row lives in shared memory (two ping-pong copies + the per-point coefficient row) for all substeps of a
-// control step; thread t updates the points t, t + THREADS, ... (conflict-free shared-memory accesses), one block
-// barrier per substep.  Same arithmetic, operation order and reward / flag semantics as the warp kernels
-// (bc1d_kernels.cuh) -- states are bit-identical to numpy -- and HBM still carries one row in and out per control
-// step.  Included at the end of bc1d_kernels.cuh.
+// Two kernels, same arithmetic, operation order and reward / flag semantics as the warp kernels (bc1d_kernels.cuh):
+// states are bit-identical to numpy, and HBM still carries one row in and out per control step.
+//   bc1d_step_cta_reg_kernel : each thread keeps K contiguous points in registers and updates them in place; one
+//                              (first, last) pair per thread crosses threads per substep through shared memory
+//                              (default; 1.8-2.1e12 grid-point updates/s on a B200).
+//   bc1d_step_cta_kernel     : the row lives in shared memory (two ping-pong copies + the coefficient row), thread t
+//                              updates the points t, t + THREADS, ...; used for ReactionDiffusion with Neumann
+//                              control, where the actuated value changes every substep.
+// One block barrier per substep in both.  Included at the end of bc1d_kernels.cuh.
 #pragma once
 #include <type_traits>
 
