@@ -233,6 +233,15 @@ int pdecg_bt_run(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32_t m
 int pdecg_bt_step_autoreset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const double* init,
                             int64_t init_env_stride, pdecg_stream_t stream);
 
+/* PDECG_BT_RAW_STEP over HOST buffers (the end-to-end form of BrainTumor1D.step for a caller whose learner lives on
+ * the host): H2D(action_host [n_envs]) -> kernel -> D2H(state row = observation [n_envs, nx], reward, flags), all on
+ * `stream`, then stream-synchronised.  Any output pointer may be NULL to skip that copy; buf->action is the device
+ * staging buffer for the actions.  autoreset_init != NULL fuses the same-step auto-reset as pdecg_bt_step_autoreset. */
+int pdecg_bt_step_host(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const double* action_host,
+                       double* obs_host, double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                       uint8_t* valid_host, const double* autoreset_init, int64_t autoreset_init_env_stride,
+                       pdecg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Family 3: TrafficPDE1D (Aw-Rascle-Zhang) + TrafficARZReward      -- all float64
  * ------------------------------------------------------------------------------------------ */
@@ -286,6 +295,13 @@ int pdecg_arz_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, pdecg
 int pdecg_arz_step_autoreset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* profile,
                              pdecg_stream_t stream);
 
+/* TrafficPDE1D.step over HOST buffers: H2D(action_host [n_envs, action_dim]) -> kernel -> D2H(obs [n_envs, 2*M],
+ * reward, flags) on `stream`, then stream-synchronised.  Output pointers may be NULL; buf->action is the device
+ * staging buffer.  autoreset_profile (DEVICE pointer, may be NULL) fuses the restart as pdecg_arz_step_autoreset. */
+int pdecg_arz_step_host(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* action_host,
+                        double* obs_host, double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                        const double* autoreset_profile, pdecg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Family 4: NavierStokes2D (Chorin projection, Jacobi pressure solve) + NSReward   -- all float64
  * ------------------------------------------------------------------------------------------ */
@@ -336,6 +352,13 @@ int pdecg_ns_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, pdecg_st
 int pdecg_ns_step_autoreset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* init_u,
                             const double* init_v, const double* init_p, int64_t init_env_stride,
                             pdecg_stream_t stream);
+/* NavierStokes2D.step over HOST buffers: H2D(action_host [n_envs]) -> kernel -> D2H(obs = U[t] [n_envs, ny, nx, 2],
+ * reward, flags) on `stream`, then stream-synchronised.  Output pointers may be NULL; buf->action is the device staging
+ * buffer.  autoreset_u/v/p (DEVICE pointers, all three or none) fuse the restart as pdecg_ns_step_autoreset. */
+int pdecg_ns_step_host(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* action_host,
+                       double* obs_host, double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                       uint8_t* valid_host, const double* autoreset_u, const double* autoreset_v,
+                       const double* autoreset_p, int64_t autoreset_env_stride, pdecg_stream_t stream);
 /* NavierStokes2D.solve_pressure (:94-116) alone, for callers such as examples/NavierStokes/NS2Doptimization.py:
  * p <- n_pressure_iters Jacobi sweeps on rhs = density/dt * (d u/dx + d v/dy), warm-started from p. */
 int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v,

@@ -146,12 +146,16 @@ def lib():
     L.pdecg_bt_run.restype = C.c_int
     L.pdecg_bt_step_autoreset.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers), C.c_void_p, C.c_int64, C.c_void_p]
     L.pdecg_bt_step_autoreset.restype = C.c_int
+    L.pdecg_bt_step_host.argtypes = [C.POINTER(BtCfg), C.POINTER(BtBuffers)] + [C.c_void_p] * 7 + [C.c_int64, C.c_void_p]
+    L.pdecg_bt_step_host.restype = C.c_int
     L.pdecg_arz_reset.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_arz_reset.restype = C.c_int
     L.pdecg_arz_step.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p]
     L.pdecg_arz_step.restype = C.c_int
     L.pdecg_arz_step_autoreset.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers), C.c_void_p, C.c_void_p]
     L.pdecg_arz_step_autoreset.restype = C.c_int
+    L.pdecg_arz_step_host.argtypes = [C.POINTER(ArzCfg), C.POINTER(ArzBuffers)] + [C.c_void_p] * 7
+    L.pdecg_arz_step_host.restype = C.c_int
     L.pdecg_ns_reset.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p]
     L.pdecg_ns_reset.restype = C.c_int
@@ -160,6 +164,8 @@ def lib():
     L.pdecg_ns_step_autoreset.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p]
     L.pdecg_ns_step_autoreset.restype = C.c_int
+    L.pdecg_ns_step_host.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers)] + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p]
+    L.pdecg_ns_step_host.restype = C.c_int
     L.pdecg_ns_solve_pressure.argtypes = [C.POINTER(NsCfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_ns_solve_pressure.restype = C.c_int
     L.pdecg_selftest_constdiv.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -189,3 +195,12 @@ def current_raw_stream(device_index: int) -> int:
         return torch._C._cuda_getCurrentRawStream(device_index)
     except AttributeError:  # pragma: no cover - older/newer torch
         return torch.cuda.current_stream(device_index).cuda_stream
+
+
+def host_ptr(t, dtype, numel, what):
+    """data_ptr() of an optional contiguous CPU tensor argument of a `*_step_host` call (None -> NULL)."""
+    if t is None:
+        return None
+    if t.device.type != "cpu" or not t.is_contiguous() or t.dtype != dtype or t.numel() != numel:
+        raise ValueError(f"{what} must be a contiguous CPU {dtype} tensor with {numel} elements")
+    return t.data_ptr()

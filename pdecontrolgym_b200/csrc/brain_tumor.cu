@@ -577,3 +577,27 @@ extern "C" int pdecg_bt_step_autoreset(const pdecg_bt_cfg* cfg, const pdecg_bt_b
     if (!init) return fail(PDECG_ERR_INVALID, "null init buffer");
     return bt_launch(cfg, buf, PDECG_BT_RAW_STEP, init, init_env_stride, stream);
 }
+
+// Host-buffer raw step: H2D(actions) -> kernel -> D2H(state = observation, reward, flags) on `stream`, then synchronised.
+extern "C" int pdecg_bt_step_host(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, const double* action_host,
+                                  double* obs_host, double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                                  uint8_t* valid_host, const double* autoreset_init, int64_t autoreset_init_env_stride,
+                                  pdecg_stream_t stream) {
+    int rc = bt_validate(cfg, buf);
+    if (rc != PDECG_OK) return rc;
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!action_host || !buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
+    if (valid_host && !buf->valid) return fail(PDECG_ERR_INVALID, "valid_host needs a device valid buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n = static_cast<size_t>(buf->n_envs);
+    cudaError_t e = cudaMemcpyAsync(const_cast<double*>(buf->action), action_host, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
+    if ((rc = bt_launch(cfg, buf, PDECG_BT_RAW_STEP, autoreset_init, autoreset_init_env_stride, stream)) != PDECG_OK) return rc;
+    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->u, n * cfg->nx * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+    if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
+    if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
+    if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
+    if (valid_host && (e = cudaMemcpyAsync(valid_host, buf->valid, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H valid: %s", cudaGetErrorString(e));
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+    return PDECG_OK;
+}

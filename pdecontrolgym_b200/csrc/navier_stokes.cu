@@ -613,3 +613,29 @@ extern "C" int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, 
     a.su = u; a.sv = v; a.sp = p; a.solve_only = 1;
     return ns_launch_generic(a, n_envs, static_cast<cudaStream_t>(stream));
 }
+
+// Host-buffer step: H2D(actions) -> kernel -> D2H(observation U[t], reward, flags) on `stream`, then synchronised.
+extern "C" int pdecg_ns_step_host(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* action_host,
+                                  double* obs_host, double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                                  uint8_t* valid_host, const double* autoreset_u, const double* autoreset_v,
+                                  const double* autoreset_p, int64_t autoreset_env_stride, pdecg_stream_t stream) {
+    int rc = ns_validate_cfg(cfg);
+    if (rc != PDECG_OK) return rc;
+    if (!buf || buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "bad buffers");
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!action_host || !buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
+    if (valid_host && !buf->valid) return fail(PDECG_ERR_INVALID, "valid_host needs a device valid buffer");
+    if ((autoreset_u || autoreset_v || autoreset_p) && !(autoreset_u && autoreset_v && autoreset_p)) return fail(PDECG_ERR_INVALID, "auto-reset needs all three initial fields");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n = static_cast<size_t>(buf->n_envs), npt = static_cast<size_t>(cfg->nx) * cfg->ny;
+    cudaError_t e = cudaMemcpyAsync(const_cast<double*>(buf->action), action_host, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
+    if ((rc = ns_launch_step(cfg, buf, autoreset_u, autoreset_v, autoreset_p, autoreset_env_stride, stream)) != PDECG_OK) return rc;
+    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->obs, n * npt * 2 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+    if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
+    if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
+    if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
+    if (valid_host && (e = cudaMemcpyAsync(valid_host, buf->valid, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H valid: %s", cudaGetErrorString(e));
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+    return PDECG_OK;
+}

@@ -340,3 +340,24 @@ extern "C" int pdecg_arz_step_autoreset(const pdecg_arz_cfg* cfg, const pdecg_ar
     if (!profile) return fail(PDECG_ERR_INVALID, "null profile buffer");
     return arz_launch_step(cfg, buf, profile, stream);
 }
+
+// Host-buffer step: H2D(actions) -> kernel -> D2H(observation, reward, flags) on `stream`, then stream-synchronised.
+extern "C" int pdecg_arz_step_host(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, const double* action_host,
+                                   double* obs_host, double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                                   const double* autoreset_profile, pdecg_stream_t stream) {
+    int rc = arz_validate(cfg, buf);
+    if (rc != PDECG_OK) return rc;
+    if (buf->n_envs == 0) return PDECG_OK;
+    if (!action_host || !buf->action) return fail(PDECG_ERR_INVALID, "null action buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n = static_cast<size_t>(buf->n_envs);
+    cudaError_t e = cudaMemcpyAsync(const_cast<double*>(buf->action), action_host, n * cfg->action_dim * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
+    if ((rc = arz_launch_step(cfg, buf, autoreset_profile, stream)) != PDECG_OK) return rc;
+    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->obs, n * 2 * cfg->M * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+    if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
+    if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
+    if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+    return PDECG_OK;
+}

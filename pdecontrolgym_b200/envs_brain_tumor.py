@@ -198,6 +198,31 @@ class BrainTumor1D(StateDictMixin):
         rest = self._out_rest(outs)
         return ((self.u.clone() if self.copy_obs else self.u),) + rest
 
+    def step_host(self, action_host, obs_host=None, reward_host=None, terminated_host=None, truncated_host=None, valid_host=None):
+        """End-to-end raw step over HOST buffers (pdecg_bt_step_host): H2D(actions) -> kernel -> D2H(state, reward,
+        flags) on the current stream, synchronised on return.  CPU tensors (pin them): `action_host` float64 [num_envs];
+        `obs_host` float64 [num_envs, nx]; `reward_host` float64 [num_envs]; flags / valid uint8 [num_envs]."""
+        if self._ic is None:
+            raise RuntimeError("call reset() before step_host()")
+        N = self.num_envs
+        a_ptr = _lib.host_ptr(action_host, torch.float64, N, "action_host")
+        if a_ptr is None:
+            raise ValueError("action_host is required")
+        if getattr(self, "_act_dev", None) is None:
+            self._act_dev = torch.empty((N,), dtype=torch.float64, device=self.device)
+        buf = self._buf
+        buf.action, buf.obs = self._act_dev.data_ptr(), None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pdecg_bt_step_host(
+                C.byref(self._cfg), C.byref(buf), a_ptr,
+                _lib.host_ptr(obs_host, torch.float64, N * self.nx, "obs_host"),
+                _lib.host_ptr(reward_host, torch.float64, N, "reward_host"),
+                _lib.host_ptr(terminated_host, torch.uint8, N, "terminated_host"),
+                _lib.host_ptr(truncated_host, torch.uint8, N, "truncated_host"),
+                _lib.host_ptr(valid_host, torch.uint8, N, "valid_host"),
+                self._ic.data_ptr() if self.autoreset else None, 0 if self._ic.shape[0] == 1 else self.nx, self._stream()))
+        return obs_host, reward_host, terminated_host, truncated_host, {}
+
     # -- reference attributes, as per-env tensors ------------------------------------------------
     def _icol(self, i):
         return self._ienv[:, i]

@@ -197,6 +197,33 @@ class NavierStokes2D(StateDictMixin):
         obs = self._obs.clone() if self.copy_obs else self._obs
         return obs, reward, terminated, truncated, info
 
+    def step_host(self, action_host, obs_host=None, reward_host=None, terminated_host=None, truncated_host=None, valid_host=None):
+        """End-to-end step over HOST buffers (pdecg_ns_step_host): H2D(actions) -> kernel -> D2H(U[t], reward, flags) on
+        the current stream, synchronised on return.  CPU tensors (pin them): `action_host` float64 [num_envs];
+        `obs_host` float64 [num_envs, ny, nx, 2]; `reward_host` float64 [num_envs]; flags / valid uint8 [num_envs]."""
+        if not self._reset_done:
+            raise RuntimeError("call reset() before step_host()")
+        N = self.num_envs
+        a_ptr = _lib.host_ptr(action_host, torch.float64, N, "action_host")
+        if a_ptr is None:
+            raise ValueError("action_host is required")
+        if getattr(self, "_act_dev", None) is None:
+            self._act_dev = torch.empty((N,), dtype=torch.float64, device=self.device)
+        buf = self._buf
+        buf.action = self._act_dev.data_ptr()
+        iu, iv, ip = self._init if self.autoreset else (None, None, None)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pdecg_ns_step_host(
+                C.byref(self._cfg), C.byref(buf), a_ptr,
+                _lib.host_ptr(obs_host, torch.float64, N * self.nx * self.ny * 2, "obs_host"),
+                _lib.host_ptr(reward_host, torch.float64, N, "reward_host"),
+                _lib.host_ptr(terminated_host, torch.uint8, N, "terminated_host"),
+                _lib.host_ptr(truncated_host, torch.uint8, N, "truncated_host"),
+                _lib.host_ptr(valid_host, torch.uint8, N, "valid_host"),
+                None if iu is None else iu.data_ptr(), None if iv is None else iv.data_ptr(), None if ip is None else ip.data_ptr(),
+                self.nx * self.ny, self._stream()))
+        return obs_host, reward_host, terminated_host, truncated_host, {}
+
     def solve_pressure(self, u, v, p_prev):
         """Batched `solve_pressure` (navier_stokes2D.py:94-116) for external callers; returns the new p."""
         u, v = self._field(u, "u"), self._field(v, "v")

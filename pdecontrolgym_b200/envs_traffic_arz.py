@@ -204,6 +204,32 @@ class TrafficPDE1D(StateDictMixin):
                                                                   self._terminated.data_ptr(), self._truncated.data_ptr())
         return obs, reward, terminated, truncated, self.info
 
+    def step_host(self, action_host, obs_host=None, reward_host=None, terminated_host=None, truncated_host=None):
+        """End-to-end step over HOST buffers (pdecg_arz_step_host): H2D(actions) -> kernel -> D2H(obs, reward, flags)
+        on the current stream, synchronised on return.  All arguments are CPU tensors (pin them for full PCIe bandwidth):
+        `action_host` float64 [num_envs, action_dim]; `obs_host` float64 [num_envs, 2*M]; `reward_host` float64
+        [num_envs]; flags uint8 [num_envs].  Outputs are written in place and returned."""
+        N, nact = self.num_envs, self._cfg.action_dim
+        a_ptr = _lib.host_ptr(action_host, torch.float64, N * nact, "action_host")
+        if a_ptr is None:
+            raise ValueError("action_host is required")
+        if getattr(self, "_act_dev", None) is None:
+            self._act_dev = torch.empty((N, nact), dtype=torch.float64, device=self.device)
+        buf = self._buf
+        buf.action = self._act_dev.data_ptr()
+        fused = self.autoreset and self.simulation_type != "outlet-train"
+        if self.autoreset and not fused:
+            raise NotImplementedError("step_host with autoreset is not available for 'outlet-train' (rs is re-drawn on the host)")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pdecg_arz_step_host(
+                C.byref(self._cfg), C.byref(buf), a_ptr,
+                _lib.host_ptr(obs_host, torch.float64, N * 2 * self.M, "obs_host"),
+                _lib.host_ptr(reward_host, torch.float64, N, "reward_host"),
+                _lib.host_ptr(terminated_host, torch.uint8, N, "terminated_host"),
+                _lib.host_ptr(truncated_host, torch.uint8, N, "truncated_host"),
+                self._profile.data_ptr() if fused else None, self._stream()))
+        return obs_host, reward_host, terminated_host, truncated_host, self.info
+
     # reference attributes
     r = property(lambda s: s._ry[:, 0, :])
     y = property(lambda s: s._ry[:, 1, :])

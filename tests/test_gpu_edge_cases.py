@@ -301,3 +301,63 @@ def test_navier_stokes_fused_autoreset_equals_step_then_masked_reset(cuda_device
     n_done = _staggered_pair(fused, manual, reset, lambda k: acts[k], 16, ("u", "v", "p", "time_index"),
                              _stagger_by_masked_reset(reset, lambda k: acts[k], stag))
     assert n_done >= N
+
+
+@pytest.mark.parametrize("autoreset", [False, True])
+def test_step_host_matches_step_for_arz_bt_ns(cuda_device, autoreset):
+    """pdecg_{arz,bt,ns}_step_host (H2D actions -> kernel -> D2H observation / reward / flags) == the device-resident
+    step of a twin env, with and without the fused same-step auto-reset."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    rng = np.random.default_rng(12)
+
+    def pinned(*shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype).pin_memory()
+
+    # Traffic-ARZ ('both': two actions per env), 24-step episodes
+    N = 6
+    kw = dict(T=1.5, dt=0.25, X=500, dx=10, simulation_type="both", autoreset=autoreset)
+    e1 = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=cuda_device, **kw)
+    e2 = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=cuda_device, **kw)
+    e1.reset(), e2.reset()
+    oh, rh, teh, trh = pinned(N, 102), pinned(N), pinned(N, dtype=torch.uint8), pinned(N, dtype=torch.uint8)
+    for k in range(30):
+        a = torch.from_numpy(rng.uniform(0.9, 1.5, (N, 2)))
+        o, r, te, tr, _ = e1.step(a)
+        e2.step_host(a.pin_memory(), oh, rh, teh, trh)
+        assert torch.equal(o.cpu(), oh) and torch.equal(r.cpu(), rh), f"arz step {k}"
+        assert torch.equal(te.cpu(), teh.bool()) and torch.equal(tr.cpu(), trh.bool())
+        assert torch.equal(e1._ry, e2._ry) and torch.equal(e1._fenv, e2._fenv)
+
+    # BrainTumor raw step, 12-day episodes
+    xs = np.linspace(0, 100, 101)
+    ic = 0.8e5 * np.exp(-0.25 * xs ** 2)[None, :] * rng.uniform(0.5, 1.5, (N, 1))
+    kw = dict(total_dosage=61.2, T=12, dt=1, X=100, dx=1, t1_detection_radius=2, autoreset=autoreset)
+    e1 = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, **kw)
+    e2 = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, **kw)
+    e1.reset(options={"init_condition": ic}), e2.reset(options={"init_condition": ic})
+    oh, vh = pinned(N, 101), pinned(N, dtype=torch.uint8)
+    for k in range(16):
+        a = torch.from_numpy(rng.uniform(0, 0.1, N))
+        o, r, te, tr, info = e1.step(a)
+        e2.step_host(a.pin_memory(), oh, rh, teh, trh, vh)
+        assert torch.equal(o.cpu(), oh) and torch.equal(r.cpu(), rh), f"bt day {k}"
+        assert torch.equal(te.cpu(), teh.bool()) and torch.equal(tr.cpu(), trh.bool()) and torch.equal(info["valid"].cpu(), vh.bool())
+        assert torch.equal(e1._ienv, e2._ienv) and torch.equal(e1._fenv, e2._fenv)
+
+    # NavierStokes (warp kernel), 5-step episodes
+    n = 21
+    kw = dict(boundary_condition=BC, U_ref=rng.uniform(-1, 1, (50, n, n, 2)), action_ref=np.ones(100), reward_class=pcg.NSReward(0.1),
+              maximum_pressure_iteration=9, T=0.006, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05, autoreset=autoreset)
+    e1 = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, **kw)
+    e2 = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, **kw)
+    init = tuple(rng.uniform(-1, 1, (N, n, n)) for _ in range(3))
+    e1.reset(options={"init": init}), e2.reset(options={"init": init})
+    oh = pinned(N, n, n, 2)
+    for k in range(8):
+        a = torch.from_numpy(rng.uniform(2, 4, N))
+        o, r, te, tr, info = e1.step(a)
+        e2.step_host(a.pin_memory(), oh, rh, teh, trh, vh)
+        assert torch.equal(o.cpu(), oh) and torch.equal(r.cpu(), rh), f"ns step {k}"
+        assert torch.equal(te.cpu(), teh.bool()) and torch.equal(info["valid"].cpu(), vh.bool())
+        assert torch.equal(e1.p, e2.p) and torch.equal(e1.time_index, e2.time_index)
