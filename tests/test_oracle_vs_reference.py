@@ -18,9 +18,9 @@ pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tre
 quiet = lambda: contextlib.redirect_stdout(io.StringIO())  # noqa: E731
 
 
-def _bc1d_pair(env, ct, sl, st, nz, bd, ad, rk, precision, limit=False, steps=12):
+def _bc1d_pair(env, ct, sl, st, nz, bd, ad, rk, precision, limit=False, steps=12, nx=None):
     ref = load_reference()
-    kw, npts, beta, nt = bc1d_case(env, None, steps)
+    kw, npts, beta, nt = bc1d_case(env, nx, steps)
     beta = beta.astype(bd)
     nt_r = nt - 1
     if rk == "tuned":
@@ -79,18 +79,30 @@ def test_bc1d_rewards_full_episode(env, rk):
     _bc1d_pair(env, "Dirchilet", "full", None, False, np.float64, np.float64, rk, "ref", limit=True)
 
 
-@pytest.mark.parametrize("st", ["inlet", "outlet", "both"])
-@pytest.mark.parametrize("cf", [1, 3])
-def test_traffic_arz(st, cf):
+@pytest.mark.parametrize("env", ["rd", "tr"])
+@pytest.mark.parametrize("nx", [37, 300, 511, 700, 1500, 4097])
+def test_bc1d_other_grids(env, nx):
+    """Grids other than the examples' (incl. the sizes served by the CTA-per-env CUDA kernels): the oracle the GPU
+    parity tests lean on is pinned to the live reference there too."""
+    warnings.simplefilter("ignore")
+    _bc1d_pair(env, "Dirchilet", "full", None, True, np.float32, np.float32, "tuned", "ref", steps=3, nx=nx)
+    _bc1d_pair(env, "Neumann", "collocated", None, False, np.float64, np.float64, ("differential", 2), "ref", steps=3, nx=nx)
+    _bc1d_pair(env, "Dirchilet", "opposite", "Neumann", True, np.float64, np.float32, ("t-horizon", 2), "fp64", steps=3, nx=nx)
+
+
+@pytest.mark.parametrize("st,cf,X,dx,dt", [("inlet", 1, 500, 10, 0.25), ("outlet", 1, 500, 10, 0.25), ("both", 1, 500, 10, 0.25),
+                                           ("inlet", 3, 500, 10, 0.25), ("outlet", 3, 500, 10, 0.25), ("both", 3, 500, 10, 0.25),
+                                           ("both", 2, 500, 4, 0.1), ("outlet", 1, 500, 1.75, 0.04375), ("both", 2, 500, 1, 0.025)])
+def test_traffic_arz(st, cf, X, dx, dt):
     ref = load_reference()
-    kw = dict(T=20, dt=0.25, X=500, dx=10)
+    kw = dict(T=20 * dt / 0.25, dt=dt, X=X, dx=dx)
     with quiet():
         renv = ref.TrafficPDE1D(simulation_type=st, control_freq=cf, limit_pde_state_size=True, reward_class=ref.TrafficARZReward(), **kw)
     oenv = O.TrafficARZOracle(1, simulation_type=st, control_freq=cf, limit_pde_state_size=True, **kw)
     o1, _ = renv.reset()
     assert np.array_equal(o1, oenv.reset()[0])
     rng = np.random.default_rng(3)
-    for k in range(400):
+    for k in range(400 if dx == 10 else 120):
         a = rng.uniform(0.7 * 1.2, 1.3 * 1.2, size=2 if st == "both" else 1)
         o1, r1, te1, tr1, _ = renv.step(a.copy())
         o2, r2, te2, tr2 = oenv.step(a[None, :])
@@ -122,13 +134,39 @@ def test_brain_tumor_wrapper_schedules():
         assert renv.cDeathDay == oenv.cDeathDay[0] and rw.soft_constraint_violations == ow.soft_constraint_violations
 
 
-def test_navier_stokes():
+@pytest.mark.parametrize("X", [63, 300, 460])
+def test_brain_tumor_other_grids(X):
+    """Raw BrainTumor1D stepping on domains other than the notebook's 200 mm (up to the 512-point CUDA limit)."""
+    from tests.golden.gen_golden import BT_P, bt_ic
+    ref = load_reference()
+    P = {**BT_P, "X": X, "T": 150}
+    renv = ref.BrainTumor1D(reward_class=ref.BrainTumorReward(), normalize=True, reset_init_condition_func=bt_ic, verbose=False, **P)
+    oenv = O.BrainTumorOracle(1, **P)
+    renv.t_benchmark = 60
+    oenv.t_benchmark = np.array([60])
+    with quiet():
+        o1, _ = renv.reset()
+    assert np.array_equal(o1, oenv.reset(bt_ic(X, X + 1))[0])
+    for day in range(149):
+        with quiet():
+            out = renv.step(0.03)
+        o2, r2, te2, tr2, valid = oenv.step(np.array([0.03]))
+        if out is None:
+            assert not valid[0]
+            break
+        o1, r1, te1, tr1, _ = out
+        assert np.array_equal(o1, o2[0]) and float(r1) == float(r2[0]) and (bool(te1), bool(tr1)) == (bool(te2[0]), bool(tr2[0])), f"day {day}"
+
+
+@pytest.mark.parametrize("n", [21, 11, 33, 64])
+def test_navier_stokes(n):
     ref = load_reference()
     rng = np.random.default_rng(5)
-    uref = rng.uniform(-1, 1, (200, 21, 21, 2))
+    uref = rng.uniform(-1, 1, (200, n, n, 2))
     bc = {"upper": ["Controllable", "Neumann"], "lower": ["Neumann", "Dirchilet"], "left": ["Dirchilet", "Controllable"], "right": ["Neumann", "Neumann"]}
-    u0, v0, p0 = (rng.uniform(-1, 1, (21, 21)) for _ in range(3))
-    P = dict(T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05)
+    u0, v0, p0 = (rng.uniform(-1, 1, (n, n)) for _ in range(3))
+    h = 1.0 / (n - 1)
+    P = dict(T=0.2 * (h / 0.05) ** 2, dt=1e-3 * (h / 0.05) ** 2, X=1, dx=h, Y=1, dy=h)
     renv = ref.NavierStokes2D(reset_init_condition_func=lambda X: (u0.copy(), v0.copy(), p0.copy()), boundary_condition=bc, U_ref=uref,
                               action_ref=2.0 * np.ones(1000), reward_class=ref.NSReward(0.1), action_dim=1, maximum_pressure_iteration=41, **P)
     oenv = O.NavierStokesOracle(1, boundary_condition=bc, U_ref=uref, action_ref=2.0 * np.ones(1000), maximum_pressure_iteration=41, **P)
