@@ -45,10 +45,21 @@ BC1D_CASES = [
 ]
 
 
-def gen_bc1d():
+# grids beyond the examples' (the CTA-per-env CUDA kernels): name, ..., f64 state, nx, control steps
+BC1D_LARGE_CASES = [
+    ("rd_700_dir_full_tuned", "rd", "Dirchilet", "full", None, True, "float32", "float32", "tuned", False, 700, 4),
+    ("tr_1500_dir_full_tuned", "tr", "Dirchilet", "full", None, True, "float32", "float32", "tuned", False, 1500, 4),
+    ("rd_2500_neu_col_norm_fp64", "rd", "Neumann", "collocated", None, False, "float64", "float64", ("temporal", 2), True, 2500, 3),
+    ("tr_4097_dir_opp_diff_b64", "tr", "Dirchilet", "opposite", "Neumann", True, "float64", "float32", ("differential", 1), False, 4097, 3),
+]
+
+
+def gen_bc1d(cases=None, fname="bc1d_reference_runs.npz"):
     out = {}
-    for (name, env, ct, sl, st, nz, bd, ad, rk, f64) in BC1D_CASES:
-        kw, npts, beta, nt = bc1d_case(env, None, 12)
+    for case in (BC1D_CASES if cases is None else cases):
+        (name, env, ct, sl, st, nz, bd, ad, rk, f64) = case[:10]
+        nx, steps = (case[10], case[11]) if len(case) > 10 else (None, 12)
+        kw, npts, beta, nt = bc1d_case(env, nx, steps)
         beta = beta.astype(bd)
         nt_r = nt - 1
         if rk == "tuned":
@@ -68,7 +79,7 @@ def gen_bc1d():
             renv.beta = np.asarray(renv.beta, dtype=np.float64)
             obs0 = renv.sensing_update(renv.u[0], renv.dx, renv.sensing_noise_func)
         acts, obs, rew, term, trunc = [], [np.asarray(obs0)], [], [], []
-        for k in range(12):
+        for k in range(steps):
             a = np.array([rng.uniform(-1, 1) if nz else rng.uniform(-3, 3)], dtype=ad)
             o, r, te, tr, _ = renv.step(a)
             acts.append(a[0]); obs.append(np.array(o)); rew.append(float(r)); term.append(bool(te)); trunc.append(bool(tr))
@@ -79,8 +90,8 @@ def gen_bc1d():
         out[name + "/reward"] = np.array(rew)
         out[name + "/terminated"] = np.array(term)
         out[name + "/truncated"] = np.array(trunc)
-    np.savez_compressed(os.path.join(HERE, "bc1d_reference_runs.npz"), **out)
-    print("bc1d:", len(BC1D_CASES), "cases")
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+    print(fname, len(BC1D_CASES if cases is None else cases), "cases")
 
 
 def gen_arz():
@@ -195,6 +206,7 @@ def ref_root():
 
 if __name__ == "__main__":
     gen_bc1d()
+    gen_bc1d(BC1D_LARGE_CASES, "bc1d_large_grid_reference_runs.npz")
     gen_arz()
     gen_brain_tumor()
     gen_ns()

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 from oracle import np_oracle as O
-from tests.golden.gen_golden import BC1D_CASES, BT_P, bt_ic
+from tests.golden.gen_golden import BC1D_CASES, BC1D_LARGE_CASES, BT_P, bt_ic
 from tests.helpers import bc1d_case
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -21,15 +21,17 @@ def _to_np(x):
 
 # ---- Transport / ReactionDiffusion --------------------------------------------------------------------
 def bc1d_cases():
-    return [c[0] for c in BC1D_CASES]
+    return [c[0] for c in BC1D_CASES] + [c[0] for c in BC1D_LARGE_CASES]
 
 
 def replay_bc1d(name, backend, device=None, reward_rtol=0.0):
     """backend: 'oracle' or 'cuda'.  States/observations must equal the reference bit for bit; rewards
     exactly for the oracle (same numpy routines), within `reward_rtol` of the row norms for CUDA."""
-    g = load("bc1d_reference_runs.npz")
-    (_, env, ct, sl, st, nz, bd, ad, rk, f64) = next(c for c in BC1D_CASES if c[0] == name)
-    kw, npts, beta, nt = bc1d_case(env, None, 12)
+    case = next(c for c in BC1D_CASES + BC1D_LARGE_CASES if c[0] == name)
+    (_, env, ct, sl, st, nz, bd, ad, rk, f64) = case[:10]
+    nx, steps = (case[10], case[11]) if len(case) > 10 else (None, 12)       # large-grid cases carry their own size
+    g = load("bc1d_large_grid_reference_runs.npz" if len(case) > 10 else "bc1d_reference_runs.npz")
+    kw, npts, beta, nt = bc1d_case(env, nx, steps)
     ic, beta, acts = g[name + "/ic"], g[name + "/beta"], g[name + "/actions"]
     common = dict(normalize=nz, sensing_loc=sl, control_type=ct, sensing_type=st, limit_pde_state_size=False,
                   max_state_value=30.0, max_control_value=20, **kw)
@@ -50,7 +52,7 @@ def replay_bc1d(name, backend, device=None, reward_rtol=0.0):
         step = lambda a: e.step(a)[:4]  # noqa: E731
     want = g[name + "/obs"]
     assert np.array_equal(_to_np(obs).reshape(want[0].shape), want[0]), f"{name}: reset obs"
-    for k in range(12):
+    for k in range(steps):
         o, r, te, tr = step(np.array([acts[k]], dtype=acts.dtype))
         o = _to_np(o).reshape(want[k + 1].shape)
         assert o.dtype == want.dtype, (o.dtype, want.dtype)
