@@ -60,3 +60,45 @@ def test_traffic_static_helpers_match_reference_formulas():
     rho, y = np.array([0.1, 0.12]), np.array([0.3, -0.2])
     assert np.array_equal(T.F_r(40, 0.16, rho, y), y + rho * (40 * (1 - rho / 0.16)))
     assert np.array_equal(T.F_y(40, 0.16, rho, y), y * (y / rho + 40 * (1 - rho / 0.16)))
+
+
+def test_host_buffer_argument_validation():
+    """`step_host` arguments are checked on the host before any CUDA call (pdecontrolgym_b200._lib.host_ptr)."""
+    import torch
+    from pdecontrolgym_b200 import _lib
+    assert _lib.host_ptr(None, torch.float64, 4, "x") is None
+    t = torch.zeros(4, dtype=torch.float64)
+    assert _lib.host_ptr(t, torch.float64, 4, "x") == t.data_ptr()
+    for bad in (torch.zeros(4, dtype=torch.float32), torch.zeros(5, dtype=torch.float64), torch.zeros(2, 4, dtype=torch.float64)[:, ::2]):
+        with pytest.raises(ValueError, match="contiguous CPU"):
+            _lib.host_ptr(bad, torch.float64, 4, "x")
+    assert issubclass(pcg.PdecgError, RuntimeError) and pcg.PdecgError(-2, "msg").code == -2
+
+
+def test_adjoint_wall_zeroing_matches_the_example():
+    """controllers.NavierStokesAdjoint._zero_walls == apply_boundary of examples/NavierStokes/NS2Doptimization.py:55-60."""
+    import torch
+    from pdecontrolgym_b200.controllers import NavierStokesAdjoint
+    rng = np.random.default_rng(0)
+    a1, a2 = rng.uniform(-1, 1, (3, 7, 7)), rng.uniform(-1, 1, (3, 7, 7))
+    t1, t2 = NavierStokesAdjoint._zero_walls(torch.from_numpy(a1.copy()), torch.from_numpy(a2.copy()))
+    for a in (a1, a2):
+        a[:, :, [-1, 0]] = 0.
+        a[:, [-1, 0], :] = 0.
+    assert np.array_equal(t1.numpy(), a1) and np.array_equal(t2.numpy(), a2)
+
+
+def test_batched_helpers_match_the_reference_formulas():
+    """Batched central_difference / laplace (navier_stokes2D.py:9-22) on CPU tensors vs the slice expressions."""
+    import torch
+    f = np.random.default_rng(1).uniform(-1, 1, (2, 9, 9))
+    t = torch.from_numpy(f)
+    want = np.zeros_like(f)
+    want[:, 1:-1, 1:-1] = (f[:, 1:-1, 2:] - f[:, 1:-1, 0:-2]) / (2 * 0.05)
+    np.testing.assert_allclose(pcg.central_difference(t, "x", 0.05).numpy(), want, rtol=1e-15, atol=0)
+    want = np.zeros_like(f)
+    want[:, 1:-1, 1:-1] = (f[:, 2:, 1:-1] - f[:, 0:-2, 1:-1]) / (2 * 0.05)
+    np.testing.assert_allclose(pcg.central_difference(t, "y", 0.05).numpy(), want, rtol=1e-15, atol=0)
+    want = np.zeros_like(f)
+    want[:, 1:-1, 1:-1] = (f[:, 1:-1, 0:-2] + f[:, 0:-2, 1:-1] - 4 * f[:, 1:-1, 1:-1] + f[:, 1:-1, 2:] + f[:, 2:, 1:-1]) / (0.05 * 0.05)
+    np.testing.assert_allclose(pcg.laplace(t, 0.05, 0.05).numpy(), want, rtol=1e-14, atol=0)
