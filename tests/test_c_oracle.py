@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import np_oracle as O
-from oracle.c_oracle import Bc1dCOracle
+from oracle.c_oracle import ArzCOracle, Bc1dCOracle, NsCOracle
 from tests.helpers import bc1d_case, make_ics
 
 
@@ -50,3 +50,61 @@ def test_c_oracle_stops_at_episode_end_and_other_grids():
             c.step(a)
             assert np.array_equal(c.u, o.u)
         assert (c.t == nt - 1).all()
+
+
+def test_c_oracle_large_grids():
+    """No size limit in the C restatement: the grids served by the CTA-per-env CUDA kernels."""
+    for env, nx in (("rd", 700), ("tr", 1500), ("rd", 4097)):
+        kw, npts, beta, nt = bc1d_case(env, nx, 2)
+        ics = make_ics(np.random.default_rng(2), 2, npts)
+        Orc = O.ReactionDiffusionOracle if env == "rd" else O.TransportOracle
+        for precision, bd in (("ref", np.float32), ("fp64", np.float64)):
+            o = Orc(2, reward=O.NormRewardSpec(nt - 1, norm=2), precision=precision, normalize=True, **kw)
+            c = Bc1dCOracle(env, precision=precision, normalize=True, **kw)
+            o.reset(ics, beta.astype(bd))
+            c.reset(ics, beta.astype(bd))
+            for k in range(2):
+                a = np.array([0.3, -0.7], dtype=np.float32)
+                o.step(a)
+                c.step(a)
+                assert np.array_equal(c.u, o.u)
+
+
+@pytest.mark.parametrize("st,cf,dx,dt", [("inlet", 1, 10, 0.25), ("outlet", 3, 10, 0.25), ("both", 2, 10, 0.25), ("both", 2, 4, 0.1), ("outlet", 1, 1, 0.025)])
+def test_c_oracle_traffic_arz_matches_numpy_oracle(st, cf, dx, dt):
+    """Plain-C Traffic-ARZ integrator == numpy oracle bit for bit (states, velocities, float time), across the
+    time-based termination and on finer grids."""
+    B = 5
+    kw = dict(T=20 * dt / 0.25, dt=dt, X=500, dx=dx)
+    o = O.TrafficARZOracle(B, simulation_type=st, control_freq=cf, **kw)
+    o.reset()
+    c = ArzCOracle(simulation_type=st, control_freq=cf, **kw)
+    c.reset(o.r, o.y, o.qs)
+    rng = np.random.default_rng(3)
+    for k in range(400 if dx == 10 else 100):
+        a = rng.uniform(0.7 * 1.2, 1.3 * 1.2, size=(B, 2 if st == "both" else 1))
+        obs = o.step(a)[0]
+        got = c.step(a)
+        assert np.array_equal(got, obs), f"step {k}"
+        assert np.array_equal(c.y, o.y) and np.array_equal(c.time, o.time_index), f"step {k}"
+
+
+@pytest.mark.parametrize("n,iters", [(21, 37), (11, 5), (33, 12), (64, 3)])
+def test_c_oracle_navier_stokes_matches_numpy_oracle(n, iters):
+    """Plain-C NavierStokes2D step == numpy oracle bit for bit (u, v, p), mixed boundary conditions."""
+    bc = {"upper": ["Controllable", "Neumann"], "lower": ["Neumann", "Dirchilet"], "left": ["Dirchilet", "Controllable"], "right": ["Neumann", "Neumann"]}
+    h = 1.0 / (n - 1)
+    P = dict(T=0.2 * (h / 0.05) ** 2, dt=1e-3 * (h / 0.05) ** 2, X=1, dx=h, Y=1, dy=h)
+    B = 3
+    rng = np.random.default_rng(n)
+    o = O.NavierStokesOracle(B, boundary_condition=bc, U_ref=np.zeros((200, n, n, 2)), action_ref=2.0 * np.ones(1000), maximum_pressure_iteration=iters, **P)
+    u0, v0, p0 = (rng.uniform(-1, 1, (B, n, n)) for _ in range(3))
+    o.reset(u0, v0, p0)
+    c = NsCOracle(P["dt"], h, h, n, n, bc, maximum_pressure_iteration=iters)
+    c.reset(u0, v0, p0)
+    for k in range(6):
+        a = rng.uniform(2, 4, B)
+        U = o.step(a)[0]
+        got = c.step(a)
+        assert np.array_equal(got, U), f"step {k}"
+        assert np.array_equal(c.p, o.p), f"step {k}: pressure"
