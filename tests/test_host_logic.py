@@ -102,3 +102,55 @@ def test_batched_helpers_match_the_reference_formulas():
     want = np.zeros_like(f)
     want[:, 1:-1, 1:-1] = (f[:, 1:-1, 0:-2] + f[:, 0:-2, 1:-1] - 4 * f[:, 1:-1, 1:-1] + f[:, 1:-1, 2:] + f[:, 2:, 1:-1]) / (0.05 * 0.05)
     np.testing.assert_allclose(pcg.laplace(t, 0.05, 0.05).numpy(), want, rtol=1e-14, atol=0)
+
+
+class _FakeVecEnv:
+    """Minimal stand-in with the vector-env surface of this package (CPU tensors) for the adapter logic tests."""
+
+    def __init__(self, n=3, autoreset=True):
+        import torch
+        self.num_envs, self.autoreset, self.t = n, autoreset, 0
+        self.single_observation_space = self.single_action_space = self.observation_space = self.action_space = None
+        self._torch = torch
+
+    def reset(self, seed=None, options=None):
+        self.t = 0
+        return self._torch.zeros(self.num_envs, 4), {}
+
+    def step(self, actions):
+        self.t += 1
+        torch = self._torch
+        obs = torch.full((self.num_envs, 4), float(self.t))
+        term = torch.tensor([self.t % 3 == 0, False, False][:self.num_envs])
+        trunc = torch.tensor([False, self.t % 2 == 0, False][:self.num_envs])
+        return obs, torch.arange(self.num_envs, dtype=torch.float64), term, trunc, {"valid": torch.ones(self.num_envs, dtype=torch.bool)}
+
+    def close(self):
+        self.closed = True
+
+
+def test_protocol_adapters_on_a_fake_env():
+    from pdecontrolgym_b200.adapters import GymnasiumVectorAdapter, SB3VecEnvAdapter, TrajectoryRecorder
+    g = GymnasiumVectorAdapter(_FakeVecEnv())
+    obs, info = g.reset(seed=1)
+    assert isinstance(obs, np.ndarray) and obs.shape == (3, 4) and info == {}
+    obs, rew, term, trunc, info = g.step(np.zeros(3))
+    assert all(isinstance(x, np.ndarray) for x in (obs, rew, term, trunc, info["valid"])) and term.dtype == bool
+    with pytest.raises(ValueError, match="autoreset=True"):
+        SB3VecEnvAdapter(_FakeVecEnv(autoreset=False))
+    s = SB3VecEnvAdapter(_FakeVecEnv())
+    assert s.reset().shape == (3, 4)
+    s.step_async(np.zeros(3))
+    s.step_wait()
+    obs, rew, dones, infos = s.step(np.zeros(3))                  # t == 2: env 1 truncated
+    assert rew.dtype == np.float32 and dones.tolist() == [False, True, False]
+    assert [i["TimeLimit.truncated"] for i in infos] == [False, True, False]
+    obs, rew, dones, infos = s.step(np.zeros(3))                  # t == 3: env 0 terminated (not a time-limit truncation)
+    assert dones.tolist() == [True, False, False] and not infos[0]["TimeLimit.truncated"]
+    assert s.env_is_wrapped(object) == [False] * 3 and s.seed(7) == [7, 7, 7]
+    rec = TrajectoryRecorder(_FakeVecEnv(), max_steps=2)
+    rec.reset()
+    for _ in range(4):                                            # only the first max_steps steps are kept
+        rec.step(None)
+    h = rec.history()
+    assert h.shape == (3, 3, 4) and h[:, 0, 0].tolist() == [0.0, 1.0, 2.0]
