@@ -108,3 +108,59 @@ def test_c_oracle_navier_stokes_matches_numpy_oracle(n, iters):
         got = c.step(a)
         assert np.array_equal(got, U), f"step {k}"
         assert np.array_equal(c.p, o.p), f"step {k}: pressure"
+
+
+def test_c_oracle_property_random_arz_and_ns_configurations():
+    """Hypothesis: random physical parameters, grids, control frequencies and boundary-condition tables -- the C and
+    numpy restatements stay bit-identical (NaN / inf patterns of unstable draws included)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+    @given(sim=st.sampled_from(["inlet", "outlet", "both"]), cf=st.integers(1, 4), M=st.integers(5, 140),
+           vm=st.floats(10, 60), rm=st.floats(0.1, 0.3), tau=st.floats(5, 120), cfl=st.floats(0.1, 1.2), seed=st.integers(0, 10 ** 6))
+    def arz(sim, cf, M, vm, rm, tau, cfl, seed):
+        X = 500.0
+        dx = X / (M - 1)
+        if len(np.arange(0, X + dx, dx)) != M:
+            return
+        dt = cfl * dx / vm
+        ro_s = 0.75 * rm
+        kw = dict(T=30 * dt, dt=dt, X=X, dx=dx)
+        with np.errstate(all="ignore"):
+            o = O.TrafficARZOracle(3, simulation_type=sim, control_freq=cf, v_max=vm, ro_max=rm, tau=tau, ro_steady=ro_s,
+                                   v_steady=vm * (1 - ro_s / rm), **kw)
+            o.reset()
+            c = ArzCOracle(simulation_type=sim, control_freq=cf, v_max=vm, ro_max=rm, tau=tau, **kw)
+            c.reset(o.r, o.y, o.qs)
+            rng = np.random.default_rng(seed)
+            for k in range(12):
+                a = o.qs[:, None] * rng.uniform(0.6, 1.4, size=(3, 2 if sim == "both" else 1))
+                obs = o.step(a)[0]
+                got = c.step(a)
+                assert np.array_equal(got, obs, equal_nan=True) and np.array_equal(c.y, o.y, equal_nan=True)
+                assert np.array_equal(c.time, o.time_index)
+
+    @settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+    @given(n=st.integers(4, 40), iters=st.integers(0, 12), nu=st.floats(0.01, 0.5), rho=st.floats(0.5, 2.0),
+           bcs=st.lists(st.sampled_from(["Dirchilet", "Neumann", "Controllable"]), min_size=8, max_size=8), seed=st.integers(0, 10 ** 6))
+    def ns(n, iters, nu, rho, bcs, seed):
+        bc = {side: [bcs[2 * i], bcs[2 * i + 1]] for i, side in enumerate(("upper", "lower", "left", "right"))}
+        h = 1.0 / (n - 1)
+        dt = 0.2 * (0.5 * h * h / nu)
+        P = dict(T=50 * dt, dt=dt, X=1, dx=h, Y=1, dy=h)
+        rng = np.random.default_rng(seed)
+        o = O.NavierStokesOracle(2, boundary_condition=bc, U_ref=np.zeros((60, n, n, 2)), action_ref=np.ones(100),
+                                 maximum_pressure_iteration=iters, viscosity=nu, density=rho, **P)
+        u0, v0, p0 = (rng.uniform(-2, 2, (2, n, n)) for _ in range(3))
+        o.reset(u0, v0, p0)
+        c = NsCOracle(dt, h, h, n, n, bc, viscosity=nu, density=rho, maximum_pressure_iteration=iters)
+        c.reset(u0, v0, p0)
+        for k in range(4):
+            a = rng.uniform(-3, 3, 2)
+            with np.errstate(all="ignore"):
+                U = o.step(a)[0]
+            assert np.array_equal(c.step(a), U, equal_nan=True) and np.array_equal(c.p, o.p, equal_nan=True)
+
+    arz()
+    ns()
