@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PDECG_ABI_VERSION 1
+#define PDECG_ABI_VERSION 2
 
 typedef void* pdecg_stream_t; /* cudaStream_t */
 
@@ -107,6 +107,10 @@ typedef struct {
                                 history the reference rewards index into                    */
     void* obs_copy;          /* optional [n_envs, npts] S: the step / reset kernels also store the new state here,
                                 so a caller gets a private full-state observation without a separate device copy */
+    int32_t obs_copy_f32;    /* non-zero: obs_copy (and pdecg_bc1d_autoreset::final_obs) hold float32 whatever S is --
+                                the dtype of the reference's observation_space (base_env_1d.py:33-35); each element
+                                is the state value rounded once to float32 (numpy `row.astype(np.float32)`).  The
+                                resident state keeps its precision.                                             */
 } pdecg_bc1d_buffers;
 
 /* Number of doubles of reward carry per env for this configuration. */
@@ -149,16 +153,25 @@ typedef struct pdecg_bc1d_autoreset {
     uint64_t seed;
     int64_t env_id_offset;
     int32_t* episode;        /* random != 0: [n_envs] episode counters                                           */
+    void* final_obs;         /* optional: the observation of the step that ENDED the episode, written for restarted envs
+                                only (rows of the other envs are left alone) before their row is re-initialised --
+                                what SB3 calls infos[i]["terminal_observation"] and gymnasium "final_observation"
+                                (examples/transportPDE/transport1Dppo.py:88-90 bootstraps from it on truncation).
+                                [n_envs, npts] for FULL sensing, [n_envs] otherwise; S, or float32 if obs_copy_f32 */
 } pdecg_bc1d_autoreset;
 int pdecg_bc1d_step_autoreset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
                               const pdecg_bc1d_autoreset* autoreset, pdecg_stream_t stream);
 
 /* Same step, but `action_host` ([n_envs], cfg.action_dtype) and the outputs are HOST buffers:
- * H2D(actions) -> kernel -> D2H(obs, reward, flags), all on `stream`, then stream-synchronised.
- * obs_host is [n_envs, npts] S for FULL sensing, [n_envs] S otherwise; any output pointer may be
- * NULL to skip that copy.  Device buffers in `buf` are still the caller's (buf->action is the
+ * H2D(actions) -> kernel -> D2H(obs, reward, flags), then synchronised.  The batch is cut into chunks that
+ * rotate over four library-owned streams ordered after `stream`, so the copy-out of one chunk overlaps the
+ * kernels of the next ones.  obs_host is [n_envs, npts] for FULL sensing, [n_envs] S otherwise; any output
+ * pointer may be NULL to skip that copy.  For FULL sensing the observation is copied out of buf->obs_copy when the
+ * caller provides that device buffer (dtype S, or float32 with obs_copy_f32 -- half the PCIe bytes of a float64
+ * state), else straight out of the state.  Device buffers in `buf` are still the caller's (buf->action is the
  * device staging buffer for the actions).  `autoreset` (may be NULL) fuses the same-step auto-reset as in
- * pdecg_bc1d_step_autoreset; the observation copied out for a restarted env is then its new initial row. */
+ * pdecg_bc1d_step_autoreset; the observation copied out for a restarted env is then its new initial row
+ * (autoreset->final_obs, a DEVICE buffer, still receives the terminal one). */
 int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffers* buf,
                          const void* action_host, void* obs_host, double* reward_host,
                          uint8_t* terminated_host, uint8_t* truncated_host,
@@ -218,6 +231,10 @@ typedef struct {
     uint8_t* terminated;    /* [n_envs]                                                                 */
     uint8_t* truncated;     /* [n_envs]                                                                 */
     uint8_t* valid;         /* [n_envs] 0 where the reference's step() would have returned None (:135)  */
+    double* final_obs;      /* optional, pdecg_bt_step_autoreset only: [n_envs, nx] terminal observation (the state row of
+                               the day that ended the episode) of the envs that restart; other rows are left alone  */
+    const uint8_t* mask;    /* optional, PDECG_BT_WRAP_RESET only: [n_envs], run the wrapper reset (Growth stage, consecutive
+                               <- 0) only for envs whose byte is non-zero -- TherapyWrapper.reset of a subset of a batch */
 } pdecg_bt_buffers;
 
 /* BrainTumor1D.reset (:347-384): u <- init ([n_envs or 1, nx] float64), stage <- Growth, counters <- 0;
@@ -248,7 +265,10 @@ int pdecg_bt_step_host(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, con
 typedef enum { PDECG_ARZ_INLET = 0, PDECG_ARZ_OUTLET = 1, PDECG_ARZ_BOTH = 2, PDECG_ARZ_OUTLET_TRAIN = 3 } pdecg_arz_type;
 /* Per-env float64 values, [n_envs, PDECG_ARZ_NF64]: the float time (traffic_arz_env.py:148 -- `time_index`
  * advances by dt per STEP and is compared with T/dt, reference quirk Q9) and the steady state. */
-enum { PDECG_ARZ_F_TIME = 0, PDECG_ARZ_F_RS = 1, PDECG_ARZ_F_VS = 2, PDECG_ARZ_F_QS = 3, PDECG_ARZ_NF64 = 4 };
+enum { PDECG_ARZ_F_TIME = 0, PDECG_ARZ_F_RS = 1, PDECG_ARZ_F_VS = 2, PDECG_ARZ_F_QS = 3,
+       /* action_space.low / .high: built ONCE in __init__ from the constructor's qs (:97-100) and never updated by
+        * reset(), although 'outlet-train' re-draws rs / qs there (:243-247) -- step() keeps clipping with these */
+       PDECG_ARZ_F_ACT_LO = 4, PDECG_ARZ_F_ACT_HI = 5, PDECG_ARZ_NF64 = 6 };
 
 /* Constructor kwargs of TrafficPDE1D (traffic_arz_env.py:23-100); the dt/dx/tau combinations are
  * passed as the Python floats the reference forms (:202-222) so the kernel multiplies by the same bits. */
@@ -278,6 +298,8 @@ typedef struct {
     double* reward;          /* [n_envs]                                                                */
     uint8_t* terminated;     /* [n_envs]                                                                */
     uint8_t* truncated;      /* [n_envs]                                                                */
+    double* final_obs;       /* optional, pdecg_arz_step_autoreset only: [n_envs, 2*M] terminal observation of the envs
+                                that restart; other rows are left alone                                          */
 } pdecg_arz_buffers;
 
 /* TrafficPDE1D.reset (:237-267): rho <- rs*profile, y, v from the fixed sinusoidal initial condition.
@@ -337,6 +359,8 @@ typedef struct {
     uint8_t* terminated;     /* [n_envs]                                                                    */
     uint8_t* truncated;      /* [n_envs] always 0 (:155)                                                    */
     uint8_t* valid;          /* [n_envs] 0 where the reference would raise IndexError (step past nt-1)      */
+    double* final_obs;       /* optional, pdecg_ns_step_autoreset only: [n_envs, ny, nx, 2] terminal observation U[nt-1]
+                                of the envs that restart; other rows are left alone                                 */
 } pdecg_ns_buffers;
 
 /* NavierStokes2D.reset (:171-194): u, v, p <- init_* ([n_envs or 1, ny, nx]); time_index <- 0; obs <- U[0]. */

@@ -281,7 +281,7 @@ class TrafficARZOracle:
     Python's global `random` for the '*-train' types, traffic_arz_env.py:66-70,251-256)."""
 
     def __init__(self, B, T, dt, X, dx, simulation_type="inlet", v_steady=10, ro_steady=0.12,
-                 v_max=40, ro_max=0.16, tau=60, limit_pde_state_size=False, control_freq=1):
+                 v_max=40, ro_max=0.16, tau=60, limit_pde_state_size=False, control_freq=1, rs_init=None):
         assert isinstance(control_freq, int) and control_freq >= 1
         if simulation_type not in ("inlet", "outlet", "both", "outlet-train"):
             raise ValueError("Invalid simulation type")     # 'inlet-train' crashes in the reference
@@ -298,7 +298,8 @@ class TrafficARZOracle:
                 raise ValueError("The steady state velocity and density do not satisfy the equilibrium condition.")
             self.set_steady(np.full(B, float(ro_steady)), vs=np.full(B, float(v_steady)))
         else:
-            self.set_steady(np.full(B, 0.12))
+            # the constructor's own draw (:66-70) fixes the action bounds for the env's lifetime; pass `rs_init`
+            self.set_steady(np.full(B, 0.12) if rs_init is None else np.broadcast_to(np.asarray(rs_init, dtype=np.float64), (B,)).copy())
         self.x = np.arange(0, X + dx, dx)            # traffic_arz_env.py:74
         self.M = len(self.x)
         self.L = X
@@ -321,7 +322,10 @@ class TrafficARZOracle:
             self.qs = self.rs * self.vs               # :70,256
         else:
             self.qs = self.vs * self.rs               # :63
-        self.act_low, self.act_high = self.qs * 0.8, 1.2 * self.qs   # :98-100
+        # :97-100 -- action_space is built ONCE in __init__ from the constructor's qs; reset() re-draws rs / qs for
+        # 'outlet-train' (:251-256) but never refreshes the bounds step() clips with (:161,166)
+        if not hasattr(self, "act_low"):
+            self.act_low, self.act_high = self.qs * 0.8, 1.2 * self.qs
 
     def reset(self, rs=None):
         """traffic_arz_env.py:237-267 (does NOT reset time_index -- that is terminate()'s side effect)."""

@@ -7,9 +7,12 @@ This module injects the stubs in `oracle/_stubs` and pre-registers empty package
 the env / reward *sub-modules* are imported straight from `/root/reference` without touching
 the broken `__init__` files.  No reference source is copied into this repository.
 
-`/root/reference` only exists in the build container.  It is used
-  (1) by `tests/golden/gen_golden.py` to produce the committed golden vectors, and
-  (2) by `tests/test_oracle_vs_reference.py`, which is skipped when the tree is absent.
+Where the reference comes from (first hit wins): `$PDECG_REFERENCE_ROOT`, `/root/reference` (build container
+only), `oracle/_ref/` -- the verbatim, git-ignored copy staged by `oracle/make_ref.py` at build() time, which
+travels to the GPU box with the snapshot.  It is used
+  (1) by `tests/golden/gen_golden.py` to produce the committed golden vectors,
+  (2) by `tests/test_oracle_vs_reference.py`, which is skipped when no tree is found, and
+  (3) by `bench.py` as the CPU arm (`--impl reference`, `cpu_baseline.kind == "reference"`).
 Nothing under `pdecontrolgym_b200/` may import this file.
 """
 import importlib
@@ -17,8 +20,24 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PDECG_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "_stubs")
+
+
+def _find_root():
+    cands = [os.environ.get("PDECG_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "pde_control_gym", "src")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
+
+
+def reference_kind() -> str:
+    """'live' (the read-only checkout in the build container) or 'staged' (oracle/_ref copy)."""
+    return "staged" if os.path.abspath(REFERENCE_ROOT) == os.path.join(_HERE, "_ref") else "live"
 
 
 def reference_available() -> bool:

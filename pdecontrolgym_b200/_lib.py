@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PDECG_LIB", os.path.join(_HERE, "lib", "libpdecg.so"))   # override: A/B testing of builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 PREC = {"ref": 0, "fp64": 1, "fp32": 2}
 F32, F64 = 0, 1
@@ -43,7 +43,7 @@ class Bc1dBuffers(C.Structure):
         ("n_envs", C.c_int64), ("u", C.c_void_p), ("beta", C.c_void_p), ("beta_env_stride", C.c_int64),
         ("action", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
         ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("time_index", C.c_void_p),
-        ("carry", C.c_void_p), ("obs_copy", C.c_void_p),
+        ("carry", C.c_void_p), ("obs_copy", C.c_void_p), ("obs_copy_f32", C.c_int32),
     ]
 
 
@@ -51,7 +51,7 @@ class Bc1dAutoReset(C.Structure):
     _fields_ = [
         ("init", C.c_void_p), ("init_dtype", C.c_int32), ("random", C.c_int32), ("init_env_stride", C.c_int64),
         ("lo", C.c_double), ("hi", C.c_double), ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
-        ("episode", C.c_void_p),
+        ("episode", C.c_void_p), ("final_obs", C.c_void_p),
     ]
 
 
@@ -70,6 +70,7 @@ class BtBuffers(C.Structure):
         ("n_envs", C.c_int64), ("u", C.c_void_p), ("obs", C.c_void_p), ("x_scale", C.c_void_p),
         ("action", C.c_void_p), ("ienv", C.c_void_p), ("fenv", C.c_void_p), ("reward", C.c_void_p),
         ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("valid", C.c_void_p),
+        ("final_obs", C.c_void_p), ("mask", C.c_void_p),
     ]
 
 
@@ -86,6 +87,7 @@ class ArzBuffers(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int64), ("ry", C.c_void_p), ("obs", C.c_void_p), ("action", C.c_void_p),
         ("fenv", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
+        ("final_obs", C.c_void_p),
     ]
 
 
@@ -103,6 +105,7 @@ class NsBuffers(C.Structure):
         ("n_envs", C.c_int64), ("u", C.c_void_p), ("v", C.c_void_p), ("p", C.c_void_p), ("obs", C.c_void_p),
         ("action", C.c_void_p), ("u_ref", C.c_void_p), ("action_ref", C.c_void_p), ("time_index", C.c_void_p),
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("valid", C.c_void_p),
+        ("final_obs", C.c_void_p),
     ]
 
 

@@ -124,6 +124,7 @@ extern "C" int pdecg_bc1d_step_autoreset(const pdecg_bc1d_cfg* cfg, const pdecg_
     a.ar.init = ar->init;
     a.ar.init_stride = ar->random ? 0 : ar->init_env_stride;
     a.ar.rnd = ar->random ? RandomIc{1, ar->lo, ar->hi, ar->seed, ar->env_id_offset, ar->episode} : RandomIc{};
+    a.ar.final_obs = ar->final_obs;
     return launch_mode(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -164,13 +165,14 @@ extern "C" int pdecg_bc1d_reset_random(const pdecg_bc1d_cfg* cfg, const pdecg_bc
     return reset_impl(cfg, buf, profile, profile_dtype, 0, mask, rnd, stream);
 }
 
-// Host-buffer step, pipelined: the batch is cut into chunks that alternate between two library-owned
-// streams, so the D2H copy of chunk c overlaps the kernel of chunk c+1 (the observation copy-out is the
+// Host-buffer step, pipelined: the batch is cut into chunks that rotate over four library-owned streams, so
+// the D2H copy of chunk c overlaps the kernels of the chunks behind it (the observation copy-out is the
 // PCIe-bound part of an end-to-end step with full-state sensing).
 namespace {
+constexpr int kPipeStreams = 4;
 struct HostPipe {
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
+    cudaStream_t s[kPipeStreams] = {};
+    cudaEvent_t start = nullptr, done[kPipeStreams] = {};
     bool ready = false;
 };
 constexpr int kMaxDevices = 64;
@@ -183,7 +185,7 @@ int ensure_pipe(HostPipe** out) {
     if (dev < 0 || dev >= kMaxDevices) return fail(PDECG_ERR_UNSUPPORTED, "device index %d out of range", dev);
     HostPipe& p = g_pipes[dev];
     if (!p.ready) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kPipeStreams; ++i) {
             if ((e = cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
             if ((e = cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
         }
@@ -213,19 +215,22 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
     const size_t ssz = cfg->precision == PDECG_PREC_FP64 ? 8 : 4;
     const size_t bsz = (cfg->precision == PDECG_PREC_REF) ? (cfg->beta_dtype == PDECG_F64 ? 8 : 4) : ssz;
     const bool full = cfg->sensing_loc == PDECG_SENSE_FULL;
-    const size_t obs_row = full ? static_cast<size_t>(a.npts) * ssz : ssz;
+    // FULL sensing: the observation leaves through obs_copy when the caller gave one (possibly float32), else from the state
+    const bool via_copy = full && buf->obs_copy != nullptr;
+    const size_t osz = (via_copy && buf->obs_copy_f32) ? 4 : ssz;
+    const size_t obs_row = full ? static_cast<size_t>(a.npts) * osz : ssz;
     // chunks of >= 4096 envs, at most 8 of them
     int nchunk = static_cast<int>(n / 4096);
     nchunk = nchunk < 1 ? 1 : (nchunk > 8 ? 8 : nchunk);
     const int64_t per = ((n + nchunk - 1) / nchunk + 3) / 4 * 4;
     cudaError_t e = cudaEventRecord(g_pipe.start, user);      // order after whatever the caller queued
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
-    for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(g_pipe.s[i], g_pipe.start, 0);
+    for (int i = 0; i < kPipeStreams; ++i) cudaStreamWaitEvent(g_pipe.s[i], g_pipe.start, 0);
     MapEnvsScope map_scope(n);                                // every chunk uses the lane mapping of the whole batch
     auto off = [](const void* p, size_t bytes) { return p ? static_cast<const char*>(p) + bytes : nullptr; };
     for (int c = 0; c * per < n; ++c) {
         const int64_t lo = c * per, cnt = (lo + per <= n) ? per : n - lo;
-        cudaStream_t st = g_pipe.s[c & 1];
+        cudaStream_t st = g_pipe.s[c % kPipeStreams];
         pdecg_bc1d_buffers b = *buf;
         b.n_envs = cnt;
         b.u = const_cast<char*>(off(buf->u, lo * a.npts * ssz));
@@ -237,7 +242,7 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
         b.truncated = buf->truncated + lo;
         b.time_index = buf->time_index + lo;
         b.carry = buf->carry + lo * a.carry_len;
-        b.obs_copy = nullptr;                                  // the host path copies straight from the state
+        b.obs_copy = via_copy ? const_cast<char*>(off(buf->obs_copy, lo * obs_row)) : nullptr;
         if ((e = cudaMemcpyAsync(const_cast<void*>(b.action), off(action_host, lo * asz), cnt * asz, cudaMemcpyHostToDevice, st)) != cudaSuccess)
             return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
         if (autoreset) {
@@ -246,13 +251,14 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
             if (!ar.random) ar.init = off(ar.init, lo * ar.init_env_stride * isz);
             ar.env_id_offset += lo;
             if (ar.episode) ar.episode += lo;
+            if (ar.final_obs) ar.final_obs = const_cast<char*>(off(ar.final_obs, lo * (full ? a.npts : 1) * ((buf->obs_copy_f32 && ssz == 8) ? 4 : ssz)));
             rc = pdecg_bc1d_step_autoreset(cfg, &b, &ar, st);
         } else {
             rc = pdecg_bc1d_step(cfg, &b, st);
         }
         if (rc != PDECG_OK) return rc;
         if (obs_host) {
-            const void* src = full ? static_cast<const void*>(b.u) : static_cast<const void*>(b.obs);
+            const void* src = via_copy ? static_cast<const void*>(b.obs_copy) : (full ? static_cast<const void*>(b.u) : static_cast<const void*>(b.obs));
             if ((e = cudaMemcpyAsync(static_cast<char*>(obs_host) + lo * obs_row, src, cnt * obs_row, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
                 return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
         }
@@ -260,7 +266,7 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
         if (terminated_host && (e = cudaMemcpyAsync(terminated_host + lo, b.terminated, cnt, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
         if (truncated_host && (e = cudaMemcpyAsync(truncated_host + lo, b.truncated, cnt, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
     }
-    for (int i = 0; i < 2; ++i) {                              // the caller's stream continues after both pipes
+    for (int i = 0; i < kPipeStreams; ++i) {                   // the caller's stream continues after every pipe
         cudaEventRecord(g_pipe.done[i], g_pipe.s[i]);
         cudaStreamWaitEvent(user, g_pipe.done[i], 0);
     }

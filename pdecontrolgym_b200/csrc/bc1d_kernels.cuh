@@ -35,6 +35,7 @@ struct AutoReset {         // pdecg_bc1d_step_autoreset: finished envs restart i
     const void* init;
     int64_t init_stride;
     RandomIc rnd;
+    void* final_obs;       // optional: terminal observation of the envs that restart (pdecg_bc1d_autoreset::final_obs)
 };
 
 struct Bc1dArgs {
@@ -316,7 +317,8 @@ __device__ __forceinline__ void reset_env(const Bc1dArgs& a, const I* __restrict
     };
     double ss = 0.0;
     S last = S(0), first = S(0), second = S(0), blast = S(0);
-    S* crow = a.buf.obs_copy ? static_cast<S*>(a.buf.obs_copy) + env * npts : nullptr;
+    void* const crow = a.buf.obs_copy;
+    const bool c32 = a.buf.obs_copy_f32 != 0;
     // ||u_0||^2 in the summation order of a 32-lane warp (32 strided partial sums, xor tree 16-8-4-2-1) whatever
     // LPE is: a half-warp segment carries two of the partial sums per lane, so both reset paths agree bit for bit
     static_assert(LPE == 32 || LPE == 16, "reset_env: 32 or 16 lanes per env");
@@ -326,7 +328,7 @@ __device__ __forceinline__ void reset_env(const Bc1dArgs& a, const I* __restrict
         for (int j = lane + r * LPE; j < npts; j += 32) {
             S v = ic(j);
             urow[j] = v;
-            if (crow) crow[j] = v;
+            if (crow) put_obs<S>(crow, c32, env * npts + j, v);
             double dv = static_cast<double>(v);
             part += dv * dv;
         }
@@ -472,7 +474,9 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
         double cm = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) cm = fmax(cm, fabs(static_cast<double>(I.coef[k])));
-        cm = seg_max<LPE>(cm, mask);
+        // lock-stepped half-warp pairs (`wide`) must take identical spans / fused-or-strict decisions: one (conservative)
+        // bound for both envs, also when their per-env coefficient rows put rho in different binades
+        cm = I.wide ? seg_max<32>(cm, kFull) : seg_max<LPE>(cm, mask);
         // upper bound of log2(rho) from the exponent field (no log2() call): rho in [2^e, 2^(e+1)) -> e + 1
         const double rho = 1.0 + 4.0 * fabs(static_cast<double>(I.Fs)) + cm;
         fuse_log2_rho = static_cast<double>(static_cast<int>((static_cast<unsigned>(__double2hiint(rho)) >> 20) & 0x7ffu) - 1022);
@@ -569,8 +573,13 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
         if constexpr (VAR == kVarFast) I.fix_boundaries();   // frozen slots may have absorbed a NaN/inf neighbour
         store_row_chunk<S, K, LPE>(I.u, urow, npts, sm, lane, mask);
     }
-    if (a.buf.obs_copy != nullptr)                           // private observation for the caller (no separate device copy)
-        store_row_chunk<S, K, LPE>(I.u, static_cast<S*>(a.buf.obs_copy) + env * npts, npts, sm, lane, mask);
+    auto store_obs_row = [&](void* base) {                   // [n_envs, npts] in the state dtype, or float32 on request
+        if (sizeof(S) == 8 && a.buf.obs_copy_f32)
+            store_row_chunk_as<float, S, K, LPE>(I.u, static_cast<float*>(base) + env * npts, npts, sm, lane, mask);
+        else
+            store_row_chunk<S, K, LPE>(I.u, static_cast<S*>(base) + env * npts, npts, sm, lane, mask);
+    };
+    if (a.buf.obs_copy != nullptr) store_obs_row(a.buf.obs_copy);   // private observation for the caller (no separate device copy)
     S (&u)[K] = I.u;
 
     const double sumsq = chunk_sumsq<S, K, LPE>(u, j0, npts, mask);
@@ -620,8 +629,8 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
     }
 
     // ---- sensing (hyperbolic.py:69-120, parabolic.py:69-118) ------------------------------------
+    S o = S(0);
     if (cfg.sensing_loc != PDECG_SENSE_FULL) {
-        S o;
         if (cfg.sensing_loc == PDECG_SENSE_COLLOCATED) {
             const S ub = row_value<S, K, LPE>(u, npts - 1, mask);
             if (cfg.control_type == PDECG_CONTROL_NEUMANN) o = ub;
@@ -641,7 +650,15 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
         a.buf.terminated[env] = terminated ? 1 : 0;
         a.buf.truncated[env] = truncated ? 1 : 0;
     }
-    if (a.ar.enabled && (terminated || truncated)) autoreset_env<S, LPE>(a, env, lane, mask);
+    if (a.ar.enabled && (terminated || truncated)) {
+        // the terminal observation survives the restart in the caller's final_obs buffer (what SB3 / gymnasium call
+        // `terminal_observation` / `final_observation`; transport1Dppo.py:88-90 bootstraps from it on truncation)
+        if (a.ar.final_obs != nullptr) {
+            if (cfg.sensing_loc == PDECG_SENSE_FULL) store_obs_row(a.ar.final_obs);
+            else if (lane == 0) put_obs<S>(a.ar.final_obs, a.buf.obs_copy_f32 != 0, env, o);
+        }
+        autoreset_env<S, LPE>(a, env, lane, mask);
+    }
 }
 
 // Lanes per env, points per lane and kernel variant for this configuration (uniform over the batch).

@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(kCtaMaxThreads, 1) bc1d_step_cta_kernel(const 
     if (want_diff) diff_norm = cta_norm<S>(cur, nxt, npts, cfg.norm_ord, red);   // `nxt` still holds row t-1
 
     // ---- write back state ------------------------------------------------------------------------
-    S* crow = a.buf.obs_copy ? static_cast<S*>(a.buf.obs_copy) + env * npts : nullptr;
+    const bool c32 = a.buf.obs_copy_f32 != 0;
     for (int j = tid; j < npts; j += nth) {
         const S v = cur[j];
         if (nsub > 0) urow[j] = v;
-        if (crow) crow[j] = v;
+        if (a.buf.obs_copy) put_obs<S>(a.buf.obs_copy, c32, env * npts + j, v);
     }
     const double sumsq = cta_sumsq<S>(cur, npts, red);
     const S norm2 = static_cast<S>(sqrt(sumsq));               // np.linalg.norm(u[t]) in the state dtype
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(kCtaMaxThreads, 1) bc1d_step_cta_kernel(const 
                 else o = cur[0];
             }
             static_cast<S*>(a.buf.obs)[env] = o;
+            if (a.ar.enabled && a.ar.final_obs != nullptr && (terminated || truncated)) put_obs<S>(a.ar.final_obs, c32, env, o);
         }
         carry[0] = bsum;
         a.buf.time_index[env] = t_end;
@@ -237,6 +238,8 @@ __global__ void __launch_bounds__(kCtaMaxThreads, 1) bc1d_step_cta_kernel(const 
         a.buf.truncated[env] = truncated ? 1 : 0;
     }
     if (a.ar.enabled && (terminated || truncated)) {
+        if (a.ar.final_obs != nullptr && cfg.sensing_loc == PDECG_SENSE_FULL)     // terminal observation for the caller
+            for (int j = tid; j < npts; j += nth) put_obs<S>(a.ar.final_obs, c32, env * npts + j, cur[j]);
         __syncthreads();                               // the step's own row / carry stores come first
         if (tid < 32) autoreset_env<S, 32>(a, env, tid, kFull);   // warp 0 restarts the env exactly like the reset kernel
     }
@@ -435,13 +438,13 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
     }
 
     // ---- write back state ------------------------------------------------------------------------
-    S* crow = a.buf.obs_copy ? static_cast<S*>(a.buf.obs_copy) + env * npts : nullptr;
+    const bool c32 = a.buf.obs_copy_f32 != 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = j0 + k;
         if (j < npts) {
             if (nsub > 0) urow[j] = u[k];
-            if (crow) crow[j] = u[k];
+            if (a.buf.obs_copy) put_obs<S>(a.buf.obs_copy, c32, env * npts + j, u[k]);
             if (j == 0) sens[0] = u[k];
             if (j == 1) sens[1] = u[k];
             if (j == npts - 2) sens[2] = u[k];
@@ -504,6 +507,7 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
                 else o = sens[0];
             }
             static_cast<S*>(a.buf.obs)[env] = o;
+            if (a.ar.enabled && a.ar.final_obs != nullptr && (terminated || truncated)) put_obs<S>(a.ar.final_obs, c32, env, o);
         }
         carry[0] = bsum;
         a.buf.time_index[env] = t_end;
@@ -512,6 +516,11 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
         a.buf.truncated[env] = truncated ? 1 : 0;
     }
     if (a.ar.enabled && (terminated || truncated)) {
+        if (a.ar.final_obs != nullptr && cfg.sensing_loc == PDECG_SENSE_FULL) {   // terminal observation for the caller
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (j0 + k < npts) put_obs<S>(a.ar.final_obs, c32, env * npts + j0 + k, u[k]);
+        }
         __syncthreads();                               // the step's own row / carry stores come first
         if (tid < 32) autoreset_env<S, 32>(a, env, tid, kFull);   // warp 0 restarts the env exactly like the reset kernel
     }

@@ -270,6 +270,7 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
             else bt_fd_lean<K, false, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, rin, treat_r, a.buf.x_scale);
         }
     } else {
+        e.last_dose = 0.0;                                           // dosage_vs_time[t] stays 0 outside Therapy (:56,160)
         if constexpr (XSREG) {
             if (dv.dx2_one) bt_fd<K, true, false, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, 0.0, 0.0, xs, a.buf.x_scale);
             else bt_fd<K, false, false, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, 0.0, 0.0, xs, a.buf.x_scale);
@@ -384,7 +385,12 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
             term = true;
         }
     } else if (a.mode == PDECG_BT_WRAP_RESET) {
-        // TherapyWrapper.reset (:408-427)
+        // TherapyWrapper.reset (:408-427); with a mask only the selected envs take part (the others keep their
+        // consecutive-treatment-day counter and everything else: they are mid-therapy patients of the same batch)
+        if (a.buf.mask != nullptr && a.buf.mask[env] == 0) {
+            if (a.buf.obs != nullptr) store_row_chunk<double, K>(u, a.buf.obs + env * nx, nx, sm, lane);
+            return;
+        }
         e.consecutive = 0;
         while (e.stage == PDECG_BT_GROWTH && e.t < last) {
             bt_day<K, MULTI>(a, dv, xs, e, u, lane, j0, 0.0, reward, term, trunc);
@@ -460,7 +466,11 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
         if (a.buf.valid) a.buf.valid[env] = valid ? 1 : 0;
     }
     if constexpr (!MULTI) {
-        if (a.ar_init != nullptr && (term || trunc)) bt_autoreset_env(a, env, lane);
+        if (a.ar_init != nullptr && (term || trunc)) {
+            if (a.buf.final_obs != nullptr)          // terminal observation for the caller, before the row is re-initialised
+                store_row_chunk<double, K>(u, a.buf.final_obs + env * nx, nx, sm, lane);
+            bt_autoreset_env(a, env, lane);
+        }
     }
 }
 

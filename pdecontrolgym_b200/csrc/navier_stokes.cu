@@ -186,7 +186,13 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
             a.buf.truncated[env] = 0;
             a.buf.reward[env] = 0.0;
         }
-        if (a.ar_u != nullptr) ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
+        if (a.ar_u != nullptr) {
+            if (a.buf.final_obs != nullptr) {        // terminal observation = the (unchanged) current U[t]
+                for (int q = tid; q < 2 * npt; q += nth) a.buf.final_obs[env * npt * 2 + q] = a.buf.obs[env * npt * 2 + q];
+                __syncthreads();
+            }
+            ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
+        }
         return;
     }
     double* gu = a.buf.u + env * npt;
@@ -275,6 +281,10 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
         if (a.buf.valid) a.buf.valid[env] = 1;
     }
     if (a.ar_u != nullptr && t1 >= cfg.nt - 1) {          // same-step auto-reset (block-uniform condition)
+        if (a.buf.final_obs != nullptr) {                 // terminal observation U[nt-1] for the caller
+            double* fobs = a.buf.final_obs + env * npt * 2;
+            for (int q = tid; q < npt; q += nth) { fobs[2 * q] = su[q]; fobs[2 * q + 1] = sv[q]; }
+        }
         __syncthreads();                                  // the step's own field / observation stores come first
         ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
     }
@@ -320,7 +330,13 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
             a.buf.truncated[env] = 0;
             a.buf.reward[env] = 0.0;
         }
-        if (a.ar_u != nullptr) ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, 32, true);
+        if (a.ar_u != nullptr) {
+            if (a.buf.final_obs != nullptr) {        // terminal observation = the (unchanged) current U[t]
+                for (int q = lane; q < 2 * NPT; q += 32) a.buf.final_obs[env * NPT * 2 + q] = a.buf.obs[env * NPT * 2 + q];
+                __syncwarp();
+            }
+            ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, 32, true);
+        }
         return;
     }
     const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
@@ -506,6 +522,10 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
         if (a.buf.valid) a.buf.valid[env] = 1;
     }
     if (a.ar_u != nullptr && t1 >= cfg.nt - 1) {          // same-step auto-reset (warp-uniform condition)
+        if (a.buf.final_obs != nullptr) {                 // terminal observation U[nt-1] for the caller
+            double2* fobs = reinterpret_cast<double2*>(a.buf.final_obs + env * NPT * 2);
+            for (int q = lane; q < NPT; q += 32) fobs[q] = make_double2(f2[q], f3[q]);
+        }
         __syncwarp();                                     // the step's own field / observation stores come first
         ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, 32, true);
     }

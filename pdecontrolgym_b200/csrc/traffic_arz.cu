@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
     const double rs = __shfl_sync(kFull, fv, PDECG_ARZ_F_RS);
     const double vs = __shfl_sync(kFull, fv, PDECG_ARZ_F_VS);
     const double qs = __shfl_sync(kFull, fv, PDECG_ARZ_F_QS);
+    // action_space.low / .high as built in __init__ (:97-100): NOT refreshed when 'outlet-train' re-draws qs in reset()
+    const double lo = __shfl_sync(kFull, fv, PDECG_ARZ_F_ACT_LO), hi = __shfl_sync(kFull, fv, PDECG_ARZ_F_ACT_HI);
 
     arz_load_finish<K>(r, r_raw, sm, lane);
     arz_load_finish<K>(y, y_raw, sm, lane);
@@ -116,7 +118,6 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
 
     // :148-170 -- float time advances once per step; actions clipped to the action space
     time = D::add(time, cfg.dt);
-    const double lo = D::mul(qs, 0.8), hi = D::mul(1.2, qs);                          // :98-100
     const double* act = a.buf.action + env * cfg.action_dim;
     const double a0 = clipd(act[0], lo, hi);
     const double a1 = (cfg.action_dim > 1) ? clipd(act[1], lo, hi) : a0;
@@ -213,19 +214,21 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
 
     arz_store<K>(r, rrow, M, sm, lane);
     arz_store<K>(y, yrow, M, sm, lane);
-    double* orow = a.buf.obs + env * 2 * M;
+    const bool restart = a.ar_profile != nullptr && (term || trunc);
     if (st == PDECG_ARZ_OUTLET_TRAIN) {                                               // :231
-        double rn[K], vn[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            rn[k] = D::div(D::sub(r[k], rs), rs);
-            vn[k] = D::div(D::sub(v[k], vs), vs);
+            r[k] = D::div(D::sub(r[k], rs), rs);                                       // (the state rows are stored already)
+            v[k] = D::div(D::sub(v[k], vs), vs);
         }
-        arz_store<K>(rn, orow, M, sm, lane);
-        arz_store<K>(vn, orow + M, M, sm, lane);
-    } else {
-        arz_store<K>(r, orow, M, sm, lane);
-        arz_store<K>(v, orow + M, M, sm, lane);
+    }
+    double* orow = a.buf.obs + env * 2 * M;
+    arz_store<K>(r, orow, M, sm, lane);
+    arz_store<K>(v, orow + M, M, sm, lane);
+    if (restart && a.buf.final_obs != nullptr) {                                      // terminal observation for the caller
+        double* frow_obs = a.buf.final_obs + env * 2 * M;
+        arz_store<K>(r, frow_obs, M, sm, lane);
+        arz_store<K>(v, frow_obs + M, M, sm, lane);
     }
     if (lane == 0) {
         frow[PDECG_ARZ_F_TIME] = time;
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
         a.buf.terminated[env] = term ? 1 : 0;
         a.buf.truncated[env] = trunc ? 1 : 0;
     }
-    if (a.ar_profile != nullptr && (term || trunc)) arz_autoreset_env(a, env, lane);
+    if (restart) arz_autoreset_env(a, env, lane);
 }
 
 // TrafficPDE1D.reset (:237-267) for one env, executed by its warp.  `keep_outputs`: leave reward / flags alone

@@ -37,20 +37,25 @@ class EpisodeStats:
         self.tot[STAT_FIELDS.index("return_max")] = float("-inf")
 
     def update(self, reward, terminated, truncated):
+        """Mask arithmetic only (no boolean indexing, no data-dependent shapes): nothing here synchronises with the
+        host, and the whole update can be captured in a CUDA graph."""
+        if reward.numel() == 0:
+            return
         done = terminated | truncated
         self.ret += reward.to(torch.float64)
         self.length += 1
-        fin = self.ret[done]
+        zero = torch.zeros((), dtype=torch.float64, device=self.device)
+        fin = torch.where(done, self.ret, zero)
         t = self.tot
         t[0] += done.sum()
         t[1] += fin.sum()
         t[2] += (fin * fin).sum()
-        t[3] += self.length[done].sum()
+        t[3] += torch.where(done, self.length, torch.zeros_like(self.length)).sum()
         t[4] += truncated.sum()
         t[5] += (terminated & ~truncated).sum()
-        if fin.numel():            # shape check only -- no device sync
-            t[6] = torch.minimum(t[6], fin.min())
-            t[7] = torch.maximum(t[7], fin.max())
+        inf = torch.full((), float("inf"), dtype=torch.float64, device=self.device)
+        t[6] = torch.minimum(t[6], torch.where(done, self.ret, inf).min())
+        t[7] = torch.maximum(t[7], torch.where(done, self.ret, -inf).max())
         t[8] += reward.numel()
         self.ret = torch.where(done, torch.zeros_like(self.ret), self.ret)
         self.length = torch.where(done, torch.zeros_like(self.length), self.length)

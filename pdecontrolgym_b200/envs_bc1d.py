@@ -86,6 +86,8 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                  autoreset: bool = False,
                  copy_obs: bool = True,
                  env_id_offset: int = 0,
+                 obs_dtype: Optional[str] = None,
+                 final_obs: bool = False,
                  **kwargs):
         super().__init__(**kwargs)
         self.sensing_noise_func = sensing_noise_func
@@ -99,6 +101,15 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         self.autoreset = bool(autoreset)
         self.copy_obs = bool(copy_obs)   # False: full-state observations are zero-copy views of the live state
         self.env_id_offset = int(env_id_offset)   # global index of env 0 (multi-GPU sharding)
+        # obs_dtype="float32": full-state observations (and final_obs) leave the kernels as float32 -- the dtype of the
+        # reference's observation_space (base_env_1d.py:33-35) -- while the resident state keeps its precision.  Halves the
+        # observation bytes of an fp64 batch (device copy and, for step_host, the PCIe copy-out).
+        if obs_dtype not in (None, "state", "float32"):
+            raise ValueError("obs_dtype must be None / 'state' (the state dtype) or 'float32'")
+        self.obs_f32 = obs_dtype == "float32"
+        if self.obs_f32 and not self.copy_obs and sensing_loc == "full":
+            raise ValueError("obs_dtype='float32' needs copy_obs=True (a zero-copy view of the state cannot change dtype)")
+        self._want_final_obs = bool(final_obs)
         self._seed, self._random_ic = 0, None
         # same messages as hyperbolic.py:60-62,87-89,122-124 / parabolic.py:85,114
         if sensing_loc not in _SENSE_LOC:
@@ -174,7 +185,15 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         buf.truncated = self._truncated.data_ptr()
         buf.time_index = self.time_index.data_ptr()
         buf.carry = self._carry.data_ptr()
+        buf.obs_copy_f32 = int(self.obs_f32)
         self._buf = buf
+        self.obs_torch_dtype = torch.float32 if self.obs_f32 else self.state_dtype
+        # autoreset + final_obs: the observation of the step that ended an episode survives the fused restart here
+        self._final_obs = None
+        if self._want_final_obs:
+            with torch.cuda.device(dev):
+                self._final_obs = torch.zeros((N, P) if sensing_loc == "full" else (N,), dtype=self.obs_torch_dtype, device=dev)
+        self._host_obs_dev = None
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
@@ -215,7 +234,9 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
 
     def _sense(self):
         obs = self.u if self.sensing_loc == "full" else self._obs_scalar
-        if self.copy_obs:
+        if self.obs_f32 and obs.dtype != torch.float32:
+            obs = obs.to(torch.float32)
+        elif self.copy_obs:
             obs = obs.clone()
         if self.sensing_noise_func is not None:
             obs = self.sensing_noise_func(obs)
@@ -304,6 +325,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             ar.seed, ar.env_id_offset, ar.episode = self._seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset, self._episode.data_ptr()
         else:
             ar.random, ar.init_env_stride = 0, self._ic_stride
+        ar.final_obs = None if self._final_obs is None else self._final_obs.data_ptr()
         return ar
 
     def _prep_action(self, action):
@@ -335,7 +357,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         # full-state observation copies are written by the kernels themselves into a fresh tensor (no clone launch)
         obs_out = None
         if self.copy_obs and self.sensing_loc == "full":
-            obs_out = torch.empty_like(self.u)
+            obs_out = torch.empty_like(self.u, dtype=self.obs_torch_dtype)
             self._buf.obs_copy = obs_out.data_ptr()
         # the kernel writes reward / flags straight into fresh tensors handed to the caller (no clone launches)
         reward, term_u8, trunc_u8 = torch.empty_like(self._reward), torch.empty_like(self._terminated), torch.empty_like(self._truncated)
@@ -353,7 +375,8 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                 if ke is not None:
                     ke[1].record()
             terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
-            info = {}
+            # rows of the envs with terminated | truncated this step are fresh (SB3 "terminal_observation")
+            info = {"final_obs": self._final_obs} if (self.autoreset and self._final_obs is not None) else {}
         finally:
             self._buf.obs_copy = None            # never leave a pointer to a caller-owned tensor behind
             self._buf.reward, self._buf.terminated, self._buf.truncated = (
@@ -388,15 +411,28 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                 raise ValueError(f"{what} must be a contiguous CPU {dtype} tensor with {numel} elements")
             return t.data_ptr()
         obs_n = self.num_envs * (self.npts if self.sensing_loc == "full" else 1)
+        full = self.sensing_loc == "full"
+        host_obs_dtype = self.obs_torch_dtype if full else self.state_dtype
+        if full and self.obs_f32 and self.state_dtype != torch.float32 and obs_host is not None:
+            # float32 observations of a float64 state: the kernel writes them into this device staging buffer
+            if self._host_obs_dev is None:
+                self._host_obs_dev = torch.empty((self.num_envs, self.npts), dtype=torch.float32, device=self.device)
+            self._buf.obs_copy = self._host_obs_dev.data_ptr()
+        try:
+            self._step_host_call(a, ptr(obs_host, host_obs_dtype, obs_n, "obs_host"), ptr, reward_host, terminated_host, truncated_host)
+        finally:
+            self._buf.obs_copy = None
+        return obs_host, reward_host, terminated_host, truncated_host, {}
+
+    def _step_host_call(self, a, obs_ptr, ptr, reward_host, terminated_host, truncated_host):
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_bc1d_step_host(
                 C.byref(self._cfg), C.byref(self._buf), a.data_ptr(),
-                ptr(obs_host, self.state_dtype, obs_n, "obs_host"),
+                obs_ptr,
                 ptr(reward_host, torch.float64, self.num_envs, "reward_host"),
                 ptr(terminated_host, torch.uint8, self.num_envs, "terminated_host"),
                 ptr(truncated_host, torch.uint8, self.num_envs, "truncated_host"),
                 C.byref(self._autoreset_desc()) if self.autoreset else None, self._stream()))
-        return obs_host, reward_host, terminated_host, truncated_host, {}
 
     # compatibility attributes read by the reference's examples
     @property

@@ -40,7 +40,8 @@ class BrainTumor1D(StateDictMixin):
                  t1_detection_radius: int = 15, t1_death_radius: int = 35,
                  reset_init_condition_func=None, total_dosage=None, verbose=False,
                  *, T, dt, X, dx, reward_class=None, normalize=False,
-                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False):
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False,
+                 final_obs: bool = False):
         if precision not in ("ref", "fp64"):
             raise ValueError("BrainTumor1D is float64 in the reference; precision must be 'ref' or 'fp64'")
         if reward_class is not None and not isinstance(reward_class, BrainTumorReward):
@@ -94,6 +95,8 @@ class BrainTumor1D(StateDictMixin):
             self._truncated = torch.zeros((N,), dtype=torch.uint8, device=dev)
             self._valid = torch.ones((N,), dtype=torch.uint8, device=dev)
             self._zero_action = torch.zeros((N,), dtype=torch.float64, device=dev)
+            # autoreset + final_obs: the state row of the day that ended an episode, kept for the envs that restarted
+            self._final_obs = torch.zeros((N, self.nx), dtype=torch.float64, device=dev) if final_obs else None
         buf = _lib.BtBuffers()
         buf.n_envs = N
         buf.u, buf.obs, buf.x_scale = self.u.data_ptr(), self._obs.data_ptr(), self.xScale.data_ptr()
@@ -108,7 +111,7 @@ class BrainTumor1D(StateDictMixin):
     def _stream(self):
         return _lib.current_raw_stream(self.device.index)
 
-    def _run(self, mode, action=None, autoreset=False):
+    def _run(self, mode, action=None, autoreset=False, mask_t=None):
         """One launch.  The kernel writes reward / flags / valid straight into fresh tensors handed to the caller (no
         clone launches); returns (reward, terminated_u8, truncated_u8, valid_u8).  `autoreset` (RAW_STEP only): envs
         that finish restart from the last initial condition inside the same launch."""
@@ -119,6 +122,8 @@ class BrainTumor1D(StateDictMixin):
         buf.obs = None if mode == RAW_STEP else self._obs.data_ptr()
         outs = tuple(torch.empty_like(t) for t in (self._reward, self._terminated, self._truncated, self._valid))
         buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
+        buf.final_obs = self._final_obs.data_ptr() if (autoreset and self._final_obs is not None) else None
+        buf.mask = None if mask_t is None else mask_t.data_ptr()
         try:
             with torch.cuda.device(self.device):
                 if autoreset:
@@ -129,6 +134,7 @@ class BrainTumor1D(StateDictMixin):
         finally:
             buf.reward, buf.terminated, buf.truncated, buf.valid = (
                 self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(), self._valid.data_ptr())
+            buf.final_obs = buf.mask = None
         return outs
 
     def _prep_action(self, action):
@@ -150,8 +156,10 @@ class BrainTumor1D(StateDictMixin):
         """(reward, terminated, truncated, info) from the fresh tensors a launch wrote."""
         reward, term_u8, trunc_u8, valid_u8 = outs
         stage = self._ienv[:, I_STAGE]              # copy_obs=False: a live zero-copy view, like the observation
-        return (reward, term_u8.view(torch.bool), trunc_u8.view(torch.bool),
-                {"stage": stage.clone() if self.copy_obs else stage, "valid": valid_u8.view(torch.bool)})
+        info = {"stage": stage.clone() if self.copy_obs else stage, "valid": valid_u8.view(torch.bool)}
+        if self.autoreset and self._final_obs is not None:
+            info["final_obs"] = self._final_obs      # rows of the envs with terminated | truncated this step are fresh
+        return (reward, term_u8.view(torch.bool), trunc_u8.view(torch.bool), info)
 
     # -- gym API -------------------------------------------------------------------------------
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
@@ -238,6 +246,24 @@ class BrainTumor1D(StateDictMixin):
     cDeathDay = property(lambda s: s._icol(I_DEATH))
     remaining_dosage = property(lambda s: s._fenv[:, F_REMAINING])
 
+    # The reference logs two per-day histories, `dosage_vs_time[t]` and `t1_radius_idx_vs_time[t]`
+    # (brain_tumor_env.py:54-56,160,276).  Here they are per-env values of the CURRENT day; record them over an episode
+    # with `TrajectoryRecorder(env, max_steps, extras=("dosage", "t1_radius_idx"))`.
+    @property
+    def dosage(self):
+        """Dose applied on the last simulated day (0 outside the Therapy stage): the entry the reference writes to
+        `dosage_vs_time[time_index]`."""
+        return self._fenv[:, F_LAST_DOSE].clone()
+
+    @property
+    def t1_radius_idx(self):
+        """`getTumorRadius(t, t1_detection_threshold) / dx` of the current state, NaN where the tumour is below the T1
+        threshold everywhere: the entry the reference writes to `t1_radius_idx_vs_time[time_index]` (:104-121,274-276)."""
+        hit = self.u >= self._cfg.t1_threshold_k
+        idx = torch.where(hit, torch.arange(self.nx, device=self.device), -1).max(dim=1).values
+        val = (idx.to(torch.float64) * self.dx) / self.dx
+        return torch.where(idx >= 0, val, torch.full_like(val, float("nan")))
+
     @property
     def t_benchmark(self):
         return self._ienv[:, I_TBENCH]
@@ -282,7 +308,11 @@ class TherapyWrapper:
         env = self.env
         env.reset(seed=seed, options=options)
         env._cfg.weekends = int(bool(self.weekends))
-        env._run(WRAP_RESET)
+        # a masked reset restarts only the selected patients: the others keep their therapy state, incl. the
+        # consecutive-treatment-day counter the weekend rule depends on (brain_tumor_env.py:408-427 is per env)
+        mask = (options or {}).get("mask")
+        mask_t = None if mask is None else torch.as_tensor(mask, device=env.device).to(torch.uint8).contiguous()
+        env._run(WRAP_RESET, mask_t=mask_t)
         return (env._obs.clone() if env.copy_obs else env._obs), {"stage": env._ienv[:, I_STAGE].clone()}
 
     def step(self, control):

@@ -44,7 +44,8 @@ class NavierStokes2D(StateDictMixin):
                  viscosity: float = 0.1, density: float = 1.0, maximum_pressure_iteration: float = 2000,
                  stable_factor: float = 0.5,
                  *, T, dt, X, dx, Y, dy, action_dim: int = 1, reward_class=None, normalize: bool = False,
-                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False):
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False,
+                 final_obs: bool = False):
         if precision not in ("ref", "fp64"):
             raise ValueError("NavierStokes2D is float64 in the reference; precision must be 'ref' or 'fp64'")
         if not isinstance(reward_class, NSReward):
@@ -73,6 +74,7 @@ class NavierStokes2D(StateDictMixin):
         self.copy_obs = copy_obs
         self.autoreset = bool(autoreset)
         self._init = None
+        self._want_final_obs = bool(final_obs)
         max_t = (0.5 * min(dx, dy) ** 2 / viscosity)
         if dt > stable_factor * max_t:
             raise RuntimeError("Stability is not guarenteed")      # :56-58
@@ -143,6 +145,8 @@ class NavierStokes2D(StateDictMixin):
         when it returns single fields)."""
         options = options or {}
         init = options.get("init")
+        if init is None and self.reset_init_condition_func is None and self._init is not None:
+            init = self._init                  # re-use the last explicit initial fields (masked restarts)
         if init is None:
             if self.reset_init_condition_func is None:
                 raise Exception("Please pass both an initial condition and a recirculation function in the parameters dictionary. See documentation for more details")
@@ -182,6 +186,13 @@ class NavierStokes2D(StateDictMixin):
         # the kernel writes reward / flags / valid straight into fresh tensors handed to the caller (no clone launches)
         outs = tuple(torch.empty_like(t) for t in internal)
         buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
+        fin = None
+        if self.autoreset and self._want_final_obs:
+            # the terminal observation U[nt-1] of the envs that restart, kept across the fused auto-reset
+            if getattr(self, "_final_obs", None) is None:
+                self._final_obs = torch.zeros_like(self._obs)
+            fin = self._final_obs
+        buf.final_obs = None if fin is None else fin.data_ptr()
         try:
             with torch.cuda.device(self.device):
                 if self.autoreset:       # same-step auto-reset to the last initial fields, inside the step launch
@@ -192,8 +203,11 @@ class NavierStokes2D(StateDictMixin):
                     _lib.check(self._L.pdecg_ns_step(C.byref(self._cfg), C.byref(buf), self._stream()))
         finally:
             buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in internal)
+            buf.final_obs = None
         reward, term_u8, trunc_u8, valid_u8 = outs
         terminated, truncated, info = term_u8.view(torch.bool), trunc_u8.view(torch.bool), {"valid": valid_u8.view(torch.bool)}
+        if fin is not None:
+            info["final_obs"] = fin            # rows of the envs with terminated this step are fresh
         obs = self._obs.clone() if self.copy_obs else self._obs
         return obs, reward, terminated, truncated, info
 

@@ -21,17 +21,18 @@ from .spaces import Box
 from .checkpoint import StateDictMixin
 
 _TYPES = {"inlet": 0, "outlet": 1, "both": 2, "outlet-train": 3}
-F_TIME, F_RS, F_VS, F_QS, NF64 = 0, 1, 2, 3, 4
+F_TIME, F_RS, F_VS, F_QS, F_ACT_LO, F_ACT_HI, NF64 = 0, 1, 2, 3, 4, 5, 6
 _RS_VALUES = (0.115, 0.12, 0.125)            # traffic_arz_env.py:66-68
 
 
 class TrafficPDE1D(StateDictMixin):
-    _STATE_TENSORS = ('_ry', '_obs', '_fenv', '_reward', '_terminated', '_truncated')
+    _STATE_TENSORS = ('_ry', '_fenv', '_reward', '_terminated', '_truncated')
     def __init__(self, simulation_type: str = "inlet", v_steady: float = 10, ro_steady: float = 0.12,
                  v_max: float = 40, ro_max: float = 0.16, tau: float = 60,
                  limit_pde_state_size: bool = False, control_freq: int = 1,
                  *, T, dt, X, dx, reward_class=None, normalize=False,
-                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False):
+                 num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False,
+                 rs_init=None, final_obs: bool = False):
         if precision not in ("ref", "fp64"):
             raise ValueError("TrafficPDE1D is float64 in the reference; precision must be 'ref' or 'fp64'")
         if reward_class is not None and not isinstance(reward_class, TrafficARZReward):
@@ -66,7 +67,10 @@ class TrafficPDE1D(StateDictMixin):
             vs = np.full(N, float(v_steady))
             qs = vs * rs                                                   # :63
         else:
-            rs = np.array([_RS_VALUES[random.randint(0, 2)] for _ in range(N)], dtype=np.float64)
+            if rs_init is None:           # the constructor's own draw (:66-68); `rs_init` pins it (tests, reproducible runs)
+                rs = np.array([_RS_VALUES[random.randint(0, 2)] for _ in range(N)], dtype=np.float64)
+            else:
+                rs = np.broadcast_to(np.asarray(rs_init, dtype=np.float64), (N,)).copy()
             vs = self.Veq(self.vm, self.rm, rs)
             qs = rs * vs                                                   # :70
         x = np.arange(0, X + dx, dx)                                       # :74
@@ -99,6 +103,9 @@ class TrafficPDE1D(StateDictMixin):
             self._reward = torch.zeros((N,), dtype=torch.float64, device=dev)
             self._terminated = torch.zeros((N,), dtype=torch.uint8, device=dev)
             self._truncated = torch.zeros((N,), dtype=torch.uint8, device=dev)
+            # autoreset + final_obs: the observation of the step that ended an episode, kept for the envs that restarted
+            self._final_obs = torch.zeros((N, 2 * self.M), dtype=torch.float64, device=dev) if final_obs else None
+        self._last_obs = None
         buf = _lib.ArzBuffers()
         buf.n_envs = N
         buf.ry, buf.obs, buf.fenv = self._ry.data_ptr(), self._obs.data_ptr(), self._fenv.data_ptr()
@@ -106,6 +113,10 @@ class TrafficPDE1D(StateDictMixin):
         buf.terminated, buf.truncated = self._terminated.data_ptr(), self._truncated.data_ptr()
         self._buf = buf
         self._set_steady(rs, vs, qs)
+        # action_space.low / .high are fixed here, from the constructor's qs (traffic_arz_env.py:97-100): reset() re-draws
+        # rs / qs for 'outlet-train' but the reference keeps clipping with these bounds (:161,166)
+        self._fenv[:, F_ACT_LO] = torch.from_numpy(qs * 0.8).to(dev)
+        self._fenv[:, F_ACT_HI] = torch.from_numpy(1.2 * qs).to(dev)
         if simulation_type == "outlet-train":
             self.single_observation_space = Box(low=-10, high=10, shape=(2 * self.M,), dtype=np.float64)
         else:
@@ -161,7 +172,16 @@ class TrafficPDE1D(StateDictMixin):
             vs = self.Veq(self.vm, self.rm, rs)
             self._set_steady(rs, vs, rs * vs, None if mask_t is None else mask_t.bool())
         self._reset_kernel(mask_t)
-        return (self._obs.clone() if self.copy_obs else self._obs), {}
+        if not self.copy_obs:
+            return self._obs, {}
+        if mask_t is not None and self._last_obs is not None:
+            # step() hands out fresh observation tensors (self._obs only receives the rows reset() writes), so the
+            # rows of the envs that were NOT reset come from the last observation returned
+            obs = torch.where(mask_t.bool().unsqueeze(1), self._obs, self._last_obs)
+        else:
+            obs = self._obs.clone()
+        self._last_obs = obs
+        return obs, {}
 
     def step(self, action):
         """traffic_arz_env.py:131-233: clip the flow-rate action(s), `control_freq` Lax-Wendroff substeps,
@@ -187,6 +207,8 @@ class TrafficPDE1D(StateDictMixin):
         # writes the new observation rows where the step wrote).  'outlet-train' re-draws rs per episode on the host, so
         # it keeps the step + masked-reset sequence.
         fused = self.autoreset and self.simulation_type != "outlet-train"
+        buf.final_obs = self._final_obs.data_ptr() if (fused and self._final_obs is not None) else None
+        info = self.info
         try:
             with torch.cuda.device(self.device):
                 if fused:
@@ -196,13 +218,22 @@ class TrafficPDE1D(StateDictMixin):
             terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
             if self.autoreset and not fused:
                 done = torch.bitwise_or(term_u8, trunc_u8)
-                # reward / flags of the restart go to the internal buffers
+                if self._final_obs is not None:
+                    self._final_obs.copy_(torch.where(done.bool().unsqueeze(1), obs, self._final_obs))
+                # reward / flags of the restart go to the internal buffers, its observation rows replace the finished ones
                 buf.reward, buf.terminated, buf.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
-                self.reset(options={"mask": done})
+                buf.obs = self._obs.data_ptr()
+                self._last_obs = obs
+                obs, _ = self.reset(options={"mask": done})
+            if self.autoreset and self._final_obs is not None:
+                info = dict(self.info, final_obs=self._final_obs)   # rows of the envs that finished this step are fresh
         finally:
             buf.obs, buf.reward, buf.terminated, buf.truncated = (self._obs.data_ptr(), self._reward.data_ptr(),
                                                                   self._terminated.data_ptr(), self._truncated.data_ptr())
-        return obs, reward, terminated, truncated, self.info
+            buf.final_obs = None
+        if self.copy_obs:
+            self._last_obs = obs
+        return obs, reward, terminated, truncated, info
 
     def step_host(self, action_host, obs_host=None, reward_host=None, terminated_host=None, truncated_host=None):
         """End-to-end step over HOST buffers (pdecg_arz_step_host): H2D(actions) -> kernel -> D2H(obs, reward, flags)

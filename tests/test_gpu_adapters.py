@@ -5,28 +5,51 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_adapters_shapes_and_semantics(cuda_device):
+def test_adapters_follow_the_vector_env_protocols(cuda_device):
+    """The gymnasium (same-step and next-step auto-reset) and SB3 adapters on a CUDA env, driven by the vendored
+    protocol checkers; terminal observations equal the oracle's last row, restarted rows equal the initial condition."""
     import pdecontrolgym_b200 as pcg
+    from oracle import np_oracle as O
     from pdecontrolgym_b200.adapters import GymnasiumVectorAdapter, SB3VecEnvAdapter
-    kw = dict(T=0.002, dt=1e-5, X=1, dx=5e-3, control_sample_rate=1e-3, normalize=True, reward_class=pcg.TunedReward1D(200))
-    env = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=6, device=cuda_device, autoreset=True, **kw)
-    opts = {"init_condition": pcg.UniformScaleIC(1, 10), "beta": np.zeros(201)}
-    g = GymnasiumVectorAdapter(env)
-    obs, info = g.reset(seed=3, options=opts)
-    assert isinstance(obs, np.ndarray) and obs.shape == (6, 201) and obs.dtype == np.float32
-    obs, r, te, tr, info = g.step(np.zeros((6, 1), dtype=np.float32))
-    assert r.shape == (6,) and te.dtype == bool and not te.any()
-    obs, r, te, tr, info = g.step(np.zeros((6, 1), dtype=np.float32))
-    assert te.all()
-    s = SB3VecEnvAdapter(env)
-    obs = s.reset()
-    s.step_async(np.zeros((6, 1), dtype=np.float32))
-    obs, r, dones, infos = s.step_wait()
-    assert obs.shape == (6, 201) and r.dtype == np.float32 and len(infos) == 6 and not dones.any()
-    obs, r, dones, infos = s.step(np.zeros((6, 1), dtype=np.float32))
-    assert dones.all() and not infos[0]["TimeLimit.truncated"]
+    from tests.vecenv_protocol import drive_gymnasium, drive_sb3
+    N = 6
+    kw = dict(T=0.003, dt=1e-5, X=1, dx=5e-3, control_sample_rate=1e-3, normalize=True)       # 3 control steps per episode
+    rng = np.random.default_rng(2)
+    ic = rng.uniform(1, 2, (N, 1)) * np.ones((N, 201))
+    beta = (50 * np.cos(8 * np.arccos(np.linspace(0, 1, 201)))).astype(np.float32)
+    acts = rng.uniform(-1, 1, (8, N, 1)).astype(np.float32)
+    orc = O.ReactionDiffusionOracle(N, reward=O.TunedReward1DSpec(300, -1e3, 3e2), **kw)
+    orc.reset(ic, beta)
+    rows = [orc.step(acts[k].reshape(-1))[0].copy() for k in range(3)]                         # one oracle episode
+    opts = {"init_condition": ic, "beta": beta}
+
+    env = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=N, device=cuda_device, autoreset=True, final_obs=True,
+                   reward_class=pcg.TunedReward1D(300), **kw)
+    log = drive_gymnasium(GymnasiumVectorAdapter(env), lambda k: acts[k], 4, (201,), reset_kwargs={"options": opts})
+    assert log[0][0].dtype == np.float32 and np.array_equal(log[0][0], rows[0]) and not log[0][2].any()
+    obs, rew, term, trunc, infos = log[2]
+    assert term.all() and np.array_equal(infos["final_obs"], rows[2]) and np.array_equal(obs, ic.astype(np.float32))
+    assert np.array_equal(log[3][0], orc_first_step(O, kw, ic, beta, acts[3]))                 # the new episode continues from the IC
+
+    log = drive_sb3(SB3VecEnvAdapter(env), lambda k: acts[k], 3, (201,))
+    obs, rew, dones, infos = log[2]
+    assert dones.all() and all(np.array_equal(infos[i]["terminal_observation"], rows[2][i]) for i in range(N))
+    assert not infos[0]["TimeLimit.truncated"] and np.array_equal(obs, ic.astype(np.float32))
     with pytest.raises(ValueError):
-        SB3VecEnvAdapter(pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=2, device=cuda_device, **kw))
+        SB3VecEnvAdapter(pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=2, device=cuda_device, reward_class=pcg.TunedReward1D(300), **kw))
+
+    env2 = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=N, device=cuda_device, autoreset=False,
+                    reward_class=pcg.TunedReward1D(300), **kw)
+    log = drive_gymnasium(GymnasiumVectorAdapter(env2, autoreset_mode="next_step"), lambda k: acts[k], 6, (201,), reset_kwargs={"options": opts})
+    assert log[2][2].all() and np.array_equal(log[2][0], rows[2])                              # the finishing step returns the terminal row
+    assert not log[3][2].any() and np.array_equal(log[3][0], ic.astype(np.float32)) and (log[3][1] == 0).all()
+    assert np.array_equal(log[4][0], orc_first_step(O, kw, ic, beta, acts[4]))
+
+
+def orc_first_step(O, kw, ic, beta, act):
+    orc = O.ReactionDiffusionOracle(ic.shape[0], reward=O.TunedReward1DSpec(300, -1e3, 3e2), **kw)
+    orc.reset(ic, beta)
+    return orc.step(act.reshape(-1))[0]
 
 
 def test_arz_backstepping_drives_to_steady_state(cuda_device):

@@ -425,3 +425,109 @@ def test_small_batch_latency_mapping(cuda_device, env, monkeypatch):
     o, r, te, tr, _ = e1.step(torch.from_numpy(a))
     e2.step_host(torch.from_numpy(a).pin_memory(), obs_h, rew_h, None, None)
     assert np.array_equal(o.cpu().numpy(), obs_h.numpy()) and np.array_equal(r.cpu().numpy(), rew_h.numpy())
+
+
+def test_halfwarp_pair_with_per_env_beta_in_different_binades(cuda_device):
+    """Two envs share a warp (16 lanes each) and run the substep loop in lock step.  Their growth bound
+    rho = 1 + 4F + max|dt*beta| decides how many substeps may use the exact-FMA form; with PER-ENV beta rows that put
+    rho on either side of a power of two (F just below 0.25: rho ~ 2) the two envs must still agree on that count.
+    States stay bit-identical to the oracle for both."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    nx, sub, steps, B = 200, 100, 6, 8
+    dx = 1.0 / nx
+    dt = 0.2499 * dx * dx
+    kw = dict(T=dt * sub * steps, dt=dt, X=1, dx=dx, control_sample_rate=dt * sub, normalize=True, max_control_value=20)
+    nt_r = sub * steps
+    rng = np.random.default_rng(11)
+    ics = make_ics(rng, B, nx + 1)
+    shape = np.cos(8 * np.arccos(np.linspace(0, 1, nx + 1)))
+    beta = np.empty((B, nx + 1))
+    beta[1::2] = (1e-3 / dt) * shape[None, :]                            # odd envs: max|dt*beta| = 1e-3 -> rho = 2.0006 > 2
+    beta[0::2] = (1e-5 / dt) * shape[None, :]                            # even envs: max|dt*beta| = 1e-5 -> rho = 1.99961 < 2
+    assert 1 + 4 * 0.2499 + 1e-5 < 2 < 1 + 4 * 0.2499 + 1e-3
+    oenv = O.ReactionDiffusionOracle(B, reward=O.NormRewardSpec(nt_r, norm=2), precision="fp64", **kw)
+    genv = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=B, device=cuda_device, precision="fp64",
+                    reward_class=pcg.NormReward(nt_r, norm="2"), **kw)
+    o_ref = oenv.reset(ics, beta)
+    o_gpu, _ = genv.reset(options={"init_condition": ics, "beta": beta})
+    assert np.array_equal(o_gpu.cpu().numpy(), o_ref)
+    for k in range(steps):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        o_ref, r_ref, te_ref, tr_ref = oenv.step(a)
+        o_gpu, r_gpu, te_gpu, tr_gpu, _ = genv.step(torch.from_numpy(a))
+        assert np.array_equal(o_gpu.cpu().numpy(), o_ref), f"step {k}"
+        np.testing.assert_allclose(r_gpu.cpu().numpy(), r_ref, rtol=1e-12)
+    assert te_ref.all() and te_gpu.all()
+
+
+@pytest.mark.parametrize("env,nx", [("rd", None), ("tr", None), ("rd", 700), ("tr", 2500)])
+def test_float32_observations_and_final_obs(cuda_device, env, nx):
+    """obs_dtype='float32' on a float64 batch: every observation the kernels hand out (step, reset, fused restart,
+    final_obs, step_host) is the oracle's float64 row rounded once to float32 (`astype(np.float32)`), while the resident
+    state stays float64 and bit-identical.  final_obs holds the terminal row of the envs that restarted; the returned
+    observation of those envs is the new episode's initial row.  Warp kernels and both CTA-per-env kernels."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    steps, B = 4, 6
+    kw, npts, beta, nt = bc1d_case(env, nx, steps)
+    nt_r = nt - 1
+    common = dict(normalize=True, max_control_value=20, **kw)
+    rng = np.random.default_rng(5)
+    ics = make_ics(rng, B, npts)
+    Orc = O.ReactionDiffusionOracle if env == "rd" else O.TransportOracle
+    oenv = Orc(B, reward=O.NormRewardSpec(nt_r, norm=2), precision="fp64", **common)
+    eid = "PDEControlGym-ReactionDiffusionPDE1D" if env == "rd" else "PDEControlGym-TransportPDE1D"
+    mk = lambda **extra: pcg.make(eid, num_envs=B, device=cuda_device, precision="fp64", reward_class=pcg.NormReward(nt_r, norm="2"),  # noqa: E731
+                                  autoreset=True, obs_dtype="float32", final_obs=True, **extra, **common)
+    genv, henv = mk(), mk()
+    o_ref = oenv.reset(ics, beta)
+    o_gpu, _ = genv.reset(options={"init_condition": ics, "beta": beta})
+    henv.reset(options={"init_condition": ics, "beta": beta})
+    assert o_gpu.dtype == torch.float32 and np.array_equal(o_gpu.cpu().numpy(), o_ref.astype(np.float32))
+    obs_h = torch.empty(B, npts, dtype=torch.float32).pin_memory()
+    rew_h, te_h, tr_h = torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.uint8).pin_memory(), torch.empty(B, dtype=torch.uint8).pin_memory()
+    for k in range(steps):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        o_ref, r_ref, te_ref, tr_ref = oenv.step(a)
+        o_gpu, r_gpu, te_gpu, tr_gpu, info = genv.step(torch.from_numpy(a))
+        henv.step_host(torch.from_numpy(a), obs_h, rew_h, te_h, tr_h)
+        assert o_gpu.dtype == torch.float32
+        if k < steps - 1:
+            assert np.array_equal(o_gpu.cpu().numpy(), o_ref.astype(np.float32)), f"step {k}"
+            assert np.array_equal(genv.u.cpu().numpy(), o_ref), f"step {k}: resident float64 state"
+            assert np.array_equal(obs_h.numpy(), o_ref.astype(np.float32)), f"step {k}: step_host"
+        else:
+            assert te_gpu.all() and te_h.numpy().all()
+            fin = info["final_obs"]
+            assert fin.dtype == torch.float32 and np.array_equal(fin.cpu().numpy(), o_ref.astype(np.float32)), "terminal observation"
+            assert np.array_equal(henv._final_obs.cpu().numpy(), o_ref.astype(np.float32)), "terminal observation (step_host)"
+            assert np.array_equal(o_gpu.cpu().numpy(), ics.astype(np.float32)), "post-reset observation is the initial row"
+            assert np.array_equal(obs_h.numpy(), ics.astype(np.float32))
+            assert np.array_equal(genv.u.cpu().numpy(), ics)
+        np.testing.assert_allclose(r_gpu.cpu().numpy(), r_ref, rtol=1e-12)
+        np.testing.assert_allclose(rew_h.numpy(), r_ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("sensing", [("collocated", None), ("opposite", "Neumann")])
+def test_final_obs_scalar_sensing(cuda_device, sensing):
+    """Scalar sensing: final_obs is [num_envs] and holds the terminal sensor value of the restarted envs."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    steps, B = 3, 5
+    kw, npts, beta, nt = bc1d_case("tr", None, steps)
+    common = dict(normalize=True, max_control_value=20, sensing_loc=sensing[0], sensing_type=sensing[1], **kw)
+    rng = np.random.default_rng(6)
+    ics = make_ics(rng, B, npts)
+    oenv = O.TransportOracle(B, reward=O.TunedReward1DSpec(nt - 1, -1e3, 3e2), precision="ref", **common)
+    genv = pcg.make("PDEControlGym-TransportPDE1D", num_envs=B, device=cuda_device, precision="ref",
+                    reward_class=pcg.TunedReward1D(nt - 1, -1e3, 3e2), autoreset=True, final_obs=True, **common)
+    oenv.reset(ics, beta.astype(np.float32))
+    o0, _ = genv.reset(options={"init_condition": ics, "beta": beta.astype(np.float32)})
+    for k in range(steps):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        o_ref, r_ref, te_ref, tr_ref = oenv.step(a)
+        o_gpu, r_gpu, te_gpu, tr_gpu, info = genv.step(torch.from_numpy(a))
+    assert te_gpu.all()
+    assert np.array_equal(info["final_obs"].cpu().numpy(), np.asarray(o_ref).reshape(-1))
+    assert np.array_equal(o_gpu.cpu().numpy(), o0.cpu().numpy())

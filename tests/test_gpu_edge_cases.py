@@ -203,6 +203,8 @@ def _staggered_pair(fused, manual, reset, act, steps, state_names, stagger):
         o2, r2, te2, tr2, i2 = manual.step(act(k))
         done = te2 | tr2
         if done.any():
+            if "final_obs" in i1:       # the terminal observation of the restarted envs survives the fused restart
+                assert torch.equal(i1["final_obs"][done], o2[done]), f"step {k}: final_obs"
             o2r = reset(manual, done)
             o2 = torch.where(done.reshape((-1,) + (1,) * (o2.dim() - 1)), o2r, o2)
             n_done += int(done.sum())
@@ -231,7 +233,7 @@ def test_arz_fused_autoreset_equals_step_then_masked_reset(cuda_device, simulati
     import pdecontrolgym_b200 as pcg
     N = 9
     kw = dict(T=1.5, dt=0.25, X=500, dx=dx, simulation_type=simulation_type, v_max=vm, v_steady=vm * (1 - 0.12 / 0.16))   # 24 steps per episode
-    fused = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=cuda_device, autoreset=True, **kw)
+    fused = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=cuda_device, autoreset=True, final_obs=True, **kw)
     manual = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=N, device=cuda_device, autoreset=False, **kw)
     rng = np.random.default_rng(3)
     nact = 2 if simulation_type == "both" else 1
@@ -259,7 +261,7 @@ def test_brain_tumor_fused_autoreset_equals_step_then_masked_reset(cuda_device):
     ic = 0.8e5 * np.exp(-0.25 * xs ** 2)[None, :] * rng.uniform(0.5, 1.5, (N, 1))
     kw = dict(total_dosage=61.2, T=40, dt=1, X=200, dx=1, D=rng.uniform(0.1, 0.3, N), rho=np.linspace(0.02, 0.5, N),
               t1_detection_radius=3, t1_death_radius=6)
-    fused = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, autoreset=True, **kw)
+    fused = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, autoreset=True, final_obs=True, **kw)
     manual = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, autoreset=False, **kw)
     acts = [torch.from_numpy(rng.uniform(0, 0.1, N)) for _ in range(130)]
 
@@ -286,7 +288,7 @@ def test_navier_stokes_fused_autoreset_equals_step_then_masked_reset(cuda_device
     rng = np.random.default_rng(7)
     kw = dict(boundary_condition=BC, U_ref=rng.uniform(-1, 1, (50, n, n, 2)), action_ref=np.ones(100), reward_class=pcg.NSReward(0.1),
               maximum_pressure_iteration=7, T=0.006, dt=1e-3, X=1, dx=dx, Y=1, dy=dx)
-    fused = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, autoreset=True, **kw)
+    fused = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, autoreset=True, final_obs=True, **kw)
     manual = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, autoreset=False, **kw)
     init = tuple(rng.uniform(-1, 1, (N, n, n)) for _ in range(3))
     acts = [torch.from_numpy(rng.uniform(2, 4, N)) for _ in range(20)]
@@ -361,3 +363,36 @@ def test_step_host_matches_step_for_arz_bt_ns(cuda_device, autoreset):
         assert torch.equal(o.cpu(), oh) and torch.equal(r.cpu(), rh), f"ns step {k}"
         assert torch.equal(te.cpu(), teh.bool()) and torch.equal(info["valid"].cpu(), vh.bool())
         assert torch.equal(e1.p, e2.p) and torch.equal(e1.time_index, e2.time_index)
+
+
+def test_therapy_wrapper_masked_reset_keeps_the_other_patients(cuda_device):
+    """TherapyWrapper.reset(options={'mask': ...}) restarts only the selected patients: the others -- mid-therapy, with
+    weekends=True -- keep their consecutive-treatment-day counter, so their forced rest days land where the oracle's do."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    from tests.golden.gen_golden import BT_P, bt_ic
+    N = 4
+    ic = bt_ic(200, 201)
+    env = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, reward_class=pcg.BrainTumorReward(), **BT_P)
+    w = pcg.TherapyWrapper(env, weekends=True)
+    oenvs = [O.BrainTumorOracle(1, **BT_P) for _ in range(N)]
+    ows = [O.TherapyWrapperOracle(e, ic, weekends=True) for e in oenvs]
+    tb = w.benchmark()
+    for ow in ows:
+        assert ow.benchmark() == int(tb[0])
+    o, _ = w.reset(options={"init_condition": ic})
+    refs = [ow.reset()[0] for ow in ows]
+    assert all(np.array_equal(o[i].cpu().numpy(), refs[i]) for i in range(N))
+    mask = np.array([True, False, True, False])
+    for k in range(9):
+        if k == 3:                        # three treatment days in: patients 0 and 2 start over, 1 and 3 carry on
+            o, _ = w.reset(options={"init_condition": ic, "mask": mask})
+            for i in np.nonzero(mask)[0]:
+                assert np.array_equal(o[i].cpu().numpy(), ows[i].reset()[0])
+            assert w.consecutive_treatment_days.cpu().tolist() == [0, 3, 0, 3]
+        o, r, te, tr, _ = w.step(torch.full((N,), 0.02, dtype=torch.float64))
+        for i in range(N):
+            o2, r2, te2, tr2 = ows[i].step(0.02)
+            np.testing.assert_allclose(o[i].cpu().numpy(), o2[0], rtol=1e-13, atol=0, err_msg=f"call {k} env {i}")
+            assert float(r[i]) == float(r2[0]) and bool(te[i]) == bool(te2[0]) and bool(tr[i]) == bool(tr2[0])
+        assert env.time_index.cpu().tolist() == [int(e.t[0]) for e in oenvs], f"call {k}: day counters (weekend placement)"

@@ -9,10 +9,12 @@ from oracle import np_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def run(cuda_device, st, cf, limit, steps=400, B=4, T=20, X=500, dx=10, dt=0.25, rs=None, seed=3):
+def run(cuda_device, st, cf, limit, steps=400, B=4, T=20, X=500, dx=10, dt=0.25, rs=None, seed=3, rs_init=None):
     import torch
     import pdecontrolgym_b200 as pcg
     kw = dict(T=T, dt=dt, X=X, dx=dx)
+    if rs_init is not None:
+        kw["rs_init"] = rs_init          # 'outlet-train': the constructor's draw, which fixes the action bounds for good
     env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, simulation_type=st, control_freq=cf,
                    limit_pde_state_size=limit, reward_class=pcg.TrafficARZReward(), **kw)
     orc = O.TrafficARZOracle(B, simulation_type=st, control_freq=cf, limit_pde_state_size=limit, **kw)
@@ -46,7 +48,10 @@ def test_vs_oracle(cuda_device, st, cf, limit):
 
 
 def test_outlet_train(cuda_device):
-    run(cuda_device, "outlet-train", 2, False, rs=np.array([0.115, 0.12, 0.125, 0.12]))
+    """reset() re-draws rs / qs, but actions keep being clipped to the bounds built from the CONSTRUCTOR's draw
+    (traffic_arz_env.py:97-100 vs :251-256): every env here resets to an rs different from its construction-time one."""
+    run(cuda_device, "outlet-train", 2, False, rs=np.array([0.115, 0.12, 0.125, 0.12]), rs_init=np.array([0.125, 0.115, 0.12, 0.125]))
+    run(cuda_device, "outlet-train", 1, True, rs=np.array([0.12, 0.125, 0.115, 0.115]), rs_init=np.array([0.12, 0.12, 0.12, 0.12]), steps=120)
 
 
 @pytest.mark.parametrize("X,dx", [(100, 10), (310, 10), (640, 10), (500, 4), (500, 2), (500, 1.75), (500, 1.4), (500, 1.2), (500, 1)])   # ... 251, 287, 358, 418, 501 points
@@ -86,3 +91,33 @@ def test_errors(cuda_device):
         pcg.make("PDEControlGym-TrafficPDE1D", v_steady=11, **kw)
     with pytest.raises(AssertionError, match="control_freq"):
         pcg.make("PDEControlGym-TrafficPDE1D", control_freq=0, **kw)
+
+
+def test_fused_autoreset_final_obs(cuda_device):
+    """autoreset=True, final_obs=True: info['final_obs'] holds the terminal observation (the oracle's row of the step that
+    ended the episode) of the envs that restarted; the returned observation is the initial condition."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    B, kw = 5, dict(T=2, dt=0.25, X=500, dx=10)
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, simulation_type="outlet", autoreset=True, final_obs=True,
+                   reward_class=pcg.TrafficARZReward(), **kw)
+    orc = O.TrafficARZOracle(B, simulation_type="outlet", **kw)
+    o0, _ = env.reset()
+    ic = orc.reset()
+    rng = np.random.default_rng(0)
+    seen = 0
+    for k in range(40):
+        a = rng.uniform(1.0, 1.4, size=(B, 1))
+        o_r, r_r, te_r, tr_r = orc.step(a)
+        o_g, r_g, te_g, tr_g, info = env.step(torch.from_numpy(a))
+        done = te_r | tr_r
+        assert np.array_equal(te_g.cpu().numpy(), te_r) and np.array_equal(tr_g.cpu().numpy(), tr_r)
+        if done.any():
+            assert done.all()            # the float time ends every env's episode on the same step (T/dt = 8 -> step 32)
+            seen += 1
+            assert np.array_equal(info["final_obs"].cpu().numpy(), o_r), f"step {k}: terminal observation"
+            assert np.array_equal(o_g.cpu().numpy(), ic), f"step {k}: restarted observation"
+            orc.reset()
+        else:
+            assert np.array_equal(o_g.cpu().numpy(), o_r)
+    assert seen >= 1

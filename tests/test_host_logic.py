@@ -105,25 +105,47 @@ def test_batched_helpers_match_the_reference_formulas():
 
 
 class _FakeVecEnv:
-    """Minimal stand-in with the vector-env surface of this package (CPU tensors) for the adapter logic tests."""
+    """Minimal stand-in with the vector-env surface of this package (CPU tensors) for the adapter logic tests: env i counts
+    its own steps, observation = (episode step, env index), env 0 terminates every 3rd step, env 1 truncates every 2nd."""
 
-    def __init__(self, n=3, autoreset=True):
+    def __init__(self, n=3, autoreset=True, final_obs=True):
         import torch
-        self.num_envs, self.autoreset, self.t = n, autoreset, 0
+        self.num_envs, self.autoreset = n, autoreset
         self.single_observation_space = self.single_action_space = self.observation_space = self.action_space = None
         self._torch = torch
+        self.t = torch.zeros(n, dtype=torch.int64)
+        self._final = torch.zeros(n, 4) if (autoreset and final_obs) else None
+
+    def _obs(self):
+        return self._torch.stack([self.t.double(), self._torch.arange(self.num_envs).double(),
+                                  self._torch.zeros(self.num_envs).double(), self._torch.ones(self.num_envs).double()], dim=1).float()
 
     def reset(self, seed=None, options=None):
-        self.t = 0
-        return self._torch.zeros(self.num_envs, 4), {}
+        mask = (options or {}).get("mask")
+        if mask is None:
+            self.t.zero_()
+        else:
+            self.t[self._torch.as_tensor(mask).bool()] = 0
+        return self._obs(), {}
 
     def step(self, actions):
-        self.t += 1
         torch = self._torch
-        obs = torch.full((self.num_envs, 4), float(self.t))
-        term = torch.tensor([self.t % 3 == 0, False, False][:self.num_envs])
-        trunc = torch.tensor([False, self.t % 2 == 0, False][:self.num_envs])
-        return obs, torch.arange(self.num_envs, dtype=torch.float64), term, trunc, {"valid": torch.ones(self.num_envs, dtype=torch.bool)}
+        period = torch.tensor([3, 2, 10 ** 9][:self.num_envs])
+        finished = (self.t > 0) & (self.t % period == 0)          # stepping a finished env leaves it alone (like the CUDA envs)
+        self.t = torch.where(finished, self.t, self.t + 1)
+        hit = self.t % period == 0
+        term = hit & (torch.arange(self.num_envs) == 0)
+        trunc = hit & (torch.arange(self.num_envs) == 1)
+        info = {"valid": torch.ones(self.num_envs, dtype=torch.bool)}
+        obs = self._obs()
+        if self.autoreset:
+            done = term | trunc
+            if self._final is not None:
+                self._final = torch.where(done[:, None], obs, self._final)
+                info["final_obs"] = self._final
+            self.t = torch.where(done, torch.zeros_like(self.t), self.t)
+            obs = self._obs()
+        return obs, torch.arange(self.num_envs, dtype=torch.float64) + 1, term, trunc, info
 
     def close(self):
         self.closed = True
@@ -131,26 +153,36 @@ class _FakeVecEnv:
 
 def test_protocol_adapters_on_a_fake_env():
     from pdecontrolgym_b200.adapters import GymnasiumVectorAdapter, SB3VecEnvAdapter, TrajectoryRecorder
-    g = GymnasiumVectorAdapter(_FakeVecEnv())
-    obs, info = g.reset(seed=1)
-    assert isinstance(obs, np.ndarray) and obs.shape == (3, 4) and info == {}
-    obs, rew, term, trunc, info = g.step(np.zeros(3))
-    assert all(isinstance(x, np.ndarray) for x in (obs, rew, term, trunc, info["valid"])) and term.dtype == bool
+    from tests.vecenv_protocol import drive_gymnasium, drive_sb3
+    act = lambda k: np.zeros(3)  # noqa: E731
+    # gymnasium, same-step auto-reset: terminal observations in infos["final_obs"], new episode's first row in obs
+    log = drive_gymnasium(GymnasiumVectorAdapter(_FakeVecEnv()), act, 7, (4,))
+    obs, rew, term, trunc, infos = log[1]                          # step 2: env 1 truncated
+    assert trunc.tolist() == [False, True, False] and infos["final_obs"][1, 0] == 2 and obs[1, 0] == 0 and obs[0, 0] == 2
+    obs, rew, term, trunc, infos = log[2]                          # step 3: env 0 terminated
+    assert term.tolist() == [True, False, False] and infos["final_obs"][0, 0] == 3 and obs[0, 0] == 0
+    assert isinstance(infos["valid"], np.ndarray)
+    # gymnasium, next-step auto-reset (driven by the adapter on an env without auto-reset)
+    with pytest.raises(ValueError, match="autoreset=False"):
+        GymnasiumVectorAdapter(_FakeVecEnv(), autoreset_mode="next_step")
+    log = drive_gymnasium(GymnasiumVectorAdapter(_FakeVecEnv(autoreset=False), autoreset_mode="next_step"), act, 9, (4,))
+    assert log[1][3].tolist() == [False, True, False] and log[1][0][1, 0] == 2        # terminal row returned by the step itself
+    assert log[2][0][1, 0] == 0 and log[2][1][1] == 0 and log[2][2].tolist() == [True, False, False]
+    assert log[3][0][0, 0] == 0 and log[3][0][1, 0] == 1                               # env 0 reset, env 1 stepping again
+    # stable-baselines3
     with pytest.raises(ValueError, match="autoreset=True"):
         SB3VecEnvAdapter(_FakeVecEnv(autoreset=False))
+    log = drive_sb3(SB3VecEnvAdapter(_FakeVecEnv()), act, 7, (4,))
+    obs, rew, dones, infos = log[1]
+    assert dones.tolist() == [False, True, False] and infos[1]["TimeLimit.truncated"] and infos[1]["terminal_observation"][0] == 2
+    obs, rew, dones, infos = log[2]
+    assert dones.tolist() == [True, False, False] and not infos[0]["TimeLimit.truncated"] and infos[0]["terminal_observation"][0] == 3
     s = SB3VecEnvAdapter(_FakeVecEnv())
-    assert s.reset().shape == (3, 4)
-    s.step_async(np.zeros(3))
-    s.step_wait()
-    obs, rew, dones, infos = s.step(np.zeros(3))                  # t == 2: env 1 truncated
-    assert rew.dtype == np.float32 and dones.tolist() == [False, True, False]
-    assert [i["TimeLimit.truncated"] for i in infos] == [False, True, False]
-    obs, rew, dones, infos = s.step(np.zeros(3))                  # t == 3: env 0 terminated (not a time-limit truncation)
-    assert dones.tolist() == [True, False, False] and not infos[0]["TimeLimit.truncated"]
-    assert s.env_is_wrapped(object) == [False] * 3 and s.seed(7) == [7, 7, 7]
-    rec = TrajectoryRecorder(_FakeVecEnv(), max_steps=2)
+    assert s.seed(7) == [7, 7, 7]
+    rec = TrajectoryRecorder(_FakeVecEnv(autoreset=False), max_steps=2, extras=("t",))
     rec.reset()
     for _ in range(4):                                            # only the first max_steps steps are kept
         rec.step(None)
     h = rec.history()
-    assert h.shape == (3, 3, 4) and h[:, 0, 0].tolist() == [0.0, 1.0, 2.0]
+    assert h.shape == (3, 3, 4) and h[:, 2, 0].tolist() == [0.0, 1.0, 2.0]
+    assert rec.extra_history("t")[:, 2].tolist() == [0, 1, 2]
