@@ -361,7 +361,12 @@ typedef struct {
     uint8_t* valid;          /* [n_envs] 0 where the reference would raise IndexError (step past nt-1)      */
     double* final_obs;       /* optional, pdecg_ns_step_autoreset only: [n_envs, ny, nx, 2] terminal observation U[nt-1]
                                 of the envs that restart; other rows are left alone                                 */
+    void* work;              /* scratch of pdecg_ns_workspace_bytes(cfg, n_envs) bytes, needed only by grids beyond 4,096
+                                points per env (the HBM-resident path: u*, v*, (dx*dy)*rhs and the pressure ping-pong) */
 } pdecg_ns_buffers;
+
+/* Bytes of pdecg_ns_buffers::work this configuration needs for n_envs envs (0: the whole step lives on chip). */
+size_t pdecg_ns_workspace_bytes(const pdecg_ns_cfg* cfg, int64_t n_envs);
 
 /* NavierStokes2D.reset (:171-194): u, v, p <- init_* ([n_envs or 1, ny, nx]); time_index <- 0; obs <- U[0]. */
 int pdecg_ns_reset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* init_u,
@@ -384,9 +389,10 @@ int pdecg_ns_step_host(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, con
                        uint8_t* valid_host, const double* autoreset_u, const double* autoreset_v,
                        const double* autoreset_p, int64_t autoreset_env_stride, pdecg_stream_t stream);
 /* NavierStokes2D.solve_pressure (:94-116) alone, for callers such as examples/NavierStokes/NS2Doptimization.py:
- * p <- n_pressure_iters Jacobi sweeps on rhs = density/dt * (d u/dx + d v/dy), warm-started from p. */
+ * p <- n_pressure_iters Jacobi sweeps on rhs = density/dt * (d u/dx + d v/dy), warm-started from p.  `work`: scratch of
+ * pdecg_ns_workspace_bytes(cfg, n_envs) bytes (may be NULL when that is 0). */
 int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v,
-                            double* p, pdecg_stream_t stream);
+                            double* p, void* work, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Misc
@@ -407,6 +413,10 @@ int pdecg_probe_fp_issue(int32_t dtype, int32_t blocks, int32_t threads, int32_t
  * out_ref[i] = IEEE x[i] / d; the two must be bit-identical for every input (tests/test_gpu_constdiv.py). */
 int pdecg_selftest_constdiv(int32_t dtype, int64_t n, const void* x, double d, void* out_fast, void* out_ref,
                             pdecg_stream_t stream);
+
+/* Self-test of the correctly rounded exp() the BrainTumor kernels use for the radiation term exp(-alpha * BED)
+ * (brain_tumor_env.py:259-265): out[i] = exp_cr(x[i]) (tests/test_gpu_exp.py: bit-identical to mpmath's rounding). */
+int pdecg_selftest_exp(int64_t n, const double* x, double* out, pdecg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -312,3 +312,48 @@ int pdecg_oracle_ns_step(const pdecg_oracle_ns_cfg* c, int64_t n, double* u, dou
     }
     return 0;
 }
+
+
+/* ---- correctly rounded exp(): operation-for-operation restatement of exp_cr() in pdecontrolgym_b200/csrc/pdecg_common.cuh ----
+ * (double-double arithmetic, fixed order; compiled with -ffp-contract=off, fma() from libm).  tests/test_exp_cr.py compares
+ * it with mpmath's correctly rounded value; the GPU self-test compares the device function with this one bit for bit. */
+typedef struct { double hi, lo; } pdecg_dd;
+static pdecg_dd dd_quick(double a, double b) { pdecg_dd r; r.hi = a + b; r.lo = b + -(r.hi + -a); return r; }
+static pdecg_dd dd_add(pdecg_dd a, pdecg_dd b) {
+    const double s = a.hi + b.hi;
+    const double bb = s + -a.hi;
+    double e = (a.hi + -(s + -bb)) + (b.hi + -bb);
+    e = e + (a.lo + b.lo);
+    return dd_quick(s, e);
+}
+static pdecg_dd dd_mul(pdecg_dd a, pdecg_dd b) {
+    const double p = a.hi * b.hi;
+    double e = fma(a.hi, b.hi, -p);
+    e = e + ((a.hi * b.lo) + (a.lo * b.hi));
+    return dd_quick(p, e);
+}
+double pdecg_oracle_exp_cr(double x) {
+    if (x != x) return x;
+    if (x > 709.782712893384) return HUGE_VAL;
+    if (x < -745.1332191019412) return 0.0;
+    const double kf = rint(x * 0x1.71547652b82fep+0);
+    const pdecg_dd ln2 = {0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56};
+    pdecg_dd mk = {-kf, 0.0}, xx = {x, 0.0}, one = {1.0, 0.0};
+    pdecg_dd r = dd_add(xx, dd_mul(mk, ln2));
+    r.hi = r.hi * 0x1p-8;
+    r.lo = r.lo * 0x1p-8;
+    const pdecg_dd c[10] = {{0x1.ae64567f544e4p-26, -0x1.c062e06d1f209p-80}, {0x1.27e4fb7789f5cp-22, 0x1.cbbc05b4fa99ap-76},
+                            {0x1.71de3a556c734p-19, -0x1.c154f8ddc6c00p-73}, {0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-76},
+                            {0x1.a01a01a01a01ap-13, 0x1.a01a01a01a01ap-73}, {0x1.6c16c16c16c17p-10, -0x1.f49f49f49f49fp-65},
+                            {0x1.1111111111111p-7, 0x1.1111111111111p-63}, {0x1.5555555555555p-5, 0x1.5555555555555p-59},
+                            {0x1.5555555555555p-3, 0x1.5555555555555p-57}, {0x1.0000000000000p-1, 0.0}};
+    pdecg_dd acc = c[0];
+    for (int i = 1; i < 10; ++i) acc = dd_add(dd_mul(acc, r), c[i]);
+    acc = dd_add(dd_mul(acc, r), one);
+    acc = dd_add(dd_mul(acc, r), one);
+    for (int i = 0; i < 8; ++i) acc = dd_mul(acc, acc);
+    return scalbn(acc.hi + acc.lo, (int)kf);
+}
+void pdecg_oracle_exp_cr_array(const double* x, double* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = pdecg_oracle_exp_cr(x[i]);
+}

@@ -399,6 +399,18 @@ class TrafficARZOracle:
 GROWTH, THERAPY, POST = 0, 1, 2
 
 
+def _exp_cr(x):
+    """Correctly rounded exp via oracle/c/libpdecg_oracle.so (pdecg_oracle_exp_cr_array)."""
+    import ctypes
+    from oracle.c_oracle import lib as _load
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    L = _load()
+    L.pdecg_oracle_exp_cr_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    L.pdecg_oracle_exp_cr_array(x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
 class BrainTumorOracle:
     """`BrainTumor1D` (brain_tumor_env.py:33-384) + `BrainTumorReward` (brain_tumor_reward.py:31-73).
 
@@ -407,7 +419,11 @@ class BrainTumorOracle:
 
     def __init__(self, B, T, dt, X, dx, total_dosage, t1_detection_threshold=0.8,
                  t2_detection_threshold=0.16, dosage_termination_threshold=0.1, D=0.2, rho=0.03,
-                 alpha=0.04, alpha_beta_ratio=10, k=1e5, t1_detection_radius=15, t1_death_radius=35):
+                 alpha=0.04, alpha_beta_ratio=10, k=1e5, t1_detection_radius=15, t1_death_radius=35, exp="numpy"):
+        # exp: "numpy" -- np.exp, what the reference calls (:263; its last bit depends on the host CPU: glibc's exp or numpy's
+        # AVX512 kernel); "cr" -- the correctly rounded value (oracle/c restatement of the CUDA envs' exp_cr, checked against
+        # mpmath in tests/test_exp_cr.py): the CUDA BrainTumor1D is bit-identical to the oracle in this mode
+        self.exp = exp
         self.B = B
         self.T, self.dt, self.X, self.dx = T, dt, X, dx
         self.nt = int(round(T / dt) + 1)
@@ -492,7 +508,7 @@ class BrainTumorOracle:
                 d = np.zeros((1, self.nx))
                 d[0, self.xScale <= treatR] = applied
                 BED = d + ((d ** 2) / (self.abr))
-                R = 1.0 - np.exp(-self.alpha * BED)
+                R = 1.0 - (np.exp(-self.alpha * BED) if self.exp == "numpy" else _exp_cr(-self.alpha * BED))
                 nxt = self._fd_b(cur, sl, R)
                 self.u[b] = nxt[0]
                 if self.remaining[b] < self.dose_stop:

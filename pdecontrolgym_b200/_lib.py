@@ -105,7 +105,7 @@ class NsBuffers(C.Structure):
         ("n_envs", C.c_int64), ("u", C.c_void_p), ("v", C.c_void_p), ("p", C.c_void_p), ("obs", C.c_void_p),
         ("action", C.c_void_p), ("u_ref", C.c_void_p), ("action_ref", C.c_void_p), ("time_index", C.c_void_p),
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("valid", C.c_void_p),
-        ("final_obs", C.c_void_p),
+        ("final_obs", C.c_void_p), ("work", C.c_void_p),
     ]
 
 
@@ -169,10 +169,14 @@ def lib():
     L.pdecg_ns_step_autoreset.restype = C.c_int
     L.pdecg_ns_step_host.argtypes = [C.POINTER(NsCfg), C.POINTER(NsBuffers)] + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p]
     L.pdecg_ns_step_host.restype = C.c_int
-    L.pdecg_ns_solve_pressure.argtypes = [C.POINTER(NsCfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdecg_ns_solve_pressure.argtypes = [C.POINTER(NsCfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_ns_solve_pressure.restype = C.c_int
+    L.pdecg_ns_workspace_bytes.argtypes = [C.POINTER(NsCfg), C.c_int64]
+    L.pdecg_ns_workspace_bytes.restype = C.c_size_t
     L.pdecg_selftest_constdiv.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_selftest_constdiv.restype = C.c_int
+    L.pdecg_selftest_exp.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdecg_selftest_exp.restype = C.c_int
     L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double), C.c_void_p]
     L.pdecg_probe_fp_issue.restype = C.c_int

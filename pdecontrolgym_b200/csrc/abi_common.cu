@@ -55,9 +55,21 @@ __global__ void constdiv_selftest_kernel(const T* __restrict__ x, T d, T* __rest
     }
 }
 
+__global__ void exp_selftest_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) out[i] = exp_cr(x[i]);
+}
+
 }  // namespace pdecg
 
 using namespace pdecg;
+
+extern "C" int pdecg_selftest_exp(int64_t n, const double* x, double* out, pdecg_stream_t stream) {
+    if (n < 0 || (n > 0 && (!x || !out))) return fail(PDECG_ERR_INVALID, "bad arguments");
+    if (n == 0) return PDECG_OK;
+    exp_selftest_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n);
+    count_launch();
+    return check_launch("exp_selftest_kernel");
+}
 
 extern "C" int pdecg_selftest_constdiv(int32_t dtype, int64_t n, const void* x, double d, void* out_fast, void* out_ref,
                                        pdecg_stream_t stream) {

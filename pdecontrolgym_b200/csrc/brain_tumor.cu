@@ -260,7 +260,7 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
         double rin = 0.0;
         if (applied != 0.0) {
             const double bed = __dadd_rn(applied, __ddiv_rn(__dmul_rn(applied, applied), cfg.alpha_beta_ratio));
-            rin = __dsub_rn(1.0, exp(__dmul_rn(-cfg.alpha, bed)));
+            rin = __dsub_rn(1.0, exp_cr(__dmul_rn(-cfg.alpha, bed)));     // correctly rounded (pdecg_common.cuh)
         }
         if constexpr (XSREG) {
             if (dv.dx2_one) bt_fd<K, true, true, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, rin, treat_r, xs, a.buf.x_scale);

@@ -59,6 +59,12 @@ __device__ __forceinline__ void ns_reset_env(const NsArgs& a, const double* __re
     }
 }
 
+// navier_stokes_large.cu: the HBM-resident path for grids beyond kNsMaxPoints
+size_t ns_large_workspace_bytes(const pdecg_ns_cfg* cfg, int64_t n_envs);
+int ns_large_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, const double* ar_u, const double* ar_v, const double* ar_p,
+                  int64_t ar_stride, cudaStream_t st);
+int ns_large_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v, double* p, void* work, cudaStream_t st);
+
 using D = Strict<double>;
 constexpr int kNsThreads = 256;
 constexpr int kNsMaxPoints = 4096;   // 7 fields x 4096 x 8 B = 224 KB of the 227 KB an sm_100a CTA may use
@@ -298,32 +304,48 @@ __global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// Specialised kernel for the reference grid (nx = ny = N+2): ONE WARP = ONE ENV, Jacobi in registers.
+// Specialised kernel for the reference grid (nx = ny = N+2): a (half-)WARP = ONE ENV, Jacobi in registers.
 //
-// The N x N interior is tiled over the lanes as an RG x CG grid of BR x BC blocks (N=19: 10 x 3 lanes,
-// 2 x 7 points each, 30 of 32 lanes).  By the sweep identity above, after the first sweep every boundary
-// value is a copy of the nearest interior value, so sweeps 2..n only need the interior with CLAMPED
-// neighbours: inside a block neighbours are registers, across blocks they come from 2(BR+BC) f64 shuffles
-// per sweep, and the clamps are selects with four lane-uniform predicates at compile-time slots.  No
-// barrier and no shared-memory traffic inside the 2000-sweep loop: 5 DADD/DMUL per point per sweep.
-// The first sweep reads the true boundary values of the warm-start pressure from shared memory, so an
-// arbitrary initial pressure field is handled exactly.
-template <int N, int BR, int BC, int RG, int CG, int WPB>
+// The N x N interior is tiled over the LPE lanes of an env as an RG x CG grid of BR x BC blocks:
+//   LPE = 16 (two envs per warp), N = 19: 4 x 4 lanes, 5 x 5 points each -- 400 lane-slots for 361 points, 20 halo
+//            values per env-sweep.  One warp-sweep (two envs) is 125 DADD/DMUL + 40 SHFL + 40 FSEL.
+//   LPE = 32 (one env per warp),   N = 19: 10 x 3 lanes, 2 x 7 points each -- 448 lane-slots (30 of 32 lanes), 18 halo
+//            values: 70 DADD/DMUL + 36 SHFL + 36 FSEL per env-sweep (the round-1 mapping, kept for A/B runs).
+// The FP64 pipe issues 16 lanes per clock per SM sub-partition, so the half-warp mapping needs 125 x 2 = 250 pipe cycles
+// per TWO envs against 70 x 2 = 140 per ONE: 1.12x fewer FP64 slots per env, 1.8x fewer shuffles -- and at the BASELINE
+// batch (1,024 envs = 512 warps on 592 sub-partitions) no sub-partition hosts more than one warp, where the one-env
+// mapping put two warps on most of them (7 warps per SM).
+// By the sweep identity above, after the first sweep every boundary value is a copy of the nearest interior value, so
+// sweeps 2..n only need the interior with CLAMPED neighbours: inside a block neighbours are registers, across blocks
+// they come from 2(BR+BC) f64 shuffles per sweep (segment-wide: width = LPE), and the clamps are selects on the halo
+// values under four lane-uniform predicates.  No barrier and no shared-memory traffic inside the 2000-sweep loop:
+// 5 DADD/DMUL per point per sweep.  The first sweep reads the true boundary values of the warm-start pressure from
+// shared memory, so an arbitrary initial pressure field is handled exactly.
+// All 32 lanes run the whole kernel in lock step whatever their env's state: a segment whose env does not exist or
+// is past its last step computes on zeros and stores nothing, so every shuffle / barrier names the full warp.
+template <int N, int BR, int BC, int RG, int CG, int WPB, int LPE>
 __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) {
-    static_assert(RG * CG <= 32 && RG * BR >= N && CG * BC >= N, "bad tiling");
-    constexpr int NX = N + 2, NPT = NX * NX;
+    static_assert(LPE == 32 || LPE == 16, "32 or 16 lanes per env");
+    static_assert(RG * CG <= LPE && RG * BR >= N && CG * BC >= N, "bad tiling");
+    constexpr int NX = N + 2, NPT = NX * NX, EPW = 32 / LPE;
     extern __shared__ double smem[];
     const pdecg_ns_cfg& cfg = a.cfg;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * WPB + wib;
-    if (env >= a.buf.n_envs) return;
-    double* f0 = smem + static_cast<size_t>(wib) * 4 * NPT;   // u   -> (dx*dy)*rhs
+    const int lane = threadIdx.x & (LPE - 1), wib = threadIdx.x >> 5;
+    const int seg = (threadIdx.x & 31) / LPE;
+    const unsigned segmask = seg_mask<LPE>(threadIdx.x & 31);
+    const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * WPB + wib) * EPW;
+    if (env0 >= a.buf.n_envs) return;                          // warp-uniform
+    const int64_t env = env0 + seg;
+    const bool exists = env < a.buf.n_envs;
+    double* f0 = smem + static_cast<size_t>(wib * EPW + seg) * 4 * NPT;   // u   -> (dx*dy)*rhs
     double* f1 = f0 + NPT;                                     // v   -> pressure
     double* f2 = f1 + NPT;                                     // u*  -> u_next
     double* f3 = f2 + NPT;                                     // v*  -> v_next
 
-    const int t0 = a.buf.time_index[env];
-    if (t0 + 1 >= cfg.nt || t0 + 1 >= cfg.n_uref || t0 + 1 >= cfg.n_action_ref) {
+    const int t0 = exists ? a.buf.time_index[env] : 0;
+    const bool stale = exists && (t0 + 1 >= cfg.nt || t0 + 1 >= cfg.n_uref || t0 + 1 >= cfg.n_action_ref);
+    const bool live = exists && !stale;
+    if (stale) {                                               // the reference raises IndexError here (segment-uniform)
         if (lane == 0) {
             if (a.buf.valid) a.buf.valid[env] = 0;
             a.buf.terminated[env] = 1;
@@ -332,22 +354,24 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
         }
         if (a.ar_u != nullptr) {
             if (a.buf.final_obs != nullptr) {        // terminal observation = the (unchanged) current U[t]
-                for (int q = lane; q < 2 * NPT; q += 32) a.buf.final_obs[env * NPT * 2 + q] = a.buf.obs[env * NPT * 2 + q];
-                __syncwarp();
+                for (int q = lane; q < 2 * NPT; q += LPE) a.buf.final_obs[env * NPT * 2 + q] = a.buf.obs[env * NPT * 2 + q];
+                __syncwarp(segmask);
             }
-            ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, 32, true);
+            ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, LPE, true);
         }
-        return;
     }
+    __syncwarp();
+    if (!__any_sync(kFull, live)) return;                      // warp-uniform
     const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
     const double dxdy = D::mul(cfg.dx, cfg.dy);
     const ConstDiv<double> by_2dx(two_dx), by_2dy(two_dy), by_dxdy(dxdy);
-    double* gu = a.buf.u + env * NPT;
-    double* gv = a.buf.v + env * NPT;
-    double* gp = a.buf.p + env * NPT;
-    const double action = a.buf.action[env];
+    const int64_t envc = live ? env : 0;                       // pointers of a non-live segment are never dereferenced
+    double* gu = a.buf.u + envc * NPT;
+    double* gv = a.buf.v + envc * NPT;
+    double* gp = a.buf.p + envc * NPT;
+    const double action = live ? a.buf.action[env] : 0.0;
 
-    for (int q = lane; q < NPT; q += 32) { f0[q] = gu[q]; f1[q] = gv[q]; }
+    for (int q = lane; q < NPT; q += LPE) { f0[q] = live ? gu[q] : 0.0; f1[q] = live ? gv[q] : 0.0; }
     __syncwarp();
     auto interior = [](int q) { const int i = q / NX, j = q - i * NX; return i >= 1 && i <= N && j >= 1 && j <= N; };
     auto cdx = [&](const double* f, int q) { return by_2dx(D::sub(f[q + 1], f[q - 1])); };
@@ -360,7 +384,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
         return by_dxdy(s);
     };
     // ---- predictor (:130-138) ----
-    for (int q = lane; q < NPT; q += 32) {
+    for (int q = lane; q < NPT; q += LPE) {
         double us = f0[q], vs = f1[q];
         if (interior(q)) {
             const double u0 = us, v0 = vs;
@@ -379,8 +403,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
             for (int comp = 0; comp < 2; ++comp) {
                 double* f = comp == 0 ? fu : fv;
                 const int cond = cfg.bc[side][comp];
-                if (lane < NX) {
-                    const int q = lane;
+                for (int q = lane; q < NX; q += LPE) {
                     int dst, src;
                     if (side == PDECG_NS_LOWER) { dst = q; src = NX + q; }
                     else if (side == PDECG_NS_UPPER) { dst = (NX - 1) * NX + q; src = (NX - 2) * NX + q; }
@@ -397,9 +420,9 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
     apply_bc(f2, f3);
     // ---- (dx*dy)*rhs into f0, warm-start pressure into f1 ----
     const double rho_dt = D::div(cfg.density, cfg.dt);
-    for (int q = lane; q < NPT; q += 32) {
+    for (int q = lane; q < NPT; q += LPE) {
         f0[q] = interior(q) ? D::mul(dxdy, D::mul(rho_dt, D::add(cdx(f2, q), cdy(f3, q)))) : 0.0;
-        f1[q] = gp[q];
+        f1[q] = live ? gp[q] : 0.0;
     }
     __syncwarp();
 
@@ -425,37 +448,66 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
         constexpr int RLAST = (N - 1) / BR, RSLOT = (N - 1) % BR;     // block / slot holding interior row N-1
         constexpr int CLAST = (N - 1) / BC, CSLOT = (N - 1) % BC;
         const bool top = rg == 0, bottom = rg == RLAST, leftmost = cg == 0, rightmost = cg == CLAST;
-        for (int it = 1; it < cfg.n_pressure_iters; ++it) {
-            double up_h[BC], dn_h[BC], lf_h[BR], rt_h[BR];
+        // Halo values of a block (the neighbouring blocks' edge rows / columns); the clamp at the domain edge is a select
+        // on the halo: the neighbour beyond the edge is the point itself.
+        struct Halo { double up[BC], dn[BC], lf[BR], rt[BR]; };
+        auto exchange_rows = [&](const double (&src)[BR][BC], Halo& h) {
 #pragma unroll
             for (int cc = 0; cc < BC; ++cc) {
-                up_h[cc] = __shfl_up_sync(kFull, p[BR - 1][cc], CG);
-                dn_h[cc] = __shfl_down_sync(kFull, p[0][cc], CG);
+                h.up[cc] = __shfl_up_sync(kFull, src[BR - 1][cc], CG, LPE);
+                h.dn[cc] = __shfl_down_sync(kFull, src[0][cc], CG, LPE);
+                h.up[cc] = top ? src[0][cc] : h.up[cc];
+                if constexpr (RSLOT == BR - 1) h.dn[cc] = bottom ? src[BR - 1][cc] : h.dn[cc];
             }
+        };
+        auto exchange_cols = [&](const double (&src)[BR][BC], Halo& h) {
 #pragma unroll
             for (int rr = 0; rr < BR; ++rr) {
-                lf_h[rr] = __shfl_up_sync(kFull, p[rr][BC - 1], 1);
-                rt_h[rr] = __shfl_down_sync(kFull, p[rr][0], 1);
+                h.lf[rr] = __shfl_up_sync(kFull, src[rr][BC - 1], 1, LPE);
+                h.rt[rr] = __shfl_down_sync(kFull, src[rr][0], 1, LPE);
+                h.lf[rr] = leftmost ? src[rr][0] : h.lf[rr];
+                if constexpr (CSLOT == BC - 1) h.rt[rr] = rightmost ? src[rr][BC - 1] : h.rt[rr];
             }
-            double n[BR][BC];
+        };
+        auto exchange = [&](const double (&src)[BR][BC], Halo& h) { exchange_rows(src, h); exchange_cols(src, h); };
+        auto point = [&](const double (&src)[BR][BC], const Halo& h, int rr, int cc) {
+            const double self = src[rr][cc];
+            const double up = (rr > 0) ? src[rr > 0 ? rr - 1 : 0][cc] : h.up[cc];
+            double dn = (rr < BR - 1) ? src[rr < BR - 1 ? rr + 1 : 0][cc] : h.dn[cc];
+            if constexpr (RSLOT < BR - 1) { if (rr == RSLOT) dn = bottom ? self : dn; }
+            const double lf = (cc > 0) ? src[rr][cc > 0 ? cc - 1 : 0] : h.lf[rr];
+            double rt = (cc < BC - 1) ? src[rr][cc < BC - 1 ? cc + 1 : 0] : h.rt[rr];
+            if constexpr (CSLOT < BC - 1) { if (cc == CSLOT) rt = rightmost ? self : rt; }
+            double acc = D::add(lf, up);             // ((left + up) + right) + down
+            acc = D::add(acc, rt);
+            acc = D::add(acc, dn);
+            return D::mul(0.25, D::sub(acc, b[rr][cc]));
+        };
+        // One sweep `src` (with its halo `hs`) -> `dst` (and its halo `hd`).  The block's EDGE points come first and
+        // their shuffles are issued at once; the interior points, which need no halo, are computed while the shuffles
+        // are in flight: the sweep-to-sweep recurrence (edge values -> shuffle -> edge values) overlaps with them.
+        auto sweep = [&](const double (&src)[BR][BC], const Halo& hs, double (&dst)[BR][BC], Halo& hd) {
 #pragma unroll
             for (int rr = 0; rr < BR; ++rr)
 #pragma unroll
-                for (int cc = 0; cc < BC; ++cc) {
-                    const double self = p[rr][cc];
-                    double up = (rr > 0) ? p[rr > 0 ? rr - 1 : 0][cc] : up_h[cc];
-                    if (rr == 0) up = top ? self : up;
-                    double dn = (rr < BR - 1) ? p[rr < BR - 1 ? rr + 1 : 0][cc] : dn_h[cc];
-                    if (rr == RSLOT) dn = bottom ? self : dn;
-                    double lf = (cc > 0) ? p[rr][cc > 0 ? cc - 1 : 0] : lf_h[rr];
-                    if (cc == 0) lf = leftmost ? self : lf;
-                    double rt = (cc < BC - 1) ? p[rr][cc < BC - 1 ? cc + 1 : 0] : rt_h[rr];
-                    if (cc == CSLOT) rt = rightmost ? self : rt;
-                    double acc = D::add(lf, up);             // ((left + up) + right) + down
-                    acc = D::add(acc, rt);
-                    acc = D::add(acc, dn);
-                    n[rr][cc] = D::mul(0.25, D::sub(acc, b[rr][cc]));
-                }
+                for (int cc = 0; cc < BC; ++cc)
+                    if (rr == 0 || rr == BR - 1 || cc == 0 || cc == BC - 1) dst[rr][cc] = point(src, hs, rr, cc);
+            exchange(dst, hd);
+#pragma unroll
+            for (int rr = 1; rr < BR - 1; ++rr)
+#pragma unroll
+                for (int cc = 1; cc < BC - 1; ++cc) dst[rr][cc] = point(src, hs, rr, cc);
+        };
+        double n[BR][BC];
+        Halo hp, hn;
+        if (cfg.n_pressure_iters > 1) exchange(p, hp);
+        int it = 1;
+        for (; it + 2 <= cfg.n_pressure_iters; it += 2) {   // register ping-pong: no copies in the steady state
+            sweep(p, hp, n, hn);
+            sweep(n, hn, p, hp);
+        }
+        if (it < cfg.n_pressure_iters) {
+            sweep(p, hp, n, hn);
 #pragma unroll
             for (int rr = 0; rr < BR; ++rr)
 #pragma unroll
@@ -471,7 +523,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
             }
         __syncwarp();
         // boundary values = nearest interior value (the four Neumann copies of :110-113, in their order)
-        for (int q = lane; q < NPT; q += 32) {
+        for (int q = lane; q < NPT; q += LPE) {
             if (!interior(q)) {
                 const int i = q / NX, j = q - i * NX;
                 f1[q] = f1[clampi(i, 1, N) * NX + clampi(j, 1, N)];
@@ -482,7 +534,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
 
     // ---- corrector (:143-146) ----
     const double dt_rho = D::div(cfg.dt, cfg.density);
-    for (int q = lane; q < NPT; q += 32) {
+    for (int q = lane; q < NPT; q += LPE) {
         if (interior(q)) {
             f2[q] = D::sub(f2[q], D::mul(dt_rho, cdx(f1, q)));
             f3[q] = D::sub(f3[q], D::mul(dt_rho, cdy(f1, q)));
@@ -493,24 +545,26 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
 
     // ---- store, observation U[t], reward ----
     const int t1 = t0 + 1;
-    const double* uref = a.buf.u_ref + static_cast<int64_t>(t1) * NPT * 2;
-    double* gobs = a.buf.obs + env * NPT * 2;
+    const double* uref = a.buf.u_ref + static_cast<int64_t>(live ? t1 : 0) * NPT * 2;
+    double* gobs = a.buf.obs + envc * NPT * 2;
     double ss = 0.0;
-    for (int q = lane; q < NPT; q += 32) {
-        const double un = f2[q], vn = f3[q];
-        gu[q] = un;
-        gv[q] = vn;
-        gp[q] = f1[q];
-        const double du = D::sub(un, uref[2 * q]), dv = D::sub(vn, uref[2 * q + 1]);
-        ss += du * du;
-        ss += dv * dv;
+    if (live) {
+        for (int q = lane; q < NPT; q += LPE) {
+            const double un = f2[q], vn = f3[q];
+            gu[q] = un;
+            gv[q] = vn;
+            gp[q] = f1[q];
+            const double du = D::sub(un, uref[2 * q]), dv = D::sub(vn, uref[2 * q + 1]);
+            ss += du * du;
+            ss += dv * dv;
+        }
+        // interleaved (u, v) observation: coalesced 16-byte pairs
+        for (int q = lane; q < NPT; q += LPE) {
+            reinterpret_cast<double2*>(gobs)[q] = make_double2(f2[q], f3[q]);
+        }
     }
-    // interleaved (u, v) observation: coalesced 16-byte pairs
-    for (int q = lane; q < NPT; q += 32) {
-        reinterpret_cast<double2*>(gobs)[q] = make_double2(f2[q], f3[q]);
-    }
-    ss = warp_sum(ss);
-    if (lane == 0) {
+    ss = seg_sum<LPE>(ss);                                     // full-warp mask: every lane is here
+    if (live && lane == 0) {
         const double nrm = sqrt(ss);
         double r1 = D::div(D::div(D::mul(-0.5, D::mul(nrm, nrm)), static_cast<double>(NX)), static_cast<double>(NX));
         const double da = fabs(D::sub(action, a.buf.action_ref[t1]));
@@ -521,13 +575,13 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
         a.buf.truncated[env] = 0;
         if (a.buf.valid) a.buf.valid[env] = 1;
     }
-    if (a.ar_u != nullptr && t1 >= cfg.nt - 1) {          // same-step auto-reset (warp-uniform condition)
+    if (live && a.ar_u != nullptr && t1 >= cfg.nt - 1) {  // same-step auto-reset (segment-uniform condition)
         if (a.buf.final_obs != nullptr) {                 // terminal observation U[nt-1] for the caller
             double2* fobs = reinterpret_cast<double2*>(a.buf.final_obs + env * NPT * 2);
-            for (int q = lane; q < NPT; q += 32) fobs[q] = make_double2(f2[q], f3[q]);
+            for (int q = lane; q < NPT; q += LPE) fobs[q] = make_double2(f2[q], f3[q]);
         }
-        __syncwarp();                                     // the step's own field / observation stores come first
-        ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, 32, true);
+        __syncwarp(segmask);                              // the step's own field / observation stores come first
+        ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, LPE, true);
     }
 }
 
@@ -535,13 +589,19 @@ static int ns_validate_cfg(const pdecg_ns_cfg* cfg) {
     if (!cfg) return fail(PDECG_ERR_INVALID, "null cfg");
     if (cfg->abi_version != PDECG_ABI_VERSION) return fail(PDECG_ERR_INVALID, "abi_version mismatch");
     if (cfg->nx < 3 || cfg->ny < 3) return fail(PDECG_ERR_INVALID, "need nx, ny >= 3");
-    if (cfg->nx * cfg->ny > kNsMaxPoints) return fail(PDECG_ERR_UNSUPPORTED, "grid %dx%d exceeds the shared-memory-resident limit of %d points per env", cfg->nx, cfg->ny, kNsMaxPoints);
+    if (cfg->nx > 8192 || cfg->ny > 8192) return fail(PDECG_ERR_UNSUPPORTED, "grid %dx%d exceeds the limit of 8192 points per direction", cfg->nx, cfg->ny);
     if (cfg->n_pressure_iters < 0) return fail(PDECG_ERR_INVALID, "maximum_pressure_iteration < 0");
     if (!(cfg->dt > 0) || !(cfg->dx > 0) || !(cfg->dy > 0)) return fail(PDECG_ERR_INVALID, "dt, dx, dy must be positive");
     for (int s = 0; s < 4; ++s)
         for (int c = 0; c < 2; ++c)
             if (cfg->bc[s][c] < PDECG_NS_DIRICHLET || cfg->bc[s][c] > PDECG_NS_CONTROLLABLE) return fail(PDECG_ERR_INVALID, "bad boundary condition code");
     return PDECG_OK;
+}
+
+// Grids of more than kNsMaxPoints points per env (or any grid with PDECG_NS_TILED set: A/B runs, tests) take the
+// HBM-resident path of navier_stokes_large.cu; everything else stays on chip for the whole step.
+static bool ns_use_large(const pdecg_ns_cfg* cfg) {
+    return cfg->nx * cfg->ny > kNsMaxPoints || getenv("PDECG_NS_TILED") != nullptr;
 }
 
 static size_t ns_smem_bytes(const pdecg_ns_cfg* cfg) { return static_cast<size_t>(7) * cfg->nx * cfg->ny * sizeof(double); }
@@ -590,19 +650,26 @@ static int ns_launch_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, 
     if (buf->n_envs == 0) return PDECG_OK;
     if (!buf->u || !buf->v || !buf->p || !buf->obs || !buf->action || !buf->u_ref || !buf->action_ref || !buf->time_index || !buf->reward || !buf->terminated || !buf->truncated)
         return fail(PDECG_ERR_INVALID, "null device buffer");
+    if (ns_use_large(cfg)) return ns_large_step(cfg, buf, ar_u, ar_v, ar_p, ar_stride, static_cast<cudaStream_t>(stream));
     NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0, ar_u, ar_v, ar_p, ar_stride};
     if (cfg->nx == 21 && cfg->ny == 21 && !getenv("PDECG_NS_GENERIC")) {
-        // the reference grid (examples/NavierStokes/NS2Dppo.py:29-32): warp-per-env register kernel
+        // the reference grid (examples/NavierStokes/NS2Dppo.py:29-32): register-resident kernel, two envs per warp
+        // (4 x 4 lanes of 5 x 5 points each); PDECG_NS_LPE32 selects the one-env-per-warp mapping (10 x 3 lanes of 2 x 7).
         // Warps never cooperate, so the CTA size only sets the scheduling granularity: small batches (fewer warps than
         // the GPU can hold at full rate) use one-warp CTAs so that the block scheduler spreads them evenly over the SMs.
         constexpr int kN = 19;
-        const bool small = (buf->n_envs < 148 * 16 || getenv("PDECG_NS_WPB1")) && !getenv("PDECG_NS_WPB4");
+        const bool lpe32 = getenv("PDECG_NS_LPE32") != nullptr;
+        const int epw = lpe32 ? 1 : 2;
+        const int64_t warps = (buf->n_envs + epw - 1) / epw;
+        const bool small = (warps < 148 * 16 || getenv("PDECG_NS_WPB1")) && !getenv("PDECG_NS_WPB4");
         const int wpb = small ? 1 : kWarpsPerBlock;
-        const size_t smem_w = static_cast<size_t>(wpb) * 4 * (kN + 2) * (kN + 2) * sizeof(double);
-        auto kern = small ? ns_step_warp_kernel<kN, 2, 7, 10, 3, 1> : ns_step_warp_kernel<kN, 2, 7, 10, 3, kWarpsPerBlock>;
+        const size_t smem_w = static_cast<size_t>(wpb) * epw * 4 * (kN + 2) * (kN + 2) * sizeof(double);
+        void (*kern)(const NsArgs);
+        if (lpe32) kern = small ? ns_step_warp_kernel<kN, 2, 7, 10, 3, 1, 32> : ns_step_warp_kernel<kN, 2, 7, 10, 3, kWarpsPerBlock, 32>;
+        else kern = small ? ns_step_warp_kernel<kN, 5, 5, 4, 4, 1, 16> : ns_step_warp_kernel<kN, 5, 5, 4, 4, kWarpsPerBlock, 16>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_w));
         if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        const unsigned grid = static_cast<unsigned>((buf->n_envs + wpb - 1) / wpb);
+        const unsigned grid = static_cast<unsigned>((warps + wpb - 1) / wpb);
         kern<<<grid, wpb * 32, smem_w, static_cast<cudaStream_t>(stream)>>>(a);
         count_launch();
         return check_launch("ns_step_warp_kernel");
@@ -620,13 +687,19 @@ extern "C" int pdecg_ns_step_autoreset(const pdecg_ns_cfg* cfg, const pdecg_ns_b
     return ns_launch_step(cfg, buf, init_u, init_v, init_p, init_env_stride, stream);
 }
 
+extern "C" size_t pdecg_ns_workspace_bytes(const pdecg_ns_cfg* cfg, int64_t n_envs) {
+    if (!cfg || n_envs <= 0 || cfg->nx < 3 || cfg->ny < 3 || !ns_use_large(cfg)) return 0;
+    return ns_large_workspace_bytes(cfg, n_envs);
+}
+
 extern "C" int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const double* u, const double* v, double* p,
-                                       pdecg_stream_t stream) {
+                                       void* work, pdecg_stream_t stream) {
     int rc = ns_validate_cfg(cfg);
     if (rc != PDECG_OK) return rc;
     if (n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (n_envs == 0) return PDECG_OK;
     if (!u || !v || !p) return fail(PDECG_ERR_INVALID, "null device buffer");
+    if (ns_use_large(cfg)) return ns_large_solve_pressure(cfg, n_envs, u, v, p, work, static_cast<cudaStream_t>(stream));
     NsArgs a{};
     a.cfg = *cfg;
     a.buf.n_envs = n_envs;

@@ -118,6 +118,11 @@ class NavierStokes2D(StateDictMixin):
         buf.u_ref, buf.action_ref = self.U_ref.data_ptr(), self.action_ref.data_ptr()
         buf.time_index, buf.reward = self.time_index.data_ptr(), self._reward.data_ptr()
         buf.terminated, buf.truncated, buf.valid = self._terminated.data_ptr(), self._truncated.data_ptr(), self._valid.data_ptr()
+        # grids beyond 64 x 64 do not fit one SM's shared memory: their step streams tiles through HBM and needs scratch
+        # (predictor fields, right-hand side, pressure ping-pong), owned here like every other device buffer
+        wbytes = int(self._L.pdecg_ns_workspace_bytes(C.byref(cfg), N))
+        self._work = torch.empty((wbytes + 7) // 8, dtype=torch.float64, device=dev) if wbytes else None
+        buf.work = None if self._work is None else self._work.data_ptr()
         self._buf = buf
         self._reset_done = False
         self.single_observation_space = Box(np.full((self.nx, self.ny, 2), -np.inf, dtype="float32"),
@@ -242,8 +247,11 @@ class NavierStokes2D(StateDictMixin):
         """Batched `solve_pressure` (navier_stokes2D.py:94-116) for external callers; returns the new p."""
         u, v = self._field(u, "u"), self._field(v, "v")
         p = self._field(p_prev, "p_prev").clone()
+        wbytes = int(self._L.pdecg_ns_workspace_bytes(C.byref(self._cfg), u.shape[0]))
+        work = torch.empty((wbytes + 7) // 8, dtype=torch.float64, device=self.device) if wbytes else None
         with torch.cuda.device(self.device):
-            _lib.check(self._L.pdecg_ns_solve_pressure(C.byref(self._cfg), u.shape[0], u.data_ptr(), v.data_ptr(), p.data_ptr(), self._stream()))
+            _lib.check(self._L.pdecg_ns_solve_pressure(C.byref(self._cfg), u.shape[0], u.data_ptr(), v.data_ptr(), p.data_ptr(),
+                                                       None if work is None else work.data_ptr(), self._stream()))
         return p
 
     @property

@@ -79,4 +79,18 @@ elif which == "ns_large":
     a = torch.empty(N, dtype=torch.float64, device=dev).uniform_(2, 4)
     for _ in range(3):
         env.step(a)
+elif which == "ns_tiled":
+    # 512 x 512: the HBM-resident path (navier_stokes_large.cu); 101 sweeps = 1 plain + 10 tiled launches of 10
+    N, n = 96, 512
+    h = 1.0 / (n - 1)
+    dt = 1e-3 * (h / 0.05) ** 2
+    bc = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
+    env = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=dev, boundary_condition=bc, U_ref=np.zeros((8, n, n, 2)),
+                   action_ref=2.0 * np.ones(1000), reward_class=pcg.NSReward(0.1), action_dim=1, maximum_pressure_iteration=101, T=100 * dt, dt=dt,
+                   X=1, dx=h, Y=1, dy=h, copy_obs=False)
+    c = torch.empty(3, N, 1, 1, dtype=torch.float64, device=dev).uniform_(-5, 5) * torch.ones(1, n, n, dtype=torch.float64, device=dev)
+    env.reset(options={"init": (c[0], c[1], c[2])})
+    a = torch.empty(N, dtype=torch.float64, device=dev).uniform_(2, 4)
+    for _ in range(2):
+        env.step(a)
 torch.cuda.synchronize()

@@ -110,9 +110,13 @@ def test_invalid_configs_are_rejected_without_a_gpu(lib):
     assert L.pdecg_ns_step(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None) == lib.OK          # n_envs == 0
     ncfg.nx = ncfg.ny = 64
     assert L.pdecg_ns_step(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None) == lib.OK          # 4,096 points still fit
-    ncfg.nx = ncfg.ny = 65
+    assert L.pdecg_ns_workspace_bytes(ctypes.byref(ncfg), 10) == 0                                      # lives on chip
+    ncfg.nx = ncfg.ny = 65                                                                             # HBM-resident path: needs scratch
+    assert L.pdecg_ns_workspace_bytes(ctypes.byref(ncfg), 10) == 10 * (2 * 65 * 65 + 3 * 76 * 76) * 8 + 256
+    assert L.pdecg_ns_step(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None) == lib.OK          # n_envs == 0
+    ncfg.nx = ncfg.ny = 8193
     assert L.pdecg_ns_step(ctypes.byref(ncfg), ctypes.byref(lib.NsBuffers()), None) == lib.ERR_UNSUPPORTED
-    assert b"shared-memory-resident" in L.pdecg_last_error()
+    assert b"exceeds the limit" in L.pdecg_last_error()
 
 
 def test_no_cpu_fallback():

@@ -370,10 +370,12 @@ def test_therapy_wrapper_masked_reset_keeps_the_other_patients(cuda_device):
     weekends=True -- keep their consecutive-treatment-day counter, so their forced rest days land where the oracle's do."""
     import torch
     import pdecontrolgym_b200 as pcg
+    from oracle import np_oracle as O
     from tests.golden.gen_golden import BT_P, bt_ic
     N = 4
     ic = bt_ic(200, 201)
-    env = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, reward_class=pcg.BrainTumorReward(), **BT_P)
+    env = pcg.make("PDEControlGym-BrainTumor1D", num_envs=N, device=cuda_device, reward_class=pcg.BrainTumorReward(),
+                   reset_init_condition_func=bt_ic, **BT_P)
     w = pcg.TherapyWrapper(env, weekends=True)
     oenvs = [O.BrainTumorOracle(1, **BT_P) for _ in range(N)]
     ows = [O.TherapyWrapperOracle(e, ic, weekends=True) for e in oenvs]

@@ -158,7 +158,7 @@ def test_brain_tumor_other_grids(X):
         assert np.array_equal(o1, o2[0]) and float(r1) == float(r2[0]) and (bool(te1), bool(tr1)) == (bool(te2[0]), bool(tr2[0])), f"day {day}"
 
 
-@pytest.mark.parametrize("n", [21, 11, 33, 64])
+@pytest.mark.parametrize("n", [21, 11, 33, 64, 128])
 def test_navier_stokes(n):
     ref = load_reference()
     rng = np.random.default_rng(5)
