@@ -199,6 +199,70 @@ def gen_ns():
     print("ns: target subset + mixed-BC run")
 
 
+def gen_ns_adjoint():
+    """examples/NavierStokes/NS2Doptimization.py:62-107 run with the REFERENCE's own env, central_difference, laplace and
+    solve_pressure (same statements, same order), shortened to T = 12 recorded steps and 60 Jacobi sweeps so the fixture stays
+    small: forward rollout with random actions, backward costate sweep, new action sequence."""
+    tg = np.load(os.path.join(ref_root(), "examples", "NavierStokes", "target.npz"))
+    u_target, v_target = tg["u"], tg["v"]
+    desire_states = np.stack([u_target, v_target], axis=-1)
+    bc = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
+    rng = np.random.default_rng(17)
+    c = rng.uniform(-5, 5, 3)
+    dt, dx, dy = 1e-3, 0.05, 0.05
+    env = ref.NavierStokes2D(reset_init_condition_func=lambda X: tuple(ci * np.ones_like(X) for ci in c), boundary_condition=bc,
+                             U_ref=desire_states, action_ref=2.0 * np.ones(1000), reward_class=ref.NSReward(0.1), action_dim=1,
+                             maximum_pressure_iteration=60, T=0.2, dt=dt, X=1, dx=dx, Y=1, dy=dy)
+    central_difference, laplace = ref.central_difference, ref.laplace
+
+    def apply_boundary(a1, a2):                 # :55-60
+        a1[:, [-1, 0]] = 0.
+        a1[[-1, 0], :] = 0.
+        a2[:, [-1, 0]] = 0.
+        a2[[-1, 0], :] = 0.
+        return a1, a2
+    T = 12
+    env.reset(seed=400)
+    U, V, acts_in = [], [], []
+    for t in range(T):                          # :68-72
+        a = rng.uniform(2, 4)
+        acts_in.append(a)
+        env.step(a)
+        U.append(env.u)
+        V.append(env.v)
+    u_ref = [2 for _ in range(T)]
+    Lam1, Lam2 = [], []                          # :79-101
+    Lam1.append(np.zeros_like(U[0]))
+    Lam2.append(np.zeros_like(U[0]))
+    pressure = np.zeros_like(U[0])
+    for t in range(T - 1):
+        lam1, lam2 = Lam1[-1], Lam2[-1]
+        dl1dx, dl1dy = central_difference(lam1, "x", dx), central_difference(lam1, "y", dy)
+        dl2dx, dl2dy = central_difference(lam2, "x", dx), central_difference(lam2, "y", dy)
+        laplace_l1, laplace_l2 = laplace(lam1, dx, dy), laplace(lam2, dx, dy)
+        dlam1dt = - 2 * dl1dx * U[-1-t] - dl1dy * V[-1-t] - dl2dx * V[-1-t] - 0.1 * laplace_l1 + (U[-1-t]-u_target[-1-t])
+        dlam2dt = - 2 * dl2dy * V[-1-t] - dl1dy * U[-1-t] - dl2dx * U[-1-t] - 0.1 * laplace_l2 + (V[-1-t]-v_target[-1-t])
+        lam1 = lam1 - dt * dlam1dt
+        lam2 = lam2 - dt * dlam2dt
+        lam1, lam2 = apply_boundary(lam1, lam2)
+        pressure = env.solve_pressure(lam1, lam2, pressure)
+        lam1 = lam1 - dt * central_difference(pressure, "x", dx)
+        lam2 = lam2 - dt * central_difference(pressure, "y", dy)
+        lam1, lam2 = apply_boundary(lam1, lam2)
+        Lam1.append(lam1)
+        Lam2.append(lam2)
+    Lam1 = Lam1[::-1]
+    actions = []                                 # :103-106
+    for t in range(T):
+        dl1dx2 = central_difference(Lam1[t], "y", dy)
+        actions.append(u_ref[t] - 0.1/0.1 * sum(dl1dx2[-2, :])*5*dx)
+    rows = np.arange(len(u_target) - T - 1, len(u_target))          # the target rows the backward sweep indexes from the end
+    np.savez_compressed(os.path.join(HERE, "ns_adjoint_reference_run.npz"), init=c, actions_in=np.array(acts_in), U=np.array(U), V=np.array(V),
+                        Lam1=np.array(Lam1), Lam2=np.array(Lam2[::-1]), actions_out=np.array(actions), target_rows=rows,
+                        u_target_tail=u_target[rows], v_target_tail=v_target[rows], uref_head=desire_states[:T + 2])
+    print("ns adjoint: T =", T)
+
+
 def ref_root():
     from oracle.ref_loader import REFERENCE_ROOT
     return REFERENCE_ROOT
@@ -210,6 +274,7 @@ if __name__ == "__main__":
     gen_arz()
     gen_brain_tumor()
     gen_ns()
+    gen_ns_adjoint()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

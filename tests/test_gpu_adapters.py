@@ -130,3 +130,36 @@ def test_navier_stokes_adjoint_optimiser_matches_numpy(cuda_device):
     np.testing.assert_allclose(L2.cpu().numpy(), Lam2, rtol=1e-10, atol=1e-13)
     want = np.stack([2.0 - 0.1 / 0.1 * O._cd_y(Lam1[t], dy)[:, -2, :].sum(axis=-1) * 5 * dx for t in range(T)])
     np.testing.assert_allclose(acts.cpu().numpy(), want, rtol=1e-10, atol=1e-12)
+
+
+def test_navier_stokes_adjoint_optimiser_matches_the_reference_run(cuda_device):
+    """controllers.NavierStokesAdjoint vs tests/golden/ns_adjoint_reference_run.npz -- examples/NavierStokes/NS2Doptimization.py:62-107
+    executed with the reference's own env / central_difference / laplace / solve_pressure (tests/golden/gen_golden.py::gen_ns_adjoint):
+    the forward rollout is bit-identical, costates and the new action sequence agree to 1e-10 (torch's element-wise ops
+    round a scalar division through a reciprocal multiply)."""
+    import os
+    import torch
+    import pdecontrolgym_b200 as pcg
+    from pdecontrolgym_b200.controllers import NavierStokesAdjoint
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ns_adjoint_reference_run.npz"))
+    N, T, n = 2, len(g["actions_in"]), 21
+    BC = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
+    env = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=cuda_device, reward_class=pcg.NSReward(0.1), boundary_condition=BC,
+                   U_ref=g["uref_head"], action_ref=2.0 * np.ones(100), maximum_pressure_iteration=60, T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05)
+    c = g["init"]
+    env.reset(options={"init": tuple(np.full((n, n), ci) for ci in c)})
+    U, V = [], []
+    for t in range(T):
+        obs, *_ = env.step(torch.full((N,), float(g["actions_in"][t]), dtype=torch.float64))
+        U.append(obs[..., 0].clone())
+        V.append(obs[..., 1].clone())
+    U, V = torch.stack(U), torch.stack(V)
+    for b in range(N):
+        assert np.array_equal(U[:, b].cpu().numpy(), g["U"]) and np.array_equal(V[:, b].cpu().numpy(), g["V"]), "forward rollout"
+    adj = NavierStokesAdjoint(env)
+    L1, L2 = adj.costates(U, V, g["u_target_tail"], g["v_target_tail"])
+    acts = adj.actions(U, V, g["u_target_tail"], g["v_target_tail"], 2.0)
+    for b in range(N):
+        np.testing.assert_allclose(L1[:, b].cpu().numpy(), g["Lam1"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(L2[:, b].cpu().numpy(), g["Lam2"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(acts[:, b].cpu().numpy(), g["actions_out"], rtol=1e-10)
