@@ -88,6 +88,8 @@ typedef struct {
     int32_t horizon;              /* pdecg_horizon       (NormReward)                              */
     int32_t t_horizon_length;     /* NormReward                                                   */
     double truncate_penalty, terminate_reward, norm_coeff;
+    int32_t truncate_nonfinite;   /* non-zero: an env whose state row has blown up (inf / NaN) comes out `truncated` -- NOT what
+                                     the reference does (there inf / NaN just propagate, parabolic.py:148-150 quirk); default 0 */
 } pdecg_bc1d_cfg;
 
 /* Device buffers of one batch.  npts = nx (Transport) or nx+1 (ReactionDiffusion, ghost point).
@@ -111,6 +113,8 @@ typedef struct {
                                 the dtype of the reference's observation_space (base_env_1d.py:33-35); each element
                                 is the state value rounded once to float32 (numpy `row.astype(np.float32)`).  The
                                 resident state keeps its precision.                                             */
+    uint8_t* nonfinite;      /* optional [n_envs]: 1 where the state row holds an inf / NaN (or squares overflow float64)
+                                after this step -- a per-env failure flag for the learner                            */
 } pdecg_bc1d_buffers;
 
 /* Number of doubles of reward carry per env for this configuration. */
@@ -216,6 +220,9 @@ typedef struct {
     double alpha, alpha_beta_ratio;
     double t1_detection_radius, t1_death_radius;
     double total_dosage;
+    int32_t precision;           /* pdecg_precision: REF / FP64 = float64 like the reference; FP32 = opt-in fast mode: u / obs /
+                                    final_obs hold float32, the finite-difference update runs in float32 (same operation order);
+                                    doses, D, rho, the radiation factor, reward and every counter stay float64 / int32   */
 } pdecg_bt_cfg;
 
 typedef struct {
@@ -287,12 +294,15 @@ typedef struct {
     double c3;                    /* dt / dx                          :218   */
     double c4;                    /* 0.5 * dt / tau                   :221   */
     double vm_over_rm;            /* self.vm / self.rm                :84    */
+    int32_t precision;            /* pdecg_precision: REF / FP64 = float64 like the reference (bit-identical states);
+                                     FP32 = opt-in fast mode: ry / obs / final_obs hold float32, arithmetic in float32 (same
+                                     operation order); actions, fenv and reward stay float64                            */
 } pdecg_arz_cfg;
 
 typedef struct {
     int64_t n_envs;
-    double* ry;              /* [n_envs, 2, M] state: density rho then y = rho*(v - Veq(rho))            */
-    double* obs;             /* [n_envs, 2*M]  concat(rho, v)  (normalised deviations for OUTLET_TRAIN)  */
+    double* ry;              /* [n_envs, 2, M] state: density rho then y = rho*(v - Veq(rho))  (float32 data in FP32 mode) */
+    double* obs;             /* [n_envs, 2*M]  concat(rho, v)  (normalised deviations for OUTLET_TRAIN)  (float32 in FP32 mode) */
     const double* action;    /* [n_envs, action_dim] flow-rate control(s)                               */
     double* fenv;            /* [n_envs, PDECG_ARZ_NF64]                                                */
     double* reward;          /* [n_envs]                                                                */

@@ -35,6 +35,7 @@ class Bc1dCfg(C.Structure):
         ("max_state_value", C.c_double), ("reward_nt", C.c_int32), ("norm_ord", C.c_int32),
         ("horizon", C.c_int32), ("t_horizon_length", C.c_int32),
         ("truncate_penalty", C.c_double), ("terminate_reward", C.c_double), ("norm_coeff", C.c_double),
+        ("truncate_nonfinite", C.c_int32),
     ]
 
 
@@ -43,7 +44,7 @@ class Bc1dBuffers(C.Structure):
         ("n_envs", C.c_int64), ("u", C.c_void_p), ("beta", C.c_void_p), ("beta_env_stride", C.c_int64),
         ("action", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
         ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("time_index", C.c_void_p),
-        ("carry", C.c_void_p), ("obs_copy", C.c_void_p), ("obs_copy_f32", C.c_int32),
+        ("carry", C.c_void_p), ("obs_copy", C.c_void_p), ("obs_copy_f32", C.c_int32), ("nonfinite", C.c_void_p),
     ]
 
 
@@ -61,7 +62,7 @@ class BtCfg(C.Structure):
         ("dt", C.c_double), ("dx", C.c_double), ("k", C.c_double), ("t1_threshold_k", C.c_double),
         ("t2_threshold_k", C.c_double), ("dosage_termination_threshold", C.c_double),
         ("alpha", C.c_double), ("alpha_beta_ratio", C.c_double), ("t1_detection_radius", C.c_double),
-        ("t1_death_radius", C.c_double), ("total_dosage", C.c_double),
+        ("t1_death_radius", C.c_double), ("total_dosage", C.c_double), ("precision", C.c_int32),
     ]
 
 
@@ -79,7 +80,7 @@ class ArzCfg(C.Structure):
         ("abi_version", C.c_int32), ("simulation_type", C.c_int32), ("M", C.c_int32), ("control_freq", C.c_int32),
         ("limit_pde_state_size", C.c_int32), ("action_dim", C.c_int32), ("T", C.c_double), ("dt", C.c_double),
         ("t_over_dt", C.c_double), ("vm", C.c_double), ("rm", C.c_double), ("c1", C.c_double), ("c2", C.c_double),
-        ("c3", C.c_double), ("c4", C.c_double), ("vm_over_rm", C.c_double),
+        ("c3", C.c_double), ("c4", C.c_double), ("vm_over_rm", C.c_double), ("precision", C.c_int32),
     ]
 
 

@@ -219,9 +219,10 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
     const bool via_copy = full && buf->obs_copy != nullptr;
     const size_t osz = (via_copy && buf->obs_copy_f32) ? 4 : ssz;
     const size_t obs_row = full ? static_cast<size_t>(a.npts) * osz : ssz;
-    // chunks of >= 4096 envs, at most 8 of them
+    // chunks of >= 4096 envs, at most 8 of them (PDECG_HOST_CHUNKS overrides the cap: A/B runs)
+    static const int max_chunks = [] { const char* e = getenv("PDECG_HOST_CHUNKS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
     int nchunk = static_cast<int>(n / 4096);
-    nchunk = nchunk < 1 ? 1 : (nchunk > 8 ? 8 : nchunk);
+    nchunk = nchunk < 1 ? 1 : (nchunk > max_chunks ? max_chunks : nchunk);
     const int64_t per = ((n + nchunk - 1) / nchunk + 3) / 4 * 4;
     cudaError_t e = cudaEventRecord(g_pipe.start, user);      // order after whatever the caller queued
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));

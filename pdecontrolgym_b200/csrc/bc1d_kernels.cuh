@@ -585,7 +585,10 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
     const double sumsq = chunk_sumsq<S, K, LPE>(u, j0, npts, mask);
     const S norm2 = static_cast<S>(sqrt(sumsq));               // np.linalg.norm(u[t]) in the state dtype
     const bool terminated = t_end >= cfg.nt - 1;                // hyperbolic.py:171-180
-    const bool truncated = cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value));
+    // per-env blow-up flag (no counterpart in the reference, where inf / NaN simply propagate): the row holds an inf / NaN, or
+    // values so large that their squares overflow float64; optionally folded into `truncated`
+    const bool nonfinite = !(sumsq <= 1.7976931348623157e308);
+    const bool truncated = (cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value))) || (cfg.truncate_nonfinite && nonfinite);
     const S dxs = I.dxs;
 
     double reward;
@@ -649,6 +652,7 @@ bc1d_step_kernel(const __grid_constant__ Bc1dArgs a) {
         a.buf.reward[env] = reward;
         a.buf.terminated[env] = terminated ? 1 : 0;
         a.buf.truncated[env] = truncated ? 1 : 0;
+        if (a.buf.nonfinite != nullptr) a.buf.nonfinite[env] = nonfinite ? 1 : 0;
     }
     if (a.ar.enabled && (terminated || truncated)) {
         // the terminal observation survives the restart in the caller's final_obs buffer (what SB3 / gymnasium call

@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(kCtaMaxThreads, 1) bc1d_step_cta_kernel(const 
     const double sumsq = cta_sumsq<S>(cur, npts, red);
     const S norm2 = static_cast<S>(sqrt(sumsq));               // np.linalg.norm(u[t]) in the state dtype
     const bool terminated = t_end >= cfg.nt - 1;                // hyperbolic.py:171-180
-    const bool truncated = cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value));
+    // per-env blow-up flag (no counterpart in the reference, where inf / NaN simply propagate): the row holds an inf / NaN, or
+    // values so large that their squares overflow float64; optionally folded into `truncated`
+    const bool nonfinite = !(sumsq <= 1.7976931348623157e308);
+    const bool truncated = (cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value))) || (cfg.truncate_nonfinite && nonfinite);
     double other_norm = 0.0;                                    // NormReward temporal with p != 2
     if (!tuned && !terminated && !truncated && (cfg.horizon == PDECG_HORIZON_TEMPORAL || nsub == 0) && cfg.norm_ord != kNormL2)
         other_norm = cta_norm<S>(cur, nullptr, npts, cfg.norm_ord, red);
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(kCtaMaxThreads, 1) bc1d_step_cta_kernel(const 
         a.buf.reward[env] = reward;
         a.buf.terminated[env] = terminated ? 1 : 0;
         a.buf.truncated[env] = truncated ? 1 : 0;
+        if (a.buf.nonfinite != nullptr) a.buf.nonfinite[env] = nonfinite ? 1 : 0;
     }
     if (a.ar.enabled && (terminated || truncated)) {
         if (a.ar.final_obs != nullptr && cfg.sensing_loc == PDECG_SENSE_FULL)     // terminal observation for the caller
@@ -454,7 +458,10 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
     const double sumsq = row_sumsq();                          // (its barriers also publish `sens`)
     const S norm2 = static_cast<S>(sqrt(sumsq));               // np.linalg.norm(u[t]) in the state dtype
     const bool terminated = t_end >= cfg.nt - 1;                // hyperbolic.py:171-180
-    const bool truncated = cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value));
+    // per-env blow-up flag (no counterpart in the reference, where inf / NaN simply propagate): the row holds an inf / NaN, or
+    // values so large that their squares overflow float64; optionally folded into `truncated`
+    const bool nonfinite = !(sumsq <= 1.7976931348623157e308);
+    const bool truncated = (cfg.limit_pde_state_size && (norm2 >= static_cast<S>(cfg.max_state_value))) || (cfg.truncate_nonfinite && nonfinite);
     double other_norm = 0.0;                                    // NormReward temporal with p != 2
     if (!tuned && !terminated && !truncated && (cfg.horizon == PDECG_HORIZON_TEMPORAL || nsub == 0) && cfg.norm_ord != kNormL2)
         other_norm = row_norm(cfg.norm_ord);
@@ -514,6 +521,7 @@ __global__ void __launch_bounds__(K <= 4 ? 512 : 1024, K <= 4 ? 2 : 1) bc1d_step
         a.buf.reward[env] = reward;
         a.buf.terminated[env] = terminated ? 1 : 0;
         a.buf.truncated[env] = truncated ? 1 : 0;
+        if (a.buf.nonfinite != nullptr) a.buf.nonfinite[env] = nonfinite ? 1 : 0;
     }
     if (a.ar.enabled && (terminated || truncated)) {
         if (a.ar.final_obs != nullptr && cfg.sensing_loc == PDECG_SENSE_FULL) {   // terminal observation for the caller

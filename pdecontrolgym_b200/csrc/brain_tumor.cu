@@ -27,7 +27,6 @@ struct BtArgs {
     int64_t ar_stride;
 };
 
-__device__ __noinline__ void bt_autoreset_env(const BtArgs& a, int64_t env, int lane);   // defined after the reset kernel
 
 struct BtEnv {   // the reference's per-env attributes (brain_tumor_env.py:89-101)
     int t, stage, growthDays, therapyDays, postTherapyDays, simulationDays;
@@ -37,8 +36,8 @@ struct BtEnv {   // the reference's per-env attributes (brain_tumor_env.py:89-10
 };
 
 // right-most index j with c_j >= thr (getTumorRadius, :104-121); -1 when the tumour is invisible
-template <int K>
-__device__ __forceinline__ int rightmost_ge(const double (&c)[K], int j0, int nx, double thr) {
+template <int K, typename T>
+__device__ __forceinline__ int rightmost_ge(const T (&c)[K], int j0, int nx, T thr) {
     const int kmax = nx - j0;                         // slots k >= kmax of this lane are padding
     int best = -1;
 #pragma unroll
@@ -226,6 +225,41 @@ __device__ __forceinline__ void bt_fd_lean(const pdecg_bt_cfg& cfg, const BtDivs
     }
 }
 
+// float32 fast mode (PDECG_PREC_FP32): the same update in float32, same operation order, plain IEEE divisions and clip
+template <int K, bool HASR>
+__device__ __forceinline__ void bt_fd_f32(const pdecg_bt_cfg& cfg, const float (&c)[K], float (&n)[K], int lane, int j0,
+                                           float D, float rho, float rin, double treat_r, const double* __restrict__ xg) {
+    using F = Strict<float>;
+    const int nx = cfg.nx;
+    const float dx2 = F::mul(static_cast<float>(cfg.dx), static_cast<float>(cfg.dx)), kk = static_cast<float>(cfg.k), dt = static_cast<float>(cfg.dt);
+    const float hl = __shfl_up_sync(kFull, c[K - 1], 1);
+    const float hr = __shfl_down_sync(kFull, c[0], 1);
+    float t[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float cl = (k == 0) ? hl : c[k > 0 ? k - 1 : 0];
+        const float cr = (k == K - 1) ? hr : c[k < K - 1 ? k + 1 : K - 1];
+        const float cc = c[k];
+        const float diff = F::mul(D, F::div(F::add(F::sub(cr, F::mul(2.0f, cc)), cl), dx2));
+        const float om = F::sub(1.0f, F::div(cc, kk));
+        float acc = F::add(diff, F::mul(F::mul(rho, cc), om));
+        if constexpr (HASR) {
+            const float rj = ((j0 + k < nx ? xg[j0 + k] : CUDART_INF) <= treat_r) ? rin : 0.0f;
+            acc = F::sub(acc, F::mul(F::mul(rj, cc), om));
+        }
+        t[k] = F::add(cc, F::mul(dt, acc));
+    }
+    const float from_left = __shfl_up_sync(kFull, t[K - 1], 1);
+    const float from_right = __shfl_down_sync(kFull, t[0], 1);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float v = t[k];
+        if (k == 0) v = (lane == 0) ? ((K > 1) ? t[K > 1 ? 1 : 0] : from_right) : v;
+        if (j0 + k == nx - 1) v = (k > 0) ? t[k > 0 ? k - 1 : 0] : from_left;
+        n[k] = (v < 0.0f) ? 0.0f : ((v > kk) ? kk : v);
+    }
+}
+
 __device__ __forceinline__ void bt_book(BtEnv& e) {
     if (e.stage == PDECG_BT_THERAPY) {
         e.therapyDays = e.t - e.growthDays;
@@ -237,13 +271,13 @@ __device__ __forceinline__ void bt_book(BtEnv& e) {
 }
 
 // One call of BrainTumor1D.step (:123-218) for an env with t < nt-1.
-template <int K, bool XSREG>
-__device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const double (&xs)[K], BtEnv& e, double (&u)[K], int lane, int j0,
+template <int K, bool XSREG, typename T>
+__device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const double (&xs)[K], BtEnv& e, T (&u)[K], int lane, int j0,
                                         double control, double& reward, bool& term, bool& trunc) {
     const pdecg_bt_cfg& cfg = a.cfg;
     const int nx = cfg.nx;
     e.t += 1;
-    double n[K];
+    T n[K];
     double treat_r = 0.0, applied = 0.0;
     const int stage0 = e.stage;
     if (stage0 == PDECG_BT_THERAPY) {
@@ -253,7 +287,7 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
         e.remaining = __dsub_rn(e.remaining, applied);
         e.last_dose = applied;
         // _compute_radiation_field (:247-265) uses the PREVIOUS day's T2 radius
-        const int t2 = rightmost_ge<K>(u, j0, nx, cfg.t2_threshold_k);
+        const int t2 = rightmost_ge<K, T>(u, j0, nx, static_cast<T>(cfg.t2_threshold_k));
         treat_r = (t2 < 0) ? 0.0 : __dadd_rn(__dmul_rn(static_cast<double>(t2), cfg.dx), 25.0);
         // R = 1 - exp(-alpha*BED) where xScale <= treatmentRadius, 1 - exp(-alpha*0) = 0 elsewhere (:259-265).
         // A zero dose gives BED = 0 and R = 1 - exp(-0) = +0 everywhere: skip the exp().
@@ -262,7 +296,9 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
             const double bed = __dadd_rn(applied, __ddiv_rn(__dmul_rn(applied, applied), cfg.alpha_beta_ratio));
             rin = __dsub_rn(1.0, exp_cr(__dmul_rn(-cfg.alpha, bed)));     // correctly rounded (pdecg_common.cuh)
         }
-        if constexpr (XSREG) {
+        if constexpr (sizeof(T) == 4) {
+            bt_fd_f32<K, true>(cfg, u, n, lane, j0, static_cast<float>(e.D), static_cast<float>(e.rho), static_cast<float>(rin), treat_r, a.buf.x_scale);
+        } else if constexpr (XSREG) {
             if (dv.dx2_one) bt_fd<K, true, true, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, rin, treat_r, xs, a.buf.x_scale);
             else bt_fd<K, false, true, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, rin, treat_r, xs, a.buf.x_scale);
         } else {
@@ -271,7 +307,9 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
         }
     } else {
         e.last_dose = 0.0;                                           // dosage_vs_time[t] stays 0 outside Therapy (:56,160)
-        if constexpr (XSREG) {
+        if constexpr (sizeof(T) == 4) {
+            bt_fd_f32<K, false>(cfg, u, n, lane, j0, static_cast<float>(e.D), static_cast<float>(e.rho), 0.0f, 0.0, a.buf.x_scale);
+        } else if constexpr (XSREG) {
             if (dv.dx2_one) bt_fd<K, true, false, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, 0.0, 0.0, xs, a.buf.x_scale);
             else bt_fd<K, false, false, true>(cfg, dv, u, n, lane, j0, e.D, e.rho, 0.0, 0.0, xs, a.buf.x_scale);
         } else {
@@ -282,7 +320,7 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
 #pragma unroll
     for (int k = 0; k < K; ++k) u[k] = n[k];
 
-    const int t1 = rightmost_ge<K>(u, j0, nx, cfg.t1_threshold_k);
+    const int t1 = rightmost_ge<K, T>(u, j0, nx, static_cast<T>(cfg.t1_threshold_k));
     const double t1_radius = __dmul_rn(static_cast<double>(t1), cfg.dx);
     if (stage0 == PDECG_BT_GROWTH) {
         e.growthDays = e.t;
@@ -325,22 +363,26 @@ __device__ __forceinline__ void bt_day(const BtArgs& a, const BtDivs& dv, const 
 }
 
 // MULTI = false: PDECG_BT_RAW_STEP only (one day per launch); MULTI = true: the TherapyWrapper modes.
-template <int K, bool MULTI>
+template <typename T>
+__device__ __noinline__ void bt_autoreset_env_t(const BtArgs& a, int64_t env, int lane);
+
+template <int K, bool MULTI, typename T>
 __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLOCKS_MULTI : PDECG_BT_MINBLOCKS)) bt_run_kernel(const __grid_constant__ BtArgs a) {
-    __shared__ double sm_all[kWarpsPerBlock][32 * K];
+    __shared__ T sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
     if (env >= a.buf.n_envs) return;
-    double* sm = sm_all[wib];
+    T* sm = sm_all[wib];
     const pdecg_bt_cfg& cfg = a.cfg;
     const int nx = cfg.nx;
     const int j0 = lane * K;
+    T* const obs_all = reinterpret_cast<T*>(a.buf.obs);
 
     // start the row load first: the scalar loads and their broadcast then overlap its latency
-    double* urow = a.buf.u + env * nx;
-    double u[K], u_raw[K];
-    load_row_issue<double, double, K>(u_raw, urow, nx, lane);
+    T* urow = reinterpret_cast<T*>(a.buf.u) + env * nx;
+    T u[K], u_raw[K];
+    load_row_issue<T, T, K>(u_raw, urow, nx, lane);
     // per-env scalars: one coalesced read, broadcast by shuffle
     int* irow = a.buf.ienv + env * PDECG_BT_NINT;
     double* frow = a.buf.fenv + env * PDECG_BT_NF64;
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
     e.rho = __shfl_sync(kFull, fv, PDECG_BT_F_RHO);
     e.last_dose = __shfl_sync(kFull, fv, PDECG_BT_F_LAST_DOSE);
 
-    load_row_finish<double, K>(u, u_raw, sm, lane);
+    load_row_finish<T, K>(u, u_raw, sm, lane);
 
     const BtDivs dv(cfg);
     // this lane's chunk of xScale (radiation-field mask): register-resident for the multi-day launches; the
@@ -379,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
 
     if constexpr (!MULTI) {
         if (e.t < last) {
-            bt_day<K, MULTI>(a, dv, xs, e, u, lane, j0, a.buf.action[env], reward, term, trunc);
+            bt_day<K, MULTI, T>(a, dv, xs, e, u, lane, j0, a.buf.action[env], reward, term, trunc);
         } else {
             valid = false;                       // the reference returns None here (:135)
             term = true;
@@ -388,26 +430,26 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
         // TherapyWrapper.reset (:408-427); with a mask only the selected envs take part (the others keep their
         // consecutive-treatment-day counter and everything else: they are mid-therapy patients of the same batch)
         if (a.buf.mask != nullptr && a.buf.mask[env] == 0) {
-            if (a.buf.obs != nullptr) store_row_chunk<double, K>(u, a.buf.obs + env * nx, nx, sm, lane);
+            if (obs_all != nullptr) store_row_chunk<T, K>(u, obs_all + env * nx, nx, sm, lane);
             return;
         }
         e.consecutive = 0;
         while (e.stage == PDECG_BT_GROWTH && e.t < last) {
-            bt_day<K, MULTI>(a, dv, xs, e, u, lane, j0, 0.0, reward, term, trunc);
+            bt_day<K, MULTI, T>(a, dv, xs, e, u, lane, j0, 0.0, reward, term, trunc);
             if (term || trunc) break;
         }
     } else if (a.mode == PDECG_BT_RUN_TO_END) {
         // TherapyWrapper.benchmark (:480-505): zero-dose episode, then t_benchmark <- simulationDays
-        while (!(term || trunc) && e.t < last) bt_day<K, MULTI>(a, dv, xs, e, u, lane, j0, 0.0, reward, term, trunc);
+        while (!(term || trunc) && e.t < last) bt_day<K, MULTI, T>(a, dv, xs, e, u, lane, j0, 0.0, reward, term, trunc);
         e.t_benchmark = e.simulationDays;
     } else {
         // TherapyWrapper.step (:429-478)
         if (e.stage == PDECG_BT_POST) {
-            while (!(term || trunc) && e.t < last) bt_day<K, MULTI>(a, dv, xs, e, u, lane, j0, 0.0, reward, term, trunc);
+            while (!(term || trunc) && e.t < last) bt_day<K, MULTI, T>(a, dv, xs, e, u, lane, j0, 0.0, reward, term, trunc);
             if (e.t >= last && !(term || trunc)) { valid = false; term = true; }
         } else if (e.t < last) {
             const double control = a.buf.action[env];
-            bt_day<K, MULTI>(a, dv, xs, e, u, lane, j0, control, reward, term, trunc);
+            bt_day<K, MULTI, T>(a, dv, xs, e, u, lane, j0, control, reward, term, trunc);
             e.treatment_calls += 1;
             if (reward < 0.0) e.violations += 1;
             if (cfg.weekends) {
@@ -416,15 +458,15 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
                     e.consecutive = 0;
                     // the observation returned is the therapy day's row; the two rest days' results are
                     // discarded and the loop tests the STALE flags (:470-473)
-                    if (a.buf.obs != nullptr) {
-                        store_row_chunk<double, K>(u, a.buf.obs + env * nx, nx, sm, lane);
+                    if (obs_all != nullptr) {
+                        store_row_chunk<T, K>(u, obs_all + env * nx, nx, sm, lane);
                         wrote_obs = true;
                     }
                     for (int i = 0; i < 2; ++i) {
                         if (e.t < last) {
                             double r2;
                             bool te2, tr2;
-                            bt_day<K, MULTI>(a, dv, xs, e, u, lane, j0, 0.0, r2, te2, tr2);
+                            bt_day<K, MULTI, T>(a, dv, xs, e, u, lane, j0, 0.0, r2, te2, tr2);
                         }
                         if (term || trunc) break;
                     }
@@ -436,8 +478,8 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
         }
     }
 
-    store_row_chunk<double, K>(u, urow, nx, sm, lane);
-    if (a.buf.obs != nullptr && !wrote_obs) store_row_chunk<double, K>(u, a.buf.obs + env * nx, nx, sm, lane);
+    store_row_chunk<T, K>(u, urow, nx, sm, lane);
+    if (obs_all != nullptr && !wrote_obs) store_row_chunk<T, K>(u, obs_all + env * nx, nx, sm, lane);
 
     // write back scalars (coalesced)
     int ov = iv;
@@ -468,23 +510,24 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
     if constexpr (!MULTI) {
         if (a.ar_init != nullptr && (term || trunc)) {
             if (a.buf.final_obs != nullptr)          // terminal observation for the caller, before the row is re-initialised
-                store_row_chunk<double, K>(u, a.buf.final_obs + env * nx, nx, sm, lane);
-            bt_autoreset_env(a, env, lane);
+                store_row_chunk<T, K>(u, reinterpret_cast<T*>(a.buf.final_obs) + env * nx, nx, sm, lane);
+            bt_autoreset_env_t<T>(a, env, lane);
         }
     }
 }
 
 // BrainTumor1D.reset (:347-384) for one env, executed by its warp.  `keep_outputs`: leave reward / flags / valid alone
 // (fused auto-reset: they keep the step's values).
+template <typename T>
 __device__ __forceinline__ void bt_reset_env(const BtArgs& a, const double* __restrict__ init, int64_t init_stride, int64_t env,
                                              int lane, bool keep_outputs) {
     const int nx = a.cfg.nx;
     const double* irow = init + env * init_stride;
-    double* urow = a.buf.u + env * nx;
+    T* urow = reinterpret_cast<T*>(a.buf.u) + env * nx;
     for (int j = lane; j < nx; j += 32) {
-        const double v = irow[j];
+        const T v = static_cast<T>(irow[j]);
         urow[j] = v;
-        if (a.buf.obs) a.buf.obs[env * nx + j] = v;
+        if (a.buf.obs) reinterpret_cast<T*>(a.buf.obs)[env * nx + j] = v;
     }
     // brain_tumor_env.py:363-379; t_benchmark, D, rho survive a reset
     int* ir = a.buf.ienv + env * PDECG_BT_NINT;
@@ -508,18 +551,20 @@ __device__ __forceinline__ void bt_reset_env(const BtArgs& a, const double* __re
 }
 
 // fused same-step auto-reset: out of line so the (rare) restart does not weigh on the step kernel's registers
-__device__ __noinline__ void bt_autoreset_env(const BtArgs& a, int64_t env, int lane) {
+template <typename T>
+__device__ __noinline__ void bt_autoreset_env_t(const BtArgs& a, int64_t env, int lane) {
     __syncwarp();                                  // the step's own row / scalar stores come first
-    bt_reset_env(a, a.ar_init, a.ar_stride, env, lane, true);
+    bt_reset_env<T>(a, a.ar_init, a.ar_stride, env, lane, true);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads) bt_reset_kernel(const BtArgs a, const double* __restrict__ init, int64_t init_stride,
                                                             const uint8_t* __restrict__ mask) {
     const int lane = threadIdx.x & 31;
     const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
     if (env >= a.buf.n_envs) return;
     if (mask != nullptr && mask[env] == 0) return;
-    bt_reset_env(a, init, init_stride, env, lane, false);
+    bt_reset_env<T>(a, init, init_stride, env, lane, false);
 }
 
 static int bt_validate(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf) {
@@ -528,6 +573,7 @@ static int bt_validate(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf) {
     if (cfg->nx < 4 || cfg->nt < 2) return fail(PDECG_ERR_INVALID, "need nx >= 4 and nt >= 2");
     if (cfg->nx > 512) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 512 points per env", cfg->nx);
     if (!(cfg->dt > 0) || !(cfg->dx > 0) || !(cfg->k > 0)) return fail(PDECG_ERR_INVALID, "dt, dx, k must be positive");
+    if (cfg->precision < PDECG_PREC_REF || cfg->precision > PDECG_PREC_FP32) return fail(PDECG_ERR_INVALID, "bad precision %d", cfg->precision);
     if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (buf->n_envs > 0 && (!buf->u || !buf->ienv || !buf->fenv || !buf->reward || !buf->terminated || !buf->truncated || !buf->x_scale))
         return fail(PDECG_ERR_INVALID, "null device buffer");
@@ -546,7 +592,8 @@ extern "C" int pdecg_bt_reset(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* b
     if (!init) return fail(PDECG_ERR_INVALID, "null init buffer");
     BtArgs a{*cfg, *buf, 0, nullptr, 0};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    bt_reset_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init, init_env_stride, mask);
+    if (cfg->precision == PDECG_PREC_FP32) bt_reset_kernel<float><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init, init_env_stride, mask);
+    else bt_reset_kernel<double><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init, init_env_stride, mask);
     count_launch();
     return check_launch("bt_reset_kernel");
 }
@@ -566,8 +613,11 @@ static int bt_launch(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf, int32
     switch (K) {
 #define PDECG_CASE(KK)                                                                   \
     case KK:                                                                             \
-        if (mode == PDECG_BT_RAW_STEP) bt_run_kernel<KK, false><<<grid, kThreads, 0, st>>>(a); \
-        else bt_run_kernel<KK, true><<<grid, kThreads, 0, st>>>(a);                      \
+        if (cfg->precision == PDECG_PREC_FP32) {                                          \
+            if (mode == PDECG_BT_RAW_STEP) bt_run_kernel<KK, false, float><<<grid, kThreads, 0, st>>>(a); \
+            else bt_run_kernel<KK, true, float><<<grid, kThreads, 0, st>>>(a);            \
+        } else if (mode == PDECG_BT_RAW_STEP) bt_run_kernel<KK, false, double><<<grid, kThreads, 0, st>>>(a); \
+        else bt_run_kernel<KK, true, double><<<grid, kThreads, 0, st>>>(a);               \
         break;
         PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
         PDECG_CASE(10) PDECG_CASE(12) PDECG_CASE(14) PDECG_CASE(16)
@@ -603,7 +653,8 @@ extern "C" int pdecg_bt_step_host(const pdecg_bt_cfg* cfg, const pdecg_bt_buffer
     cudaError_t e = cudaMemcpyAsync(const_cast<double*>(buf->action), action_host, n * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
     if ((rc = bt_launch(cfg, buf, PDECG_BT_RAW_STEP, autoreset_init, autoreset_init_env_stride, stream)) != PDECG_OK) return rc;
-    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->u, n * cfg->nx * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+    const size_t esz = cfg->precision == PDECG_PREC_FP32 ? sizeof(float) : sizeof(double);
+    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->u, n * cfg->nx * esz, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
     if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
     if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
     if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));

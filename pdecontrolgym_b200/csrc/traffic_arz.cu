@@ -23,21 +23,25 @@ struct ArzArgs {
     const double* ar_profile;   // pdecg_arz_step_autoreset: finished envs restart inside the step launch (nullptr: off)
 };
 
-using D = Strict<double>;
-
+// T = double: the reference's arithmetic (numpy float64, operation order kept, never contracted) -- bit-identical states.
+// T = float : the opt-in fast mode (PDECG_PREC_FP32): float32 state, observation and arithmetic, same operation order.
+template <typename T>
 struct ArzCtx {      // vm and the hoisted exact division by the constant rm
-    double vm;
-    ConstDiv<double> by_rm;
-    __device__ __forceinline__ explicit ArzCtx(const pdecg_arz_cfg& c) : vm(c.vm), by_rm(c.rm) {}
+    T vm;
+    ConstDiv<T> by_rm;
+    __device__ __forceinline__ explicit ArzCtx(const pdecg_arz_cfg& c) : vm(static_cast<T>(c.vm)), by_rm(static_cast<T>(c.rm)) {}
 };
-__device__ __forceinline__ double veq(const ArzCtx& c, double rho) {          // :271-272
-    return D::mul(c.vm, D::sub(1.0, c.by_rm(rho)));
+template <typename T>
+__device__ __forceinline__ T veq(const ArzCtx<T>& c, T rho) {          // :271-272
+    return Strict<T>::mul(c.vm, Strict<T>::sub(T(1), c.by_rm(rho)));
 }
-__device__ __forceinline__ double flux_r(const ArzCtx& c, double rho, double y) {   // :275-276
-    return D::add(y, D::mul(rho, veq(c, rho)));
+template <typename T>
+__device__ __forceinline__ T flux_r(const ArzCtx<T>& c, T rho, T y) {   // :275-276
+    return Strict<T>::add(y, Strict<T>::mul(rho, veq(c, rho)));
 }
-__device__ __forceinline__ double flux_y(const ArzCtx& c, double rho, double y) {   // :279-280
-    return D::mul(y, D::add(D::div(y, rho), veq(c, rho)));
+template <typename T>
+__device__ __forceinline__ T flux_y(const ArzCtx<T>& c, T rho, T y) {   // :279-280
+    return Strict<T>::mul(y, Strict<T>::add(Strict<T>::div(y, rho), veq(c, rho)));
 }
 __device__ __forceinline__ double clipd(double v, double lo, double hi) {            // np.clip keeps NaN
     v = (v < lo) ? lo : v;
@@ -48,93 +52,96 @@ __device__ __forceinline__ double clipd(double v, double lo, double hi) {       
 // the 8K bytes at offset 8KL: every 32-byte sector is consumed by at most two adjacent lanes, and the second access
 // of a line hits L1), which drops the shared-memory staging and its two warp barriers per row; wider chunks go through
 // the staged, fully coalesced path.
-template <int K>
-__device__ __forceinline__ void arz_load_issue(double (&tmp)[K], const double* __restrict__ g, int npts, int lane) {
+template <int K, typename T>
+__device__ __forceinline__ void arz_load_issue(T (&tmp)[K], const T* __restrict__ g, int npts, int lane) {
     if constexpr (K <= 2) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) tmp[k] = (lane * K + k < npts) ? g[lane * K + k] : 0.0;
+        for (int k = 0; k < K; ++k) tmp[k] = (lane * K + k < npts) ? g[lane * K + k] : T(0);
     } else {
-        load_row_issue<double, double, K>(tmp, g, npts, lane);
+        load_row_issue<T, T, K>(tmp, g, npts, lane);
     }
 }
-template <int K>
-__device__ __forceinline__ void arz_load_finish(double (&r)[K], const double (&tmp)[K], double* sm, int lane) {
+template <int K, typename T>
+__device__ __forceinline__ void arz_load_finish(T (&r)[K], const T (&tmp)[K], T* sm, int lane) {
     if constexpr (K <= 2) {
 #pragma unroll
         for (int k = 0; k < K; ++k) r[k] = tmp[k];
     } else {
-        load_row_finish<double, K>(r, tmp, sm, lane);
+        load_row_finish<T, K>(r, tmp, sm, lane);
     }
 }
-template <int K>
-__device__ __forceinline__ void arz_store(const double (&r)[K], double* __restrict__ g, int npts, double* sm, int lane) {
+template <int K, typename T>
+__device__ __forceinline__ void arz_store(const T (&r)[K], T* __restrict__ g, int npts, T* sm, int lane) {
     if constexpr (K <= 2) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
             if (lane * K + k < npts) g[lane * K + k] = r[k];
     } else {
-        store_row_chunk<double, K>(r, g, npts, sm, lane);
+        store_row_chunk<T, K>(r, g, npts, sm, lane);
     }
 }
 
+template <typename T>
 __device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane);   // defined after the reset kernel
 
-template <int K>
+template <int K, typename T>
 __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) arz_step_kernel(const __grid_constant__ ArzArgs a) {
-    __shared__ double sm_all[kWarpsPerBlock][32 * K];
+    using D = Strict<T>;
+    __shared__ T sm_all[kWarpsPerBlock][32 * K];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
     if (env >= a.buf.n_envs) return;
-    double* sm = sm_all[wib];
+    T* sm = sm_all[wib];
     const pdecg_arz_cfg& cfg = a.cfg;
     const int M = cfg.M;
     const int j0 = lane * K;
-    const ArzCtx ctx(cfg);
+    const ArzCtx<T> ctx(cfg);
+    const T c1 = static_cast<T>(cfg.c1), c2 = static_cast<T>(cfg.c2), c3 = static_cast<T>(cfg.c3), c4 = static_cast<T>(cfg.c4);
 
     // start the row loads first: the scalar load and its broadcast then overlap their latency
-    double* rrow = a.buf.ry + env * 2 * M;
-    double* yrow = rrow + M;
-    double r[K], y[K], r_raw[K], y_raw[K];
-    arz_load_issue<K>(r_raw, rrow, M, lane);
-    arz_load_issue<K>(y_raw, yrow, M, lane);
+    T* rrow = reinterpret_cast<T*>(a.buf.ry) + env * 2 * M;
+    T* yrow = rrow + M;
+    T r[K], y[K], r_raw[K], y_raw[K];
+    arz_load_issue<K, T>(r_raw, rrow, M, lane);
+    arz_load_issue<K, T>(y_raw, yrow, M, lane);
     double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
     const double fv = (lane < PDECG_ARZ_NF64) ? frow[lane] : 0.0;
     double time = __shfl_sync(kFull, fv, PDECG_ARZ_F_TIME);
-    const double rs = __shfl_sync(kFull, fv, PDECG_ARZ_F_RS);
-    const double vs = __shfl_sync(kFull, fv, PDECG_ARZ_F_VS);
-    const double qs = __shfl_sync(kFull, fv, PDECG_ARZ_F_QS);
+    const T rs = static_cast<T>(__shfl_sync(kFull, fv, PDECG_ARZ_F_RS));
+    const T vs = static_cast<T>(__shfl_sync(kFull, fv, PDECG_ARZ_F_VS));
+    const T qs = static_cast<T>(__shfl_sync(kFull, fv, PDECG_ARZ_F_QS));
     // action_space.low / .high as built in __init__ (:97-100): NOT refreshed when 'outlet-train' re-draws qs in reset()
     const double lo = __shfl_sync(kFull, fv, PDECG_ARZ_F_ACT_LO), hi = __shfl_sync(kFull, fv, PDECG_ARZ_F_ACT_HI);
 
-    arz_load_finish<K>(r, r_raw, sm, lane);
-    arz_load_finish<K>(y, y_raw, sm, lane);
+    arz_load_finish<K, T>(r, r_raw, sm, lane);
+    arz_load_finish<K, T>(y, y_raw, sm, lane);
     // padding slots (never stored, never read by valid points) hold (rho, y) = (1, 1) so that the divisions
     // evaluated there stay on the fast path instead of div.rn's slow 0/0 path
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        if (j0 + k >= M) { r[k] = 1.0; y[k] = 1.0; }
+        if (j0 + k >= M) { r[k] = T(1); y[k] = T(1); }
     }
 
     // :148-170 -- float time advances once per step; actions clipped to the action space
-    time = D::add(time, cfg.dt);
+    time = __dadd_rn(time, cfg.dt);
     const double* act = a.buf.action + env * cfg.action_dim;
-    const double a0 = clipd(act[0], lo, hi);
-    const double a1 = (cfg.action_dim > 1) ? clipd(act[1], lo, hi) : a0;
+    const T a0 = static_cast<T>(clipd(act[0], lo, hi));
+    const T a1 = (cfg.action_dim > 1) ? static_cast<T>(clipd(act[1], lo, hi)) : a0;
     const int st = cfg.simulation_type;
-    const double q_in = (st == PDECG_ARZ_INLET || st == PDECG_ARZ_BOTH) ? a0 : qs;
-    const double q_out = (st == PDECG_ARZ_OUTLET || st == PDECG_ARZ_OUTLET_TRAIN) ? a0 : ((st == PDECG_ARZ_BOTH) ? a1 : qs);
+    const T q_in = (st == PDECG_ARZ_INLET || st == PDECG_ARZ_BOTH) ? a0 : qs;
+    const T q_out = (st == PDECG_ARZ_OUTLET || st == PDECG_ARZ_OUTLET_TRAIN) ? a0 : ((st == PDECG_ARZ_BOTH) ? a1 : qs);
 
     for (int count = 0; count < cfg.control_freq && time < cfg.T; ++count) {          // :173
         // ---- boundary conditions (:175-190) ----
         {
-            const double r_right = __shfl_down_sync(kFull, r[0], 1);                  // node j0+K
-            const double r_left = __shfl_up_sync(kFull, r[K - 1], 1);                 // node j0-1
+            const T r_right = __shfl_down_sync(kFull, r[0], 1);                  // node j0+K
+            const T r_left = __shfl_up_sync(kFull, r[K - 1], 1);                 // node j0-1
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int j = j0 + k;
-                const double rn = (k < K - 1) ? r[k < K - 1 ? k + 1 : 0] : r_right;   // r[j+1]
-                const double rp = (k > 0) ? r[k > 0 ? k - 1 : 0] : r_left;            // r[j-1]
+                const T rn = (k < K - 1) ? r[k < K - 1 ? k + 1 : 0] : r_right;   // r[j+1]
+                const T rp = (k > 0) ? r[k > 0 ? k - 1 : 0] : r_left;            // r[j-1]
                 if (j == 0) {
                     r[k] = rn;
                     y[k] = D::sub(q_in, D::mul(r[k], veq(ctx, r[k])));
@@ -146,40 +153,40 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
             }
         }
         // ---- node fluxes ----
-        double fr[K], fy[K];
+        T fr[K], fy[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             fr[k] = flux_r(ctx, r[k], y[k]);
             fy[k] = flux_y(ctx, r[k], y[k]);
         }
-        const double r_nx = __shfl_down_sync(kFull, r[0], 1), y_nx = __shfl_down_sync(kFull, y[0], 1);
-        const double fr_nx = __shfl_down_sync(kFull, fr[0], 1), fy_nx = __shfl_down_sync(kFull, fy[0], 1);
+        const T r_nx = __shfl_down_sync(kFull, r[0], 1), y_nx = __shfl_down_sync(kFull, y[0], 1);
+        const T fr_nx = __shfl_down_sync(kFull, fr[0], 1), fy_nx = __shfl_down_sync(kFull, fy[0], 1);
         // ---- midpoints j+1/2 (:202-215) and their fluxes ----
-        double ym[K], frm[K], fym[K];
+        T ym[K], frm[K], fym[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const bool lastk = (k == K - 1);
-            const double rb = lastk ? r_nx : r[lastk ? 0 : k + 1], yb = lastk ? y_nx : y[lastk ? 0 : k + 1];
-            const double frb = lastk ? fr_nx : fr[lastk ? 0 : k + 1], fyb = lastk ? fy_nx : fy[lastk ? 0 : k + 1];
-            const double rmid = D::sub(D::mul(0.5, D::add(rb, r[k])), D::mul(cfg.c1, D::sub(frb, fr[k])));
-            const double ysum = D::add(yb, y[k]);
-            const double ymid = D::sub(D::sub(D::mul(0.5, ysum), D::mul(cfg.c1, D::sub(fyb, fy[k]))), D::mul(cfg.c2, ysum));
+            const T rb = lastk ? r_nx : r[lastk ? 0 : k + 1], yb = lastk ? y_nx : y[lastk ? 0 : k + 1];
+            const T frb = lastk ? fr_nx : fr[lastk ? 0 : k + 1], fyb = lastk ? fy_nx : fy[lastk ? 0 : k + 1];
+            const T rmid = D::sub(D::mul(T(0.5), D::add(rb, r[k])), D::mul(c1, D::sub(frb, fr[k])));
+            const T ysum = D::add(yb, y[k]);
+            const T ymid = D::sub(D::sub(D::mul(T(0.5), ysum), D::mul(c1, D::sub(fyb, fy[k]))), D::mul(c2, ysum));
             ym[k] = ymid;
             frm[k] = flux_r(ctx, rmid, ymid);
             fym[k] = flux_y(ctx, rmid, ymid);
         }
-        const double ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1);
-        const double frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1);
-        const double fym_pv = __shfl_up_sync(kFull, fym[K - 1], 1);
+        const T ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1);
+        const T frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1);
+        const T fym_pv = __shfl_up_sync(kFull, fym[K - 1], 1);
         // ---- interior update (:218-222) ----
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j = j0 + k;
-            const double yl = (k == 0) ? ym_pv : ym[k > 0 ? k - 1 : 0];
-            const double frl = (k == 0) ? frm_pv : frm[k > 0 ? k - 1 : 0];
-            const double fyl = (k == 0) ? fym_pv : fym[k > 0 ? k - 1 : 0];
-            const double rnew = D::sub(r[k], D::mul(cfg.c3, D::sub(frm[k], frl)));
-            const double ynew = D::sub(y[k], D::add(D::mul(cfg.c3, D::sub(fym[k], fyl)), D::mul(cfg.c4, D::add(ym[k], yl))));
+            const T yl = (k == 0) ? ym_pv : ym[k > 0 ? k - 1 : 0];
+            const T frl = (k == 0) ? frm_pv : frm[k > 0 ? k - 1 : 0];
+            const T fyl = (k == 0) ? fym_pv : fym[k > 0 ? k - 1 : 0];
+            const T rnew = D::sub(r[k], D::mul(c3, D::sub(frm[k], frl)));
+            const T ynew = D::sub(y[k], D::add(D::mul(c3, D::sub(fym[k], fyl)), D::mul(c4, D::add(ym[k], yl))));
             const bool interior = (j >= 1) && (j <= M - 2);
             r[k] = interior ? rnew : r[k];
             y[k] = interior ? ynew : y[k];
@@ -187,24 +194,27 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
     }
 
     // ---- velocity, reward, flags, observation (:226-233) ----
-    double v[K];
+    T v[K];
     double sv = 0.0, sr = 0.0;
     bool over = false, steady = true;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const bool valid = j0 + k < M;
-        v[k] = valid ? D::add(D::div(y[k], r[k]), veq(ctx, r[k])) : 0.0;
-        const double dv = D::sub(v[k], vs), dr = D::sub(r[k], rs);
+        v[k] = valid ? D::add(D::div(y[k], r[k]), veq(ctx, r[k])) : T(0);
+        const double dv = static_cast<double>(D::sub(v[k], vs)), dr = static_cast<double>(D::sub(r[k], rs));
         if (valid) {
             sv += dv * dv;
             sr += dr * dr;
-            over = over || (v[k] > cfg.vm) || (r[k] > cfg.rm);
+            over = over || (v[k] > static_cast<T>(cfg.vm)) || (r[k] > static_cast<T>(cfg.rm));
             steady = steady && (dv == 0.0) && (dr == 0.0);
         }
     }
     sv = warp_sum(sv);
     sr = warp_sum(sr);
-    const double reward = -D::add(D::div(sqrt(sv), vs), D::div(sqrt(sr), rs));       // traffic_arz_reward.py:22
+    // traffic_arz_reward.py:22 (float64 mode: numpy's operations on float64 norms; float32 mode: the norms are float32 values)
+    const double reward = (sizeof(T) == 8)
+        ? -__dadd_rn(__ddiv_rn(sqrt(sv), static_cast<double>(vs)), __ddiv_rn(sqrt(sr), static_cast<double>(rs)))
+        : -static_cast<double>(__fadd_rn(__fdiv_rn(static_cast<float>(sqrt(sv)), static_cast<float>(vs)), __fdiv_rn(static_cast<float>(sqrt(sr)), static_cast<float>(rs))));
     over = __any_sync(kFull, over);
     steady = __all_sync(kFull, steady);
     bool term = time >= cfg.t_over_dt;                                                // :109-111
@@ -212,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
     const bool trunc = (cfg.limit_pde_state_size && over) || steady;                  // :122-127
     if (st != PDECG_ARZ_OUTLET_TRAIN) term = term || (reward > -0.00023);             // :233
 
-    arz_store<K>(r, rrow, M, sm, lane);
-    arz_store<K>(y, yrow, M, sm, lane);
+    arz_store<K, T>(r, rrow, M, sm, lane);
+    arz_store<K, T>(y, yrow, M, sm, lane);
     const bool restart = a.ar_profile != nullptr && (term || trunc);
     if (st == PDECG_ARZ_OUTLET_TRAIN) {                                               // :231
 #pragma unroll
@@ -222,13 +232,13 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
             v[k] = D::div(D::sub(v[k], vs), vs);
         }
     }
-    double* orow = a.buf.obs + env * 2 * M;
-    arz_store<K>(r, orow, M, sm, lane);
-    arz_store<K>(v, orow + M, M, sm, lane);
+    T* orow = reinterpret_cast<T*>(a.buf.obs) + env * 2 * M;
+    arz_store<K, T>(r, orow, M, sm, lane);
+    arz_store<K, T>(v, orow + M, M, sm, lane);
     if (restart && a.buf.final_obs != nullptr) {                                      // terminal observation for the caller
-        double* frow_obs = a.buf.final_obs + env * 2 * M;
-        arz_store<K>(r, frow_obs, M, sm, lane);
-        arz_store<K>(v, frow_obs + M, M, sm, lane);
+        T* frow_obs = reinterpret_cast<T*>(a.buf.final_obs) + env * 2 * M;
+        arz_store<K, T>(r, frow_obs, M, sm, lane);
+        arz_store<K, T>(v, frow_obs + M, M, sm, lane);
     }
     if (lane == 0) {
         frow[PDECG_ARZ_F_TIME] = time;
@@ -236,25 +246,27 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
         a.buf.terminated[env] = term ? 1 : 0;
         a.buf.truncated[env] = trunc ? 1 : 0;
     }
-    if (restart) arz_autoreset_env(a, env, lane);
+    if (restart) arz_autoreset_env<T>(a, env, lane);
 }
 
 // TrafficPDE1D.reset (:237-267) for one env, executed by its warp.  `keep_outputs`: leave reward / flags alone
 // (fused auto-reset: they keep the step's values).
+template <typename T>
 __device__ __forceinline__ void arz_reset_env(const ArzArgs& a, const double* __restrict__ profile, int64_t env, int lane,
                                               bool keep_outputs) {
+    using D = Strict<T>;
     const pdecg_arz_cfg& cfg = a.cfg;
-    const ArzCtx ctx(cfg);
+    const ArzCtx<T> ctx(cfg);
     const int M = cfg.M;
     const double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
-    const double rs = frow[PDECG_ARZ_F_RS], qs = frow[PDECG_ARZ_F_QS];
-    double* rrow = a.buf.ry + env * 2 * M;
-    double* orow = a.buf.obs + env * 2 * M;
+    const T rs = static_cast<T>(frow[PDECG_ARZ_F_RS]), qs = static_cast<T>(frow[PDECG_ARZ_F_QS]);
+    T* rrow = reinterpret_cast<T*>(a.buf.ry) + env * 2 * M;
+    T* orow = reinterpret_cast<T*>(a.buf.obs) + env * 2 * M;
     for (int j = lane; j < M; j += 32) {
         // :259-261  r = rs*profile ; y = qs*1 - vm*r + (vm/rm)*r**2 ; v = y/r + Veq(r)
-        const double r = D::mul(rs, profile[j]);
-        const double y = D::add(D::sub(D::mul(qs, 1.0), D::mul(cfg.vm, r)), D::mul(cfg.vm_over_rm, D::mul(r, r)));
-        const double v = D::add(D::div(y, r), veq(ctx, r));
+        const T r = D::mul(rs, static_cast<T>(profile[j]));
+        const T y = D::add(D::sub(D::mul(qs, T(1)), D::mul(static_cast<T>(cfg.vm), r)), D::mul(static_cast<T>(cfg.vm_over_rm), D::mul(r, r)));
+        const T v = D::add(D::div(y, r), veq(ctx, r));
         rrow[j] = r;
         rrow[M + j] = y;
         orow[j] = r;                               // reset() returns concat(r, v) un-normalised in every mode,
@@ -268,18 +280,20 @@ __device__ __forceinline__ void arz_reset_env(const ArzArgs& a, const double* __
 }
 
 // fused same-step auto-reset: out of line so the (rare) restart does not weigh on the step kernel's registers
+template <typename T>
 __device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane) {
     __syncwarp();                                  // the step's own row / observation stores come first
-    arz_reset_env(a, a.ar_profile, env, lane, true);
+    arz_reset_env<T>(a, a.ar_profile, env, lane, true);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads) arz_reset_kernel(const ArzArgs a, const double* __restrict__ profile,
                                                              const uint8_t* __restrict__ mask) {
     const int lane = threadIdx.x & 31;
     const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
     if (env >= a.buf.n_envs) return;
     if (mask != nullptr && mask[env] == 0) return;
-    arz_reset_env(a, profile, env, lane, false);
+    arz_reset_env<T>(a, profile, env, lane, false);
 }
 
 static int arz_validate(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf) {
@@ -290,6 +304,7 @@ static int arz_validate(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf) 
     if (cfg->M > 512) return fail(PDECG_ERR_UNSUPPORTED, "grid of %d points exceeds the register-resident limit of 512 points per env", cfg->M);
     if (cfg->control_freq < 1) return fail(PDECG_ERR_INVALID, "control_freq must be a positive integer (got %d)", cfg->control_freq);
     if (cfg->action_dim != ((cfg->simulation_type == PDECG_ARZ_BOTH) ? 2 : 1)) return fail(PDECG_ERR_INVALID, "action_dim must be 2 for 'both', else 1");
+    if (cfg->precision < PDECG_PREC_REF || cfg->precision > PDECG_PREC_FP32) return fail(PDECG_ERR_INVALID, "bad precision %d", cfg->precision);
     if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (buf->n_envs > 0 && (!buf->ry || !buf->obs || !buf->fenv || !buf->reward || !buf->terminated || !buf->truncated))
         return fail(PDECG_ERR_INVALID, "null device buffer");
@@ -308,7 +323,8 @@ extern "C" int pdecg_arz_reset(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers
     if (!profile) return fail(PDECG_ERR_INVALID, "null profile buffer");
     ArzArgs a{*cfg, *buf, nullptr};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    arz_reset_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, profile, mask);
+    if (cfg->precision == PDECG_PREC_FP32) arz_reset_kernel<float><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, profile, mask);
+    else arz_reset_kernel<double><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, profile, mask);
     count_launch();
     return check_launch("arz_reset_kernel");
 }
@@ -324,7 +340,11 @@ static int arz_launch_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* bu
     int K = (cfg->M + 31) / 32;
     if (K > 8) K = (K + 1) / 2 * 2;                    // 257..512 points: even K in {10, 12, 14, 16}
     switch (K) {
-#define PDECG_CASE(KK) case KK: arz_step_kernel<KK><<<grid, kThreads, 0, st>>>(a); break;
+#define PDECG_CASE(KK)                                                                          \
+    case KK:                                                                                    \
+        if (cfg->precision == PDECG_PREC_FP32) arz_step_kernel<KK, float><<<grid, kThreads, 0, st>>>(a); \
+        else arz_step_kernel<KK, double><<<grid, kThreads, 0, st>>>(a);                          \
+        break;
         PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
         PDECG_CASE(10) PDECG_CASE(12) PDECG_CASE(14) PDECG_CASE(16)
 #undef PDECG_CASE
@@ -357,7 +377,8 @@ extern "C" int pdecg_arz_step_host(const pdecg_arz_cfg* cfg, const pdecg_arz_buf
     cudaError_t e = cudaMemcpyAsync(const_cast<double*>(buf->action), action_host, n * cfg->action_dim * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
     if ((rc = arz_launch_step(cfg, buf, autoreset_profile, stream)) != PDECG_OK) return rc;
-    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->obs, n * 2 * cfg->M * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+    const size_t esz = cfg->precision == PDECG_PREC_FP32 ? sizeof(float) : sizeof(double);
+    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->obs, n * 2 * cfg->M * esz, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
     if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
     if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
     if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));

@@ -88,6 +88,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                  env_id_offset: int = 0,
                  obs_dtype: Optional[str] = None,
                  final_obs: bool = False,
+                 truncate_nonfinite: bool = False,
                  **kwargs):
         super().__init__(**kwargs)
         self.sensing_noise_func = sensing_noise_func
@@ -145,6 +146,9 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         cfg.max_control_value = float(max_control_value)
         cfg.limit_pde_state_size = int(bool(limit_pde_state_size))
         cfg.max_state_value = float(max_state_value)
+        # info["nonfinite"]: per-env blow-up flag (inf / NaN in the state row), always reported; truncate_nonfinite=True also
+        # ends the episode of such an env (not reference behaviour: there inf / NaN just propagate)
+        cfg.truncate_nonfinite = int(bool(truncate_nonfinite))
         if isinstance(rw, TunedReward1D):
             cfg.reward_kind = 0
             cfg.norm_ord, cfg.horizon, cfg.t_horizon_length, cfg.norm_coeff = 2, 0, 1, 1.0
@@ -361,7 +365,9 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             self._buf.obs_copy = obs_out.data_ptr()
         # the kernel writes reward / flags straight into fresh tensors handed to the caller (no clone launches)
         reward, term_u8, trunc_u8 = torch.empty_like(self._reward), torch.empty_like(self._terminated), torch.empty_like(self._truncated)
+        nonfin_u8 = torch.empty_like(self._terminated)
         self._buf.reward, self._buf.terminated, self._buf.truncated = reward.data_ptr(), term_u8.data_ptr(), trunc_u8.data_ptr()
+        self._buf.nonfinite = nonfin_u8.data_ptr()
         ke = self._kernel_events          # optional (start, stop) CUDA events bracketing only the step kernel
         try:
             with torch.cuda.device(self.device):
@@ -377,8 +383,10 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
             # rows of the envs with terminated | truncated this step are fresh (SB3 "terminal_observation")
             info = {"final_obs": self._final_obs} if (self.autoreset and self._final_obs is not None) else {}
+            info["nonfinite"] = nonfin_u8.view(torch.bool)
         finally:
             self._buf.obs_copy = None            # never leave a pointer to a caller-owned tensor behind
+            self._buf.nonfinite = None
             self._buf.reward, self._buf.terminated, self._buf.truncated = (
                 self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr())
         if obs_out is not None:

@@ -42,8 +42,11 @@ class BrainTumor1D(StateDictMixin):
                  *, T, dt, X, dx, reward_class=None, normalize=False,
                  num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False,
                  final_obs: bool = False):
-        if precision not in ("ref", "fp64"):
-            raise ValueError("BrainTumor1D is float64 in the reference; precision must be 'ref' or 'fp64'")
+        if precision not in ("ref", "fp64", "fp32"):
+            raise ValueError("precision must be 'ref' / 'fp64' (float64 like the reference) or 'fp32' (opt-in fast mode: float32 "
+                             "state, observation and finite-difference arithmetic)")
+        self.precision = precision
+        self.state_dtype = torch.float32 if precision == "fp32" else torch.float64
         if reward_class is not None and not isinstance(reward_class, BrainTumorReward):
             raise TypeError("reward_class must be a pdecontrolgym_b200.BrainTumorReward (evaluated inside the kernel)")
         self.num_envs = N = int(num_envs)
@@ -77,12 +80,13 @@ class BrainTumor1D(StateDictMixin):
         cfg.alpha, cfg.alpha_beta_ratio = float(alpha), float(alpha_beta_ratio)
         cfg.t1_detection_radius, cfg.t1_death_radius = float(t1_detection_radius), float(t1_death_radius)
         cfg.total_dosage = self.total_dosage
+        cfg.precision = _lib.PREC[precision]
         self._cfg = cfg
         self._L = _lib.lib()
         dev = self.device
         with torch.cuda.device(dev):
-            self.u = torch.zeros((N, self.nx), dtype=torch.float64, device=dev)
-            self._obs = torch.zeros((N, self.nx), dtype=torch.float64, device=dev)
+            self.u = torch.zeros((N, self.nx), dtype=self.state_dtype, device=dev)
+            self._obs = torch.zeros((N, self.nx), dtype=self.state_dtype, device=dev)
             self.xScale = torch.from_numpy(np.linspace(0, X, self.nx)).to(dev)      # :57
             self._ienv = torch.zeros((N, NINT), dtype=torch.int32, device=dev)
             self._ienv[:, [I_FIRST_THERAPY, I_FIRST_POST, I_DEATH, I_TBENCH]] = -1
@@ -96,7 +100,7 @@ class BrainTumor1D(StateDictMixin):
             self._valid = torch.ones((N,), dtype=torch.uint8, device=dev)
             self._zero_action = torch.zeros((N,), dtype=torch.float64, device=dev)
             # autoreset + final_obs: the state row of the day that ended an episode, kept for the envs that restarted
-            self._final_obs = torch.zeros((N, self.nx), dtype=torch.float64, device=dev) if final_obs else None
+            self._final_obs = torch.zeros((N, self.nx), dtype=self.state_dtype, device=dev) if final_obs else None
         buf = _lib.BtBuffers()
         buf.n_envs = N
         buf.u, buf.obs, buf.x_scale = self.u.data_ptr(), self._obs.data_ptr(), self.xScale.data_ptr()
@@ -111,15 +115,16 @@ class BrainTumor1D(StateDictMixin):
     def _stream(self):
         return _lib.current_raw_stream(self.device.index)
 
-    def _run(self, mode, action=None, autoreset=False, mask_t=None):
+    def _run(self, mode, action=None, autoreset=False, mask_t=None, obs_out=None):
         """One launch.  The kernel writes reward / flags / valid straight into fresh tensors handed to the caller (no
         clone launches); returns (reward, terminated_u8, truncated_u8, valid_u8).  `autoreset` (RAW_STEP only): envs
         that finish restart from the last initial condition inside the same launch."""
         a = self._zero_action if action is None else action
         buf = self._buf
         buf.action = a.data_ptr()
-        # the raw step's observation is the state itself: no second [N, nx] write (HBM-bound launch)
-        buf.obs = None if mode == RAW_STEP else self._obs.data_ptr()
+        # the raw step's observation is the state itself: a second [N, nx] row is written only when the caller wants a
+        # private copy (`obs_out`, a fresh tensor: one launch instead of step + clone)
+        buf.obs = (None if obs_out is None else obs_out.data_ptr()) if mode == RAW_STEP else self._obs.data_ptr()
         outs = tuple(torch.empty_like(t) for t in (self._reward, self._terminated, self._truncated, self._valid))
         buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
         buf.final_obs = self._final_obs.data_ptr() if (autoreset and self._final_obs is not None) else None
@@ -202,9 +207,10 @@ class BrainTumor1D(StateDictMixin):
         if self._ic is None:
             raise RuntimeError("call reset() before step()")
         # same-step auto-reset is part of the step launch (the returned observation is the restarted state)
-        outs = self._run(RAW_STEP, self._prep_action(control), autoreset=self.autoreset)
+        obs = torch.empty_like(self.u) if self.copy_obs else None
+        outs = self._run(RAW_STEP, self._prep_action(control), autoreset=self.autoreset, obs_out=obs)
         rest = self._out_rest(outs)
-        return ((self.u.clone() if self.copy_obs else self.u),) + rest
+        return ((obs if self.copy_obs else self.u),) + rest
 
     def step_host(self, action_host, obs_host=None, reward_host=None, terminated_host=None, truncated_host=None, valid_host=None):
         """End-to-end raw step over HOST buffers (pdecg_bt_step_host): H2D(actions) -> kernel -> D2H(state, reward,
@@ -223,7 +229,7 @@ class BrainTumor1D(StateDictMixin):
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_bt_step_host(
                 C.byref(self._cfg), C.byref(buf), a_ptr,
-                _lib.host_ptr(obs_host, torch.float64, N * self.nx, "obs_host"),
+                _lib.host_ptr(obs_host, self.state_dtype, N * self.nx, "obs_host"),
                 _lib.host_ptr(reward_host, torch.float64, N, "reward_host"),
                 _lib.host_ptr(terminated_host, torch.uint8, N, "terminated_host"),
                 _lib.host_ptr(truncated_host, torch.uint8, N, "truncated_host"),

@@ -33,8 +33,11 @@ class TrafficPDE1D(StateDictMixin):
                  *, T, dt, X, dx, reward_class=None, normalize=False,
                  num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False,
                  rs_init=None, final_obs: bool = False):
-        if precision not in ("ref", "fp64"):
-            raise ValueError("TrafficPDE1D is float64 in the reference; precision must be 'ref' or 'fp64'")
+        if precision not in ("ref", "fp64", "fp32"):
+            raise ValueError("precision must be 'ref' / 'fp64' (float64 like the reference: bit-identical) or 'fp32' (opt-in fast "
+                             "mode: float32 state, observation and arithmetic)")
+        self.precision = precision
+        self.state_dtype = torch.float32 if precision == "fp32" else torch.float64
         if reward_class is not None and not isinstance(reward_class, TrafficARZReward):
             raise TypeError("reward_class must be a pdecontrolgym_b200.TrafficARZReward (evaluated inside the kernel)")
         assert isinstance(control_freq, int) and control_freq >= 1, \
@@ -92,19 +95,20 @@ class TrafficPDE1D(StateDictMixin):
         cfg.c3 = dt / dx                                                   # :218
         cfg.c4 = 0.5 * dt / tau                                            # :221
         cfg.vm_over_rm = v_max / ro_max                                    # :84
+        cfg.precision = _lib.PREC[precision]
         self._cfg = cfg
         self._L = _lib.lib()
         dev = self.device
         with torch.cuda.device(dev):
-            self._ry = torch.zeros((N, 2, self.M), dtype=torch.float64, device=dev)
-            self._obs = torch.zeros((N, 2 * self.M), dtype=torch.float64, device=dev)
+            self._ry = torch.zeros((N, 2, self.M), dtype=self.state_dtype, device=dev)
+            self._obs = torch.zeros((N, 2 * self.M), dtype=self.state_dtype, device=dev)
             self._fenv = torch.zeros((N, NF64), dtype=torch.float64, device=dev)
             self._profile = torch.from_numpy(self._profile_np.copy()).to(dev)
             self._reward = torch.zeros((N,), dtype=torch.float64, device=dev)
             self._terminated = torch.zeros((N,), dtype=torch.uint8, device=dev)
             self._truncated = torch.zeros((N,), dtype=torch.uint8, device=dev)
             # autoreset + final_obs: the observation of the step that ended an episode, kept for the envs that restarted
-            self._final_obs = torch.zeros((N, 2 * self.M), dtype=torch.float64, device=dev) if final_obs else None
+            self._final_obs = torch.zeros((N, 2 * self.M), dtype=self.state_dtype, device=dev) if final_obs else None
         self._last_obs = None
         buf = _lib.ArzBuffers()
         buf.n_envs = N
@@ -254,7 +258,7 @@ class TrafficPDE1D(StateDictMixin):
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_arz_step_host(
                 C.byref(self._cfg), C.byref(buf), a_ptr,
-                _lib.host_ptr(obs_host, torch.float64, N * 2 * self.M, "obs_host"),
+                _lib.host_ptr(obs_host, self.state_dtype, N * 2 * self.M, "obs_host"),
                 _lib.host_ptr(reward_host, torch.float64, N, "reward_host"),
                 _lib.host_ptr(terminated_host, torch.uint8, N, "terminated_host"),
                 _lib.host_ptr(truncated_host, torch.uint8, N, "truncated_host"),
@@ -271,7 +275,7 @@ class TrafficPDE1D(StateDictMixin):
 
     @property
     def v(self):
-        r, y = self.r, self.y
+        r, y = self.r.double(), self.y.double()
         return y / r + self.vm * (1 - r / self.rm)
 
     @property

@@ -398,3 +398,38 @@ def test_therapy_wrapper_masked_reset_keeps_the_other_patients(cuda_device):
             np.testing.assert_allclose(o[i].cpu().numpy(), o2[0], rtol=1e-13, atol=0, err_msg=f"call {k} env {i}")
             assert float(r[i]) == float(r2[0]) and bool(te[i]) == bool(te2[0]) and bool(tr[i]) == bool(tr2[0])
         assert env.time_index.cpu().tolist() == [int(e.t[0]) for e in oenvs], f"call {k}: day counters (weekend placement)"
+
+
+def test_nonfinite_flag_and_optional_truncation(cuda_device):
+    """ReactionDiffusion with Neumann control and normalize=True overflows to inf within a few steps (reference quirk Q4,
+    parabolic.py:148-150).  info['nonfinite'] flags exactly the envs whose state row holds an inf / NaN (the oracle's
+    np.isfinite), and truncate_nonfinite=True ends their episodes (an opt-in extension: the reference lets inf / NaN run on)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    from oracle import np_oracle as O
+    from tests.helpers import bc1d_case, make_ics
+    B, steps = 6, 6
+    kw, npts, beta, nt = bc1d_case("rd", None, steps)
+    common = dict(normalize=True, control_type="Neumann", max_control_value=20, **kw)
+    rng = np.random.default_rng(8)
+    ics = make_ics(rng, B, npts)
+    ics[::2] *= 1e-30                                   # every other env stays tiny for a while longer
+    orc = O.ReactionDiffusionOracle(B, reward=O.NormRewardSpec(nt - 1, norm=2), precision="ref", **common)
+    env = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=B, device=cuda_device, precision="ref", reward_class=pcg.NormReward(nt - 1, norm="2"), **common)
+    env_t = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=B, device=cuda_device, precision="ref", reward_class=pcg.NormReward(nt - 1, norm="2"),
+                     truncate_nonfinite=True, **common)
+    orc.reset(ics, beta.astype(np.float32))
+    for e in (env, env_t):
+        e.reset(options={"init_condition": ics, "beta": beta.astype(np.float32)})
+    seen = False
+    for k in range(steps - 1):
+        a = rng.uniform(-1, 1, B).astype(np.float32)
+        o_r, r_r, te_r, tr_r = orc.step(a)
+        o, r, te, tr, info = env.step(torch.from_numpy(a))
+        o2, r2, te2, tr2, info2 = env_t.step(torch.from_numpy(a))
+        bad = ~np.isfinite(o_r).all(axis=1)
+        assert np.array_equal(info["nonfinite"].cpu().numpy(), bad), f"step {k}"
+        assert not tr.any() and np.array_equal(tr2.cpu().numpy(), bad)
+        assert np.array_equal(o.cpu().numpy(), o_r, equal_nan=True)
+        seen |= bool(bad.any())
+    assert seen

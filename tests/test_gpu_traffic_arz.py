@@ -121,3 +121,34 @@ def test_fused_autoreset_final_obs(cuda_device):
         else:
             assert np.array_equal(o_g.cpu().numpy(), o_r)
     assert seen >= 1
+
+
+@pytest.mark.parametrize("st", ["outlet", "both"])
+def test_fp32_fast_mode_tolerance_and_event_agreement(cuda_device, st):
+    """precision='fp32' (opt-in): float32 state / observation / arithmetic.  Stated tolerance against the float64 mode over
+    the whole integrating part of an episode (959 steps, tutorial defaults, actions around qs): observations within 2e-4
+    relative L2 per step, rewards within 2e-4 absolute; discrete events (terminated / truncated) must agree on >= 99.9 % of
+    env-steps (event agreement rather than trajectory L2 where a threshold can flip)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    B = 64
+    kw = dict(T=240, dt=0.25, X=500, dx=10, simulation_type=st, limit_pde_state_size=True, reward_class=pcg.TrafficARZReward())
+    e64 = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, precision="fp64", **kw)
+    e32 = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, precision="fp32", **kw)
+    o64, _ = e64.reset()
+    o32, _ = e32.reset()
+    assert o32.dtype == torch.float32 and torch.allclose(o32.double(), o64, rtol=1e-6)
+    rng = np.random.default_rng(0)
+    nact = 2 if st == "both" else 1
+    agree, total, worst_obs, worst_rew = 0, 0, 0.0, 0.0
+    for k in range(959):
+        a = torch.from_numpy(rng.uniform(0.9 * 1.2, 1.1 * 1.2, (B, nact)))
+        o64, r64, te64, tr64, _ = e64.step(a)
+        o32, r32, te32, tr32, _ = e32.step(a)
+        err = torch.linalg.norm(o32.double() - o64, dim=1) / torch.linalg.norm(o64, dim=1)
+        worst_obs = max(worst_obs, float(err.max()))
+        worst_rew = max(worst_rew, float((r32 - r64).abs().max()))
+        agree += int(((te32 == te64) & (tr32 == tr64)).sum())
+        total += B
+    assert worst_obs < 2e-4 and worst_rew < 2e-4, (worst_obs, worst_rew)
+    assert agree / total >= 0.999, agree / total
