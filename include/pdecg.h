@@ -405,6 +405,40 @@ int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, const doubl
                             double* p, void* work, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Family 5: NeuronPDE1D (neuron growth control; closed loop: step() takes no action)   -- float64
+ * ------------------------------------------------------------------------------------------ */
+/* Constants the reference derives in its constructor (neuron_env.py:60-259), passed as the Python floats it forms. */
+typedef struct {
+    int32_t abi_version;
+    int32_t M;                   /* len(np.arange(0, length + dx, dx))                 :204 */
+    int32_t nt;                  /* int(round(T/dt)+1)                                 base_env_1d.py:23 */
+    int32_t reserved;
+    double dt, dx;
+    double D, a, g, RSubG;
+    double aTilde1;              /* ((a - RSubG*cInfty)/LSubC) - g - TildeRSubG        :79 */
+    double beta;                 /* D / LSubC                                          :83 */
+    double LSubS;
+    double inv_scale;            /* float(1 / SpatialToRealScale)                      :365 */
+    double H0, H1;               /* H = [1, -((a - g*LSubC)*cInfty)/D]                 :76-78 */
+    double coef;                 /* (H.T @ B)/D + gamma                                :298 */
+} pdecg_neuron_cfg;
+
+typedef struct {
+    int64_t n_envs;
+    double* u;               /* [n_envs, M] error system u(x, t); points beyond L keep their last values          */
+    double* Z;               /* [n_envs, 2] ODE state (cone concentration error, axon length error)               */
+    int32_t* L;              /* [n_envs] grid index of the moving boundary l(t)                                   */
+    double* time;            /* [n_envs] the float `time_index` (advances by dt per step, zeroed by terminate()) */
+    double* control;         /* [n_envs] the backstepping input U(t) of the last step (ControlInput, :305)        */
+    const double* pB;        /* [M]    p(x_i) @ B, evaluated by the caller exactly as the reference does (:294)    */
+    const double* p;         /* [M, 2] gain kernel p(x) (:241-243; scipy expm on the host)                        */
+    uint8_t* terminated;     /* [n_envs] terminate() fired during this call                                       */
+} pdecg_neuron_buffers;
+
+/* NeuronPDE1D.step (:263-339) applied n_steps times to every env in one launch (state stays in registers). */
+int pdecg_neuron_step(const pdecg_neuron_cfg* cfg, const pdecg_neuron_buffers* buf, int32_t n_steps, pdecg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Misc
  * ------------------------------------------------------------------------------------------ */
 const char* pdecg_last_error(void);

@@ -745,3 +745,104 @@ class NavierStokesOracle:
             - self.gamma / 2 * np.linalg.norm(a[b] - self.action_ref[self.t]) ** 2
             for b in range(self.B)])
         return U, rew, term, np.zeros(self.B, dtype=bool)
+
+
+# --------------------------------------------------------------------------------------------
+# NeuronPDE1D (neuron_env.py:8-372) -- a closed-loop simulation: step() takes NO action, the boundary input is the
+# env's own backstepping law.  The reference class cannot run as shipped (`self.atilde1` at :288 vs `aTilde1` at :78, the
+# constructor default sensing_loc="Full" raises, there is no reset()); tests pin this restatement to the class with those
+# two defects shimmed from outside (attribute alias, sensing_loc="full").  Two-element `@` products of the reference go
+# through BLAS (FMA or not, depending on the host) -- they are written out as plain products and sums here, so the pin is
+# to 1e-12, not bit for bit.
+# --------------------------------------------------------------------------------------------
+class NeuronOracle:
+    def __init__(self, B, T, dt, X, dx, cInfty=0.0119, LSubS=12e-6, k1=-1e3, k2=1e13, LSubZero=1e-6, LSubC=4e-6, a=1e-8,
+                 g=5e-7, D=10e-12, TildeRSubG=0.053, RSubG=1.783e-5):
+        from scipy.linalg import expm
+        self.B_envs = B
+        self.T, self.dt, self.X, self.dx = T, dt, X, dx
+        self.nt = int(round(T / dt) + 1)
+        self.cInfty, self.LSubS, self.LSubZero, self.LSubC = cInfty, LSubS, LSubZero, LSubC
+        self.a, self.g, self.D, self.TildeRSubG, self.RSubG = a, g, D, TildeRSubG, RSubG
+        self.gamma = (a / D) * 10                                                   # :75
+        H = np.zeros([2, 1]); H[0, 0] = 1; H[1, 0] = -1 * (((a - g * LSubC) * (cInfty)) / D)     # :76-78
+        self.aTilde1 = ((a - RSubG * cInfty) / LSubC) - g - TildeRSubG              # :79
+        Asub1 = np.array([[self.aTilde1, 0.0], [RSubG, 0.0]])
+        self.beta = D / LSubC
+        Bv = np.zeros([2, 1]); Bv[0, 0] = -1 * self.beta
+        s = np.sqrt(a ** 2 + 4 * D * g)
+        LambdaMinus = (a - s) / (2 * D)
+        LambdaPlus = (a + s) / (2 * D)
+        Kminus = 0.5 - ((a - 2 * g * LSubC) / 2) / s
+        Kplus = 0.5 + ((a - 2 * g * LSubC) / 2) / s
+        K = np.zeros([2, 1]); K[0, 0] = k1; K[1, 0] = k2
+        self.length, self.scale = X, 1                                              # :164-169
+        while self.length < 1:
+            self.length = self.length * 10
+            self.scale = self.scale / 10
+        I2, Z2 = np.eye(2), np.zeros((2, 2))
+        TR = (1.0 / D) * (g * I2 + Asub1 + (a / D) * (Bv @ H.T))
+        BR = (1.0 / D) * (Bv @ H.T + a * I2)
+        N1 = np.block([[Z2, TR], [I2, BR]])
+        Row = np.hstack([H.T, K.T - ((H.T @ Bv @ H.T) / D)])
+        Iv, Ivf = np.vstack([I2, np.zeros((2, 2))]), np.vstack([np.zeros((2, 2)), I2])
+        x = np.arange(0, self.length + dx, dx)
+        self.M = len(x)
+        dist = (self.scale * x) - LSubS
+        self.CSubEq = cInfty * (Kplus * np.exp(LambdaPlus * dist) + Kminus * np.exp(LambdaMinus * dist))
+        phi = np.stack([(Row @ expm(-1 * self.scale * (xi) * N1) @ Iv).ravel() for xi in x])
+        phip = np.stack([(Row @ expm(-1 * (self.scale) * (xi) * N1) @ Ivf).ravel() for xi in x])
+        self.p = phip - (self.gamma * phi)                                           # :243
+        self.pB = np.array([(self.p[i, :] @ Bv)[0] for i in range(self.M)])         # p[i,:] @ B  (B[1] == 0: exact either way)
+        self.H0, self.H1 = H[0, 0], H[1, 0]
+        self.coef = ((H.T @ Bv) / D + self.gamma)[0, 0]                              # :298
+        self.reset()
+
+    def conversion(self, z1):                                                       # :363-372
+        lt_code = float(1 / self.scale) * (z1 + self.LSubS)
+        raw = np.rint(lt_code / self.dx).astype(np.int64)                           # python round(): half to even
+        return np.clip(raw, 1, self.M - 1)
+
+    def reset(self):
+        B = self.B_envs
+        self.u = np.tile(2 * self.cInfty - self.CSubEq, (B, 1))                      # :224-225
+        self.Z = np.tile(np.array([self.cInfty, self.LSubZero - self.LSubS]), (B, 1))
+        self.L = self.conversion(self.Z[:, 1])
+        self.time_index = np.zeros(B)
+        self.control = np.zeros(B)
+        return self.u.copy()
+
+    def step(self):
+        """One explicit step of every env (:263-339).  Returns (u [B, M], L [B], terminated [B])."""
+        dx, dt, D, a, g = self.dx, self.dt, self.D, self.a, self.g
+        Bn = self.B_envs
+        self.time_index = self.time_index + dt
+        lt = self.Z[:, 1] + self.LSubS
+        dxr = dx * lt
+        temp, ZOld, L = self.u.copy(), self.Z.copy(), self.L
+        ar = np.arange(Bn)
+        uL, uL1, uL2 = temp[ar, L], temp[ar, L - 1], temp[ar, L - 2]
+        Z0 = (self.aTilde1 * ZOld[:, 0] - (self.beta) * ((3 * uL - 4 * uL1 + uL2) / (2 * dxr))) * dt + ZOld[:, 0]
+        Z1 = (self.RSubG * ZOld[:, 0]) * dt + ZOld[:, 1]
+        self.Z = np.stack([Z0, Z1], axis=1)
+        Ln = self.conversion(Z1)
+        u = temp.copy()
+        for b in range(Bn):
+            s = 0.0
+            for i in range(1, Ln[b]):                                               # :293-294 sequential accumulation
+                s += dxr[b] * self.pB[i] * temp[b, i]
+            mid = (((dxr[b]) * self.pB[0] * temp[b, 0]) / 2 + s + ((dxr[b] / 2) * self.pB[Ln[b]] * temp[b, Ln[b]])) / D
+            pz = self.p[Ln[b], 0] * Z0[b] + self.p[Ln[b], 1] * Z1[b]
+            ctl = lt[b] * (self.coef * temp[b, 0] - mid + pz)
+            self.control[b] = ctl
+            ufic = temp[b, 1] - ctl * dxr[b] * 2
+            u[b, 0] = ((D / (dxr[b] ** 2)) * (temp[b, 1] - 2 * temp[b, 0] + ufic) - a / (2 * dxr[b]) * (temp[b, 1] - ufic) - g * temp[b, 0]) * dt + temp[b, 0]
+            n = np.arange(1, Ln[b])
+            uxx = (temp[b, n + 1] - 2 * temp[b, n] + temp[b, n - 1]) / (dxr[b] ** 2)
+            ux = (temp[b, n + 1] - temp[b, n - 1]) / dxr[b]
+            u[b, n] = temp[b, n] + dt * (D * uxx + (((n - 1) / lt[b]) * (self.RSubG * ZOld[b, 0]) * (temp[b, n + 1] - temp[b, n - 1]) / 2) - a * ux / (2) - g * temp[b, n])
+            u[b, Ln[b]] = self.H0 * Z0[b] + self.H1 * Z1[b]
+        self.u, self.L = u, Ln
+        term = self.time_index >= self.nt
+        self.time_index = np.where(term, 0.0, self.time_index)
+        return self.u.copy(), self.L.copy(), term

@@ -17,6 +17,7 @@ from .envs_bc1d import ReactionDiffusionPDE1D, TransportPDE1D, UniformScaleIC
 from .envs_brain_tumor import BrainTumor1D, TherapyWrapper
 from .envs_traffic_arz import TrafficPDE1D
 from .envs_navier_stokes import NavierStokes2D, central_difference, laplace
+from .envs_neuron import NeuronPDE1D
 from .dist import EpisodeStats, shard_range
 from . import adapters, controllers
 from .graph import GraphedStep
@@ -32,6 +33,8 @@ REGISTRY = {
     "PDEControlGym-BrainTumor1D": BrainTumor1D,
     "PDEControlGym-TrafficPDE1D": TrafficPDE1D,
     "PDEControlGym-NavierStokes2D": NavierStokes2D,
+    # not registered by the reference (neuron_env.py is not even exported there); offered under the id its docs imply
+    "PDEControlGym-NeuronPDE1D": NeuronPDE1D,
 }
 
 
@@ -44,5 +47,5 @@ def make(id: str, num_envs: int = 1, device="cuda", precision: str = "ref", **kw
 
 make_vec = make
 
-__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "central_difference", "laplace", "EpisodeStats", "shard_range", "UniformScaleIC", "GraphedStep", "PdecgError", "BaseReward",
+__all__ = ["make", "make_vec", "REGISTRY", "TransportPDE1D", "ReactionDiffusionPDE1D", "BrainTumor1D", "TherapyWrapper", "TrafficPDE1D", "NavierStokes2D", "NeuronPDE1D", "central_difference", "laplace", "EpisodeStats", "shard_range", "UniformScaleIC", "GraphedStep", "PdecgError", "BaseReward",
            "NormReward", "TunedReward1D", "NSReward", "TrafficARZReward", "BrainTumorReward"]

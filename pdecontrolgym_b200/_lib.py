@@ -110,6 +110,22 @@ class NsBuffers(C.Structure):
     ]
 
 
+class NeuronCfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("M", C.c_int32), ("nt", C.c_int32), ("reserved", C.c_int32), ("dt", C.c_double),
+        ("dx", C.c_double), ("D", C.c_double), ("a", C.c_double), ("g", C.c_double), ("RSubG", C.c_double),
+        ("aTilde1", C.c_double), ("beta", C.c_double), ("LSubS", C.c_double), ("inv_scale", C.c_double),
+        ("H0", C.c_double), ("H1", C.c_double), ("coef", C.c_double),
+    ]
+
+
+class NeuronBuffers(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("u", C.c_void_p), ("Z", C.c_void_p), ("L", C.c_void_p), ("time", C.c_void_p),
+        ("control", C.c_void_p), ("pB", C.c_void_p), ("p", C.c_void_p), ("terminated", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -176,6 +192,8 @@ def lib():
     L.pdecg_ns_workspace_bytes.restype = C.c_size_t
     L.pdecg_selftest_constdiv.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_selftest_constdiv.restype = C.c_int
+    L.pdecg_neuron_step.argtypes = [C.POINTER(NeuronCfg), C.POINTER(NeuronBuffers), C.c_int32, C.c_void_p]
+    L.pdecg_neuron_step.restype = C.c_int
     L.pdecg_selftest_exp.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_selftest_exp.restype = C.c_int
     L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),

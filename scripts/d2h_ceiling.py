@@ -111,7 +111,7 @@ def main():
             except Exception as exc:  # noqa: BLE001
                 return repr(exc)
         print(json.dumps({"n_gpus": world, "host": {"cpus": len(os.sched_getaffinity(0)), "numa_nodes": sh("ls -d /sys/devices/system/node/node* | wc -l"),
-                                                     "hypervisor": sh("lscpu | grep -i "Hypervisor vendor""), "thp": sh("cat /sys/kernel/mm/transparent_hugepage/enabled"),
+                                                     "hypervisor": sh("lscpu | grep -i 'Hypervisor vendor'"), "thp": sh("cat /sys/kernel/mm/transparent_hugepage/enabled"),
                                                      "mem_gb": sh("awk '/MemTotal/{print int($2/1e6)}' /proc/meminfo")}}), flush=True)
     if world > 1:
         dist.destroy_process_group()
