@@ -264,6 +264,12 @@ def secondary_transport1(torch, pcg, dev, sampler, peaks, cpu_seconds):
     envk = mk(copy_obs=False)
     envk.reset(options=opts)
     k_ms = _kernel_ms(torch, dev, lambda i: envk.step(a), 100)
+    # the same step replayed from a CUDA graph (pcg.GraphedStep): no Python / ctypes between the launches
+    envg = mk()
+    envg.reset(options=opts)
+    gs = pcg.GraphedStep(envg, a)
+    envg.reset(options=opts)
+    g_ms, _, _ = _event_loop(torch, dev, lambda i: gs.step(a), 200, 10)
     envh = mk()
     envh.reset(options=opts)
     ah, oh = _pinned(torch, 1, dtype=torch.float32).zero_(), _pinned(torch, 1, 100, dtype=torch.float32)
@@ -278,6 +284,7 @@ def secondary_transport1(torch, pcg, dev, sampler, peaks, cpu_seconds):
         "config": "configs[0]", "workload": "TransportPDE1D x1 env, 100 pts, 1000 substeps/step (T=1, dt=1e-4, dx=1e-2), zero control, TunedReward1D, ref precision (f32)",
         "metric": "env_steps_per_sec", "value": 1.0 / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "n_envs": 1,
         "grid_pt_updates_per_sec": 99 * 1000 / (ms * 1e-3), "dtype": "f32", "gpu_launches_per_step": 1,
+        "graph_replay": {"ms_per_step": g_ms, "value": 1.0 / (g_ms * 1e-3), "api": "pcg.GraphedStep(env, action).step(action)"},
         "roofline": {"bound": "latency", "achieved": achieved, "peak": peak, "unit": "dependent substeps/s", "frac": achieved / peak,
                      "kernel": "bc1d_step_kernel<Transport, ModeRefB32, K=4, fast, 32 lanes/env>", "kernel_ms": k_ms, "traffic": None,
                      "peak_source": f"one warp, 1000 dependent substeps per launch: modelled critical path {chain_cycles} cycles per substep "

@@ -89,6 +89,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                  obs_dtype: Optional[str] = None,
                  final_obs: bool = False,
                  truncate_nonfinite: bool = False,
+                 report_nonfinite: bool = False,
                  **kwargs):
         super().__init__(**kwargs)
         self.sensing_noise_func = sensing_noise_func
@@ -146,9 +147,10 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         cfg.max_control_value = float(max_control_value)
         cfg.limit_pde_state_size = int(bool(limit_pde_state_size))
         cfg.max_state_value = float(max_state_value)
-        # info["nonfinite"]: per-env blow-up flag (inf / NaN in the state row), always reported; truncate_nonfinite=True also
-        # ends the episode of such an env (not reference behaviour: there inf / NaN just propagate)
+        # info["nonfinite"] (report_nonfinite=True or truncate_nonfinite=True): per-env blow-up flag (inf / NaN in the state
+        # row); truncate_nonfinite=True also ends the episode of such an env (not reference behaviour: there inf / NaN run on)
         cfg.truncate_nonfinite = int(bool(truncate_nonfinite))
+        self.report_nonfinite = bool(report_nonfinite or truncate_nonfinite)
         if isinstance(rw, TunedReward1D):
             cfg.reward_kind = 0
             cfg.norm_ord, cfg.horizon, cfg.t_horizon_length, cfg.norm_coeff = 2, 0, 1, 1.0
@@ -320,6 +322,9 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
                 None if mask_t is None else mask_t.data_ptr(), self._stream()))
 
     def _autoreset_desc(self):
+        key = (self._ic.data_ptr(), self._ic.dtype, self._random_ic, self._seed, self._ic_stride)
+        if getattr(self, "_ar_key", None) == key:      # rebuilt only when reset() changed the restart source
+            return self._ar_cached
         ar = _lib.Bc1dAutoReset()
         ar.init = self._ic.data_ptr()
         ar.init_dtype = _lib.F64 if self._ic.dtype == torch.float64 else _lib.F32
@@ -330,11 +335,15 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         else:
             ar.random, ar.init_env_stride = 0, self._ic_stride
         ar.final_obs = None if self._final_obs is None else self._final_obs.data_ptr()
+        self._ar_key, self._ar_cached = key, ar
         return ar
 
     def _prep_action(self, action):
         if isinstance(action, torch.Tensor):
             a = action
+            if (a.dim() == 1 and a.shape[0] == self.num_envs and a.device == self.device and a.is_contiguous()
+                    and (a.dtype == torch.float32 or a.dtype == torch.float64)):
+                return a                  # the common case: nothing to convert
             if a.dtype not in (torch.float32, torch.float64):
                 a = a.to(torch.float32)
             a = a.to(self.device)
@@ -364,10 +373,11 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             obs_out = torch.empty_like(self.u, dtype=self.obs_torch_dtype)
             self._buf.obs_copy = obs_out.data_ptr()
         # the kernel writes reward / flags straight into fresh tensors handed to the caller (no clone launches)
-        reward, term_u8, trunc_u8 = torch.empty_like(self._reward), torch.empty_like(self._terminated), torch.empty_like(self._truncated)
-        nonfin_u8 = torch.empty_like(self._terminated)
+        reward = torch.empty_like(self._reward)
+        flags = torch.empty((3 if self.report_nonfinite else 2, self.num_envs), dtype=torch.uint8, device=self.device)   # one allocation
+        term_u8, trunc_u8 = flags[0], flags[1]
         self._buf.reward, self._buf.terminated, self._buf.truncated = reward.data_ptr(), term_u8.data_ptr(), trunc_u8.data_ptr()
-        self._buf.nonfinite = nonfin_u8.data_ptr()
+        self._buf.nonfinite = flags[2].data_ptr() if self.report_nonfinite else None
         ke = self._kernel_events          # optional (start, stop) CUDA events bracketing only the step kernel
         try:
             with torch.cuda.device(self.device):
@@ -383,7 +393,8 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
             terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
             # rows of the envs with terminated | truncated this step are fresh (SB3 "terminal_observation")
             info = {"final_obs": self._final_obs} if (self.autoreset and self._final_obs is not None) else {}
-            info["nonfinite"] = nonfin_u8.view(torch.bool)
+            if self.report_nonfinite:
+                info["nonfinite"] = flags[2].view(torch.bool)
         finally:
             self._buf.obs_copy = None            # never leave a pointer to a caller-owned tensor behind
             self._buf.nonfinite = None

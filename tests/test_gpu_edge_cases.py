@@ -415,7 +415,8 @@ def test_nonfinite_flag_and_optional_truncation(cuda_device):
     ics = make_ics(rng, B, npts)
     ics[::2] *= 1e-30                                   # every other env stays tiny for a while longer
     orc = O.ReactionDiffusionOracle(B, reward=O.NormRewardSpec(nt - 1, norm=2), precision="ref", **common)
-    env = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=B, device=cuda_device, precision="ref", reward_class=pcg.NormReward(nt - 1, norm="2"), **common)
+    env = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=B, device=cuda_device, precision="ref", reward_class=pcg.NormReward(nt - 1, norm="2"),
+                   report_nonfinite=True, **common)
     env_t = pcg.make("PDEControlGym-ReactionDiffusionPDE1D", num_envs=B, device=cuda_device, precision="ref", reward_class=pcg.NormReward(nt - 1, norm="2"),
                      truncate_nonfinite=True, **common)
     orc.reset(ics, beta.astype(np.float32))
