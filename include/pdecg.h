@@ -458,6 +458,13 @@ int pdecg_probe_fp_issue(int32_t dtype, int32_t blocks, int32_t threads, int32_t
 int pdecg_selftest_constdiv(int32_t dtype, int64_t n, const void* x, double d, void* out_fast, void* out_ref,
                             pdecg_stream_t stream);
 
+/* Self-test of the kernels' deferred-check division (Traffic-ARZ / BrainTumor inner loops): out_fast[i] = the
+ * straight-line fast path of a[i] / b[i], out_ok[i] = 1 when both operands lie inside the exponent windows in which the
+ * kernels trust it, out_ref[i] = IEEE a[i] / b[i]; wherever out_ok is 1 the two quotients must be bit-identical
+ * (tests/test_gpu_constdiv.py). */
+int pdecg_selftest_fastdiv(int32_t dtype, int64_t n, const void* a, const void* b, void* out_fast, uint8_t* out_ok,
+                           void* out_ref, pdecg_stream_t stream);
+
 /* Self-test of the correctly rounded exp() the BrainTumor kernels use for the radiation term exp(-alpha * BED)
  * (brain_tumor_env.py:259-265): out[i] = exp_cr(x[i]) (tests/test_gpu_exp.py: bit-identical to mpmath's rounding). */
 int pdecg_selftest_exp(int64_t n, const double* x, double* out, pdecg_stream_t stream);

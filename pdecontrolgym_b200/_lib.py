@@ -194,6 +194,8 @@ def lib():
     L.pdecg_selftest_constdiv.restype = C.c_int
     L.pdecg_neuron_step.argtypes = [C.POINTER(NeuronCfg), C.POINTER(NeuronBuffers), C.c_int32, C.c_void_p]
     L.pdecg_neuron_step.restype = C.c_int
+    L.pdecg_selftest_fastdiv.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdecg_selftest_fastdiv.restype = C.c_int
     L.pdecg_selftest_exp.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pdecg_selftest_exp.restype = C.c_int
     L.pdecg_probe_fp_issue.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),

@@ -55,6 +55,16 @@ __global__ void constdiv_selftest_kernel(const T* __restrict__ x, T d, T* __rest
     }
 }
 
+template <typename T>
+__global__ void fastdiv_selftest_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ fast, uint8_t* __restrict__ ok,
+                                        T* __restrict__ ref, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        fast[i] = fast_div(a[i], b[i]);
+        ok[i] = (DivWindow<T>::a(a[i]) & DivWindow<T>::b(b[i])) ? 1 : 0;
+        ref[i] = Strict<T>::div(a[i], b[i]);
+    }
+}
+
 __global__ void exp_selftest_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) out[i] = exp_cr(x[i]);
 }
@@ -82,6 +92,19 @@ extern "C" int pdecg_selftest_constdiv(int32_t dtype, int64_t n, const void* x, 
         constdiv_selftest_kernel<float><<<592, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float>(d), static_cast<float*>(out_fast), static_cast<float*>(out_ref), n);
     count_launch();
     return check_launch("constdiv_selftest_kernel");
+}
+
+extern "C" int pdecg_selftest_fastdiv(int32_t dtype, int64_t n, const void* a, const void* b, void* out_fast, uint8_t* out_ok,
+                                      void* out_ref, pdecg_stream_t stream) {
+    if (n < 0 || (n > 0 && (!a || !b || !out_fast || !out_ok || !out_ref))) return fail(PDECG_ERR_INVALID, "bad arguments");
+    if (n == 0) return PDECG_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == PDECG_F64)
+        fastdiv_selftest_kernel<double><<<592, 256, 0, st>>>(static_cast<const double*>(a), static_cast<const double*>(b), static_cast<double*>(out_fast), out_ok, static_cast<double*>(out_ref), n);
+    else
+        fastdiv_selftest_kernel<float><<<592, 256, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(out_fast), out_ok, static_cast<float*>(out_ref), n);
+    count_launch();
+    return check_launch("fastdiv_selftest_kernel");
 }
 
 extern "C" const char* pdecg_last_error(void) { return g_err; }

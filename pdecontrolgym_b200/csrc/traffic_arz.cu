@@ -84,6 +84,117 @@ __device__ __forceinline__ void arz_store(const T (&r)[K], T* __restrict__ g, in
 template <typename T>
 __device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane);   // defined after the reset kernel
 
+template <typename T>
+struct ArzCoef { T c1, c2, c3, c4, q_in, q_out; };
+
+// One Richtmyer / Lax-Wendroff substep (:175-222) on the warp's register-resident (rho, y) row.
+//
+// FAST = false: every division is the IEEE one (ConstDiv's per-call window test for /rm, the compiler's div.rn with its
+// own range test and slow path for y/rho) -- valid for every input.
+// FAST = true : the same operations in the same order with the range tests taken out of the dependency chains: /rm is
+// ConstDiv's 3-instruction tail, y/rho is fast_div's straight-line sequence, Veq(rho) of a node is evaluated once and
+// shared by the boundary row and the node fluxes, and the boundary rows are selects instead of divergent branches.
+// Every division operand is folded into ONE predicate (DivWindow); the function returns it, and the caller redoes the
+// substep with FAST = false if any lane of the warp saw an operand outside the window -- so the states stay
+// bit-identical to the reference's for every input, at ~2/3 of the instructions on the ordinary path.
+template <int K, typename T, bool FAST>
+__device__ __forceinline__ bool arz_substep(T (&r)[K], T (&y)[K], const ArzCtx<T>& ctx, const ArzCoef<T>& co, int j0, int M) {
+    using D = Strict<T>;
+    using W = DivWindow<T>;
+    const T c1 = co.c1, c2 = co.c2, c3 = co.c3, c4 = co.c4;
+    bool ok = true;
+    T fr[K], fy[K];
+    if constexpr (FAST) {
+        // ---- boundary densities (:175-190): rho[0] = rho[1], rho[M-1] = rho[M-2] ----
+        const T r_left = __shfl_up_sync(kFull, r[K - 1], 1);                     // node j0-1
+        if constexpr (K == 1) {
+            const T r_right = __shfl_down_sync(kFull, r[0], 1);
+            r[0] = (j0 == 0) ? r_right : r[0];
+        } else {
+            r[0] = (j0 == 0) ? r[1] : r[0];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const T rp = (k > 0) ? r[k > 0 ? k - 1 : 0] : r_left;                // r[j-1] (M >= 4: never the node just rewritten)
+            r[k] = (j0 + k == M - 1) ? rp : r[k];
+        }
+        // ---- Veq at the nodes, boundary momenta, node fluxes ----
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = j0 + k;
+            const T ve = D::mul(ctx.vm, D::sub(T(1), ctx.by_rm.fast(r[k])));
+            const bool first = (k == 0) && (j == 0), last = (j == M - 1);
+            const T yb = D::sub(first ? co.q_in : co.q_out, D::mul(r[k], ve));
+            y[k] = (first || last) ? yb : y[k];
+            ok = ok & W::b(r[k]) & W::a(y[k]);
+            fr[k] = D::add(y[k], D::mul(r[k], ve));
+            fy[k] = D::mul(y[k], D::add(fast_div(y[k], r[k]), ve));
+        }
+    } else {
+        const T r_right = __shfl_down_sync(kFull, r[0], 1);                      // node j0+K
+        const T r_left = __shfl_up_sync(kFull, r[K - 1], 1);                     // node j0-1
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = j0 + k;
+            const T rn = (k < K - 1) ? r[k < K - 1 ? k + 1 : 0] : r_right;       // r[j+1]
+            const T rp = (k > 0) ? r[k > 0 ? k - 1 : 0] : r_left;                // r[j-1]
+            if (j == 0) {
+                r[k] = rn;
+                y[k] = D::sub(co.q_in, D::mul(r[k], veq(ctx, r[k])));
+            }
+            if (j == M - 1) {
+                r[k] = rp;
+                y[k] = D::sub(co.q_out, D::mul(r[k], veq(ctx, r[k])));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            fr[k] = flux_r(ctx, r[k], y[k]);
+            fy[k] = flux_y(ctx, r[k], y[k]);
+        }
+    }
+    const T r_nx = __shfl_down_sync(kFull, r[0], 1), y_nx = __shfl_down_sync(kFull, y[0], 1);
+    const T fr_nx = __shfl_down_sync(kFull, fr[0], 1), fy_nx = __shfl_down_sync(kFull, fy[0], 1);
+    // ---- midpoints j+1/2 (:202-215) and their fluxes ----
+    T ym[K], frm[K], fym[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const bool lastk = (k == K - 1);
+        const T rb = lastk ? r_nx : r[lastk ? 0 : k + 1], yb = lastk ? y_nx : y[lastk ? 0 : k + 1];
+        const T frb = lastk ? fr_nx : fr[lastk ? 0 : k + 1], fyb = lastk ? fy_nx : fy[lastk ? 0 : k + 1];
+        const T rmid = D::sub(D::mul(T(0.5), D::add(rb, r[k])), D::mul(c1, D::sub(frb, fr[k])));
+        const T ysum = D::add(yb, y[k]);
+        const T ymid = D::sub(D::sub(D::mul(T(0.5), ysum), D::mul(c1, D::sub(fyb, fy[k]))), D::mul(c2, ysum));
+        ym[k] = ymid;
+        if constexpr (FAST) {
+            const T ve = D::mul(ctx.vm, D::sub(T(1), ctx.by_rm.fast(rmid)));
+            ok = ok & W::b(rmid) & W::a(ymid);
+            frm[k] = D::add(ymid, D::mul(rmid, ve));
+            fym[k] = D::mul(ymid, D::add(fast_div(ymid, rmid), ve));
+        } else {
+            frm[k] = flux_r(ctx, rmid, ymid);
+            fym[k] = flux_y(ctx, rmid, ymid);
+        }
+    }
+    const T ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1);
+    const T frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1);
+    const T fym_pv = __shfl_up_sync(kFull, fym[K - 1], 1);
+    // ---- interior update (:218-222) ----
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = j0 + k;
+        const T yl = (k == 0) ? ym_pv : ym[k > 0 ? k - 1 : 0];
+        const T frl = (k == 0) ? frm_pv : frm[k > 0 ? k - 1 : 0];
+        const T fyl = (k == 0) ? fym_pv : fym[k > 0 ? k - 1 : 0];
+        const T rnew = D::sub(r[k], D::mul(c3, D::sub(frm[k], frl)));
+        const T ynew = D::sub(y[k], D::add(D::mul(c3, D::sub(fym[k], fyl)), D::mul(c4, D::add(ym[k], yl))));
+        const bool interior = (j >= 1) && (j <= M - 2);
+        r[k] = interior ? rnew : r[k];
+        y[k] = interior ? ynew : y[k];
+    }
+    return ok;
+}
+
 template <int K, typename T>
 __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) arz_step_kernel(const __grid_constant__ ArzArgs a) {
     using D = Strict<T>;
@@ -97,7 +208,8 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
     const int M = cfg.M;
     const int j0 = lane * K;
     const ArzCtx<T> ctx(cfg);
-    const T c1 = static_cast<T>(cfg.c1), c2 = static_cast<T>(cfg.c2), c3 = static_cast<T>(cfg.c3), c4 = static_cast<T>(cfg.c4);
+    ArzCoef<T> co;
+    co.c1 = static_cast<T>(cfg.c1); co.c2 = static_cast<T>(cfg.c2); co.c3 = static_cast<T>(cfg.c3); co.c4 = static_cast<T>(cfg.c4);
 
     // start the row loads first: the scalar load and its broadcast then overlap their latency
     T* rrow = reinterpret_cast<T*>(a.buf.ry) + env * 2 * M;
@@ -129,78 +241,43 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
     const T a0 = static_cast<T>(clipd(act[0], lo, hi));
     const T a1 = (cfg.action_dim > 1) ? static_cast<T>(clipd(act[1], lo, hi)) : a0;
     const int st = cfg.simulation_type;
-    const T q_in = (st == PDECG_ARZ_INLET || st == PDECG_ARZ_BOTH) ? a0 : qs;
-    const T q_out = (st == PDECG_ARZ_OUTLET || st == PDECG_ARZ_OUTLET_TRAIN) ? a0 : ((st == PDECG_ARZ_BOTH) ? a1 : qs);
+    co.q_in = (st == PDECG_ARZ_INLET || st == PDECG_ARZ_BOTH) ? a0 : qs;
+    co.q_out = (st == PDECG_ARZ_OUTLET || st == PDECG_ARZ_OUTLET_TRAIN) ? a0 : ((st == PDECG_ARZ_BOTH) ? a1 : qs);
 
+    const bool fast_cfg = ctx.by_rm.fast_ok();                          // uniform
     for (int count = 0; count < cfg.control_freq && time < cfg.T; ++count) {          // :173
-        // ---- boundary conditions (:175-190) ----
-        {
-            const T r_right = __shfl_down_sync(kFull, r[0], 1);                  // node j0+K
-            const T r_left = __shfl_up_sync(kFull, r[K - 1], 1);                 // node j0-1
+        if (fast_cfg) {
+            T r0[K], y0[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int j = j0 + k;
-                const T rn = (k < K - 1) ? r[k < K - 1 ? k + 1 : 0] : r_right;   // r[j+1]
-                const T rp = (k > 0) ? r[k > 0 ? k - 1 : 0] : r_left;            // r[j-1]
-                if (j == 0) {
-                    r[k] = rn;
-                    y[k] = D::sub(q_in, D::mul(r[k], veq(ctx, r[k])));
-                }
-                if (j == M - 1) {
-                    r[k] = rp;
-                    y[k] = D::sub(q_out, D::mul(r[k], veq(ctx, r[k])));
-                }
-            }
-        }
-        // ---- node fluxes ----
-        T fr[K], fy[K];
+            for (int k = 0; k < K; ++k) { r0[k] = r[k]; y0[k] = y[k]; }
+            const bool ok = arz_substep<K, T, true>(r, y, ctx, co, j0, M);
+            if (__all_sync(kFull, ok)) continue;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            fr[k] = flux_r(ctx, r[k], y[k]);
-            fy[k] = flux_y(ctx, r[k], y[k]);
+            for (int k = 0; k < K; ++k) { r[k] = r0[k]; y[k] = y0[k]; }               // rare: redo with the exact divisions
         }
-        const T r_nx = __shfl_down_sync(kFull, r[0], 1), y_nx = __shfl_down_sync(kFull, y[0], 1);
-        const T fr_nx = __shfl_down_sync(kFull, fr[0], 1), fy_nx = __shfl_down_sync(kFull, fy[0], 1);
-        // ---- midpoints j+1/2 (:202-215) and their fluxes ----
-        T ym[K], frm[K], fym[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const bool lastk = (k == K - 1);
-            const T rb = lastk ? r_nx : r[lastk ? 0 : k + 1], yb = lastk ? y_nx : y[lastk ? 0 : k + 1];
-            const T frb = lastk ? fr_nx : fr[lastk ? 0 : k + 1], fyb = lastk ? fy_nx : fy[lastk ? 0 : k + 1];
-            const T rmid = D::sub(D::mul(T(0.5), D::add(rb, r[k])), D::mul(c1, D::sub(frb, fr[k])));
-            const T ysum = D::add(yb, y[k]);
-            const T ymid = D::sub(D::sub(D::mul(T(0.5), ysum), D::mul(c1, D::sub(fyb, fy[k]))), D::mul(c2, ysum));
-            ym[k] = ymid;
-            frm[k] = flux_r(ctx, rmid, ymid);
-            fym[k] = flux_y(ctx, rmid, ymid);
-        }
-        const T ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1);
-        const T frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1);
-        const T fym_pv = __shfl_up_sync(kFull, fym[K - 1], 1);
-        // ---- interior update (:218-222) ----
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int j = j0 + k;
-            const T yl = (k == 0) ? ym_pv : ym[k > 0 ? k - 1 : 0];
-            const T frl = (k == 0) ? frm_pv : frm[k > 0 ? k - 1 : 0];
-            const T fyl = (k == 0) ? fym_pv : fym[k > 0 ? k - 1 : 0];
-            const T rnew = D::sub(r[k], D::mul(c3, D::sub(frm[k], frl)));
-            const T ynew = D::sub(y[k], D::add(D::mul(c3, D::sub(fym[k], fyl)), D::mul(c4, D::add(ym[k], yl))));
-            const bool interior = (j >= 1) && (j <= M - 2);
-            r[k] = interior ? rnew : r[k];
-            y[k] = interior ? ynew : y[k];
-        }
+        arz_substep<K, T, false>(r, y, ctx, co, j0, M);
     }
 
     // ---- velocity, reward, flags, observation (:226-233) ----
     T v[K];
+    {
+        bool ok = fast_cfg;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            v[k] = D::add(fast_div(y[k], r[k]), D::mul(ctx.vm, D::sub(T(1), ctx.by_rm.fast(r[k]))));
+            ok = ok & DivWindow<T>::b(r[k]) & DivWindow<T>::a(y[k]);
+        }
+        if (!__all_sync(kFull, ok)) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[k] = D::add(D::div(y[k], r[k]), veq(ctx, r[k]));
+        }
+    }
     double sv = 0.0, sr = 0.0;
     bool over = false, steady = true;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const bool valid = j0 + k < M;
-        v[k] = valid ? D::add(D::div(y[k], r[k]), veq(ctx, r[k])) : T(0);
+        v[k] = valid ? v[k] : T(0);
         const double dv = static_cast<double>(D::sub(v[k], vs)), dr = static_cast<double>(D::sub(r[k], rs));
         if (valid) {
             sv += dv * dv;

@@ -43,3 +43,40 @@ def test_constdiv_bit_identical_to_ieee_division(cuda_device, dtype, d):
     assert np.array_equal(np.isnan(f), nan)
     assert np.array_equal(f[~nan].view(ib), r[~nan].view(ib)), "ConstDiv differs from __fdiv_rn/__ddiv_rn"
     assert np.array_equal(r[~nan].view(ib), want[~nan].view(ib)), "device IEEE division differs from numpy"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fast_div_bit_identical_inside_its_window(cuda_device, dtype):
+    """The deferred-check division of the Traffic-ARZ / BrainTumor inner loops (csrc/pdecg_common.cuh: fast_div +
+    DivWindow): wherever the window predicate holds, the straight-line quotient equals IEEE division bit for bit;
+    the window must cover the magnitudes the PDE states take (so the fallback is the rare path) and must reject
+    zeros, denormals, infinities and NaNs."""
+    import torch
+    from pdecontrolgym_b200 import _lib
+    rng = np.random.default_rng(7 if dtype == np.float32 else 8)
+    n = 1 << 22
+    a = _inputs(dtype, n, rng)
+    b = _inputs(dtype, n, np.random.default_rng(11))
+    rng.shuffle(b)
+    # a third of the pairs: ordinary PDE magnitudes (densities 0.05..0.2, momenta -1..1)
+    m = a.size // 3
+    a[:m] = rng.uniform(-1, 1, m).astype(dtype)
+    b[:m] = rng.uniform(0.05, 0.2, m).astype(dtype)
+    at, bt = torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)
+    fast, ref = torch.empty_like(at), torch.empty_like(at)
+    ok = torch.empty(at.numel(), dtype=torch.uint8, device=cuda_device)
+    L = _lib.lib()
+    _lib.check(L.pdecg_selftest_fastdiv(_lib.F32 if dtype == np.float32 else _lib.F64, at.numel(), at.data_ptr(), bt.data_ptr(),
+                                        fast.data_ptr(), ok.data_ptr(), ref.data_ptr(),
+                                        torch.cuda.current_stream(cuda_device).cuda_stream))
+    f, r, k = fast.cpu().numpy(), ref.cpu().numpy(), ok.cpu().numpy().astype(bool)
+    ib = np.uint32 if dtype == np.float32 else np.uint64
+    with np.errstate(all="ignore"):
+        want = (a / b).astype(dtype)
+    assert k[:m].all(), "ordinary magnitudes must stay on the fast path"
+    assert k.mean() > 0.3
+    assert not np.isnan(r[k]).any() and np.isfinite(r[k]).all()
+    assert np.array_equal(f[k].view(ib), r[k].view(ib)), "fast_div differs from the device's IEEE division inside its window"
+    assert np.array_equal(r[k].view(ib), want[k].view(ib))
+    bad = (a == 0) | (b == 0) | ~np.isfinite(a) | ~np.isfinite(b) | (np.abs(a) < np.finfo(dtype).tiny) | (np.abs(b) < np.finfo(dtype).tiny)
+    assert not k[bad].any(), "zeros / denormals / inf / NaN must be routed to the exact division"

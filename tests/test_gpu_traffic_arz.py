@@ -152,3 +152,42 @@ def test_fp32_fast_mode_tolerance_and_event_agreement(cuda_device, st):
         total += B
     assert worst_obs < 2e-4 and worst_rew < 2e-4, (worst_obs, worst_rew)
     assert agree / total >= 0.999, agree / total
+
+
+@pytest.mark.parametrize("dx", [10, 4])         # 51 points (2 per lane) and 126 points (4 per lane)
+def test_exceptional_operands_take_the_exact_division(cuda_device, dx):
+    """The substep's divisions run on a deferred-check fast path (csrc/traffic_arz.cu: arz_substep<FAST>); a warp whose
+    lanes see a zero / signed-zero / tiny / huge / non-finite operand redoes the substep with the IEEE divisions.  Plant such
+    values in the state of some envs (others stay ordinary, so both paths run in one launch) and compare with the oracle."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    B, kw = 12, dict(T=20, dt=0.25 * dx / 10, X=500, dx=dx)
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, simulation_type="both", control_freq=2,
+                   reward_class=pcg.TrafficARZReward(), **kw)
+    orc = O.TrafficARZOracle(B, simulation_type="both", control_freq=2, **kw)
+    env.reset()
+    orc.reset()
+    M = orc.M
+    plant = [(0, "y", 3, 0.0), (1, "y", 7, -0.0), (2, "r", 10, 1e-150), (3, "y", 5, 1e-305), (4, "r", 20, 1e120),
+             (5, "y", M - 2, 0.0), (6, "r", 1, 5e-324), (7, "y", 30, np.inf), (8, "r", 12, np.nan), (9, "r", 25, 0.0)]
+    ry = env._ry.cpu().numpy().copy()
+    for b, which, j, val in plant:
+        if which == "r":
+            orc.r[b, j] = val
+            ry[b, 0, j] = val
+        else:
+            orc.y[b, j] = val
+            ry[b, 1, j] = val
+    env._ry.copy_(torch.from_numpy(ry).to(cuda_device))
+    rng = np.random.default_rng(5)
+    with np.errstate(all="ignore"):
+        for k in range(6):
+            a = rng.uniform(0.9, 1.5, size=(B, 2))
+            o_r, r_r, te_r, tr_r = orc.step(a)
+            o_g, r_g, te_g, tr_g, _ = env.step(torch.from_numpy(a))
+            g = o_g.cpu().numpy()
+            assert np.array_equal(np.isnan(g), np.isnan(o_r)), f"step {k}: NaN pattern"
+            fin = ~np.isnan(o_r)
+            assert np.array_equal(g[fin].view(np.uint64), o_r[fin].view(np.uint64)), f"step {k}: obs not bit-identical"
+            assert np.array_equal(env._ry.cpu().numpy()[:, 0, :][~np.isnan(orc.r)].view(np.uint64), orc.r[~np.isnan(orc.r)].view(np.uint64))
+            assert np.array_equal(te_g.cpu().numpy(), te_r) and np.array_equal(tr_g.cpu().numpy(), tr_r), f"step {k}: flags"
