@@ -15,6 +15,9 @@
 #ifndef PDECG_ARZ_MINBLOCKS
 #define PDECG_ARZ_MINBLOCKS 8    // 64 registers, 32 warps/SM (measured at 262k envs: 12 -> 0.285, 10 -> 0.262, 8 -> 0.254, 6 -> 0.297 ms)
 #endif
+#ifndef PDECG_ARZ_MINBLOCKS_H
+#define PDECG_ARZ_MINBLOCKS_H 4  // two envs per warp, up to 4 points per lane
+#endif
 namespace pdecg {
 
 struct ArzArgs {
@@ -48,31 +51,32 @@ __device__ __forceinline__ double clipd(double v, double lo, double hi) {       
     return (v > hi) ? hi : v;
 }
 
-// Row <-> register-chunk transfers.  With K <= 2 points per lane the chunk is read / written directly (lane L touches
+// Row <-> register-chunk transfers (`lane` = the lane's position in its env's segment).  With K <= 2 points per lane,
+// and in the two-envs-per-warp mapping, the chunk is read / written directly (lane L touches
 // the 8K bytes at offset 8KL: every 32-byte sector is consumed by at most two adjacent lanes, and the second access
 // of a line hits L1), which drops the shared-memory staging and its two warp barriers per row; wider chunks go through
 // the staged, fully coalesced path.
-template <int K, typename T>
+template <int K, typename T, int LPE = 32>
 __device__ __forceinline__ void arz_load_issue(T (&tmp)[K], const T* __restrict__ g, int npts, int lane) {
-    if constexpr (K <= 2) {
+    if constexpr (K <= 2 || LPE != 32) {
 #pragma unroll
         for (int k = 0; k < K; ++k) tmp[k] = (lane * K + k < npts) ? g[lane * K + k] : T(0);
     } else {
         load_row_issue<T, T, K>(tmp, g, npts, lane);
     }
 }
-template <int K, typename T>
+template <int K, typename T, int LPE = 32>
 __device__ __forceinline__ void arz_load_finish(T (&r)[K], const T (&tmp)[K], T* sm, int lane) {
-    if constexpr (K <= 2) {
+    if constexpr (K <= 2 || LPE != 32) {
 #pragma unroll
         for (int k = 0; k < K; ++k) r[k] = tmp[k];
     } else {
         load_row_finish<T, K>(r, tmp, sm, lane);
     }
 }
-template <int K, typename T>
+template <int K, typename T, int LPE = 32>
 __device__ __forceinline__ void arz_store(const T (&r)[K], T* __restrict__ g, int npts, T* sm, int lane) {
-    if constexpr (K <= 2) {
+    if constexpr (K <= 2 || LPE != 32) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
             if (lane * K + k < npts) g[lane * K + k] = r[k];
@@ -81,8 +85,8 @@ __device__ __forceinline__ void arz_store(const T (&r)[K], T* __restrict__ g, in
     }
 }
 
-template <typename T>
-__device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane);   // defined after the reset kernel
+template <typename T, int LPE>
+__device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int l, unsigned segm);   // defined after the reset kernel
 
 template <typename T>
 struct ArzCoef { T c1, c2, c3, c4, q_in, q_out; };
@@ -97,7 +101,7 @@ struct ArzCoef { T c1, c2, c3, c4, q_in, q_out; };
 // Every division operand is folded into ONE predicate (DivWindow); the function returns it, and the caller redoes the
 // substep with FAST = false if any lane of the warp saw an operand outside the window -- so the states stay
 // bit-identical to the reference's for every input, at ~2/3 of the instructions on the ordinary path.
-template <int K, typename T, bool FAST>
+template <int K, typename T, bool FAST, int LPE>
 __device__ __forceinline__ bool arz_substep(T (&r)[K], T (&y)[K], const ArzCtx<T>& ctx, const ArzCoef<T>& co, int j0, int M) {
     using D = Strict<T>;
     using W = DivWindow<T>;
@@ -106,9 +110,9 @@ __device__ __forceinline__ bool arz_substep(T (&r)[K], T (&y)[K], const ArzCtx<T
     T fr[K], fy[K];
     if constexpr (FAST) {
         // ---- boundary densities (:175-190): rho[0] = rho[1], rho[M-1] = rho[M-2] ----
-        const T r_left = __shfl_up_sync(kFull, r[K - 1], 1);                     // node j0-1
+        const T r_left = __shfl_up_sync(kFull, r[K - 1], 1, LPE);                     // node j0-1
         if constexpr (K == 1) {
-            const T r_right = __shfl_down_sync(kFull, r[0], 1);
+            const T r_right = __shfl_down_sync(kFull, r[0], 1, LPE);
             r[0] = (j0 == 0) ? r_right : r[0];
         } else {
             r[0] = (j0 == 0) ? r[1] : r[0];
@@ -131,8 +135,8 @@ __device__ __forceinline__ bool arz_substep(T (&r)[K], T (&y)[K], const ArzCtx<T
             fy[k] = D::mul(y[k], D::add(fast_div(y[k], r[k]), ve));
         }
     } else {
-        const T r_right = __shfl_down_sync(kFull, r[0], 1);                      // node j0+K
-        const T r_left = __shfl_up_sync(kFull, r[K - 1], 1);                     // node j0-1
+        const T r_right = __shfl_down_sync(kFull, r[0], 1, LPE);                      // node j0+K
+        const T r_left = __shfl_up_sync(kFull, r[K - 1], 1, LPE);                     // node j0-1
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j = j0 + k;
@@ -153,8 +157,8 @@ __device__ __forceinline__ bool arz_substep(T (&r)[K], T (&y)[K], const ArzCtx<T
             fy[k] = flux_y(ctx, r[k], y[k]);
         }
     }
-    const T r_nx = __shfl_down_sync(kFull, r[0], 1), y_nx = __shfl_down_sync(kFull, y[0], 1);
-    const T fr_nx = __shfl_down_sync(kFull, fr[0], 1), fy_nx = __shfl_down_sync(kFull, fy[0], 1);
+    const T r_nx = __shfl_down_sync(kFull, r[0], 1, LPE), y_nx = __shfl_down_sync(kFull, y[0], 1, LPE);
+    const T fr_nx = __shfl_down_sync(kFull, fr[0], 1, LPE), fy_nx = __shfl_down_sync(kFull, fy[0], 1, LPE);
     // ---- midpoints j+1/2 (:202-215) and their fluxes ----
     T ym[K], frm[K], fym[K];
 #pragma unroll
@@ -176,9 +180,9 @@ __device__ __forceinline__ bool arz_substep(T (&r)[K], T (&y)[K], const ArzCtx<T
             fym[k] = flux_y(ctx, rmid, ymid);
         }
     }
-    const T ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1);
-    const T frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1);
-    const T fym_pv = __shfl_up_sync(kFull, fym[K - 1], 1);
+    const T ym_pv = __shfl_up_sync(kFull, ym[K - 1], 1, LPE);
+    const T frm_pv = __shfl_up_sync(kFull, frm[K - 1], 1, LPE);
+    const T fym_pv = __shfl_up_sync(kFull, fym[K - 1], 1, LPE);
     // ---- interior update (:218-222) ----
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -195,41 +199,50 @@ __device__ __forceinline__ bool arz_substep(T (&r)[K], T (&y)[K], const ArzCtx<T
     return ok;
 }
 
-template <int K, typename T>
-__global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) arz_step_kernel(const __grid_constant__ ArzArgs a) {
+// One env.step() for the env(s) of one warp.
+//
+// LPE lanes per env: 32 = one freeway per warp; 16 = two per warp (grids up to 64 points; opt-in, see arz_launch_step).
+// Cross-lane traffic is full-mask with the segment's width, so both segments run in lock-step.
+//
+// FAST = true is the path the kernel runs: deferred-check divisions throughout; the operand-window predicate of every
+// substep and of the final velocity is AND-ed into one flag, voted ONCE per step, and if any lane of the warp saw an
+// exceptional operand the function returns false BEFORE storing anything -- the kernel then calls the out-of-line
+// FAST = false instance, which redoes the whole step from the (untouched) global state with IEEE divisions.
+template <int K, typename T, int LPE, bool FAST>
+__device__ __forceinline__ bool arz_step_env(const ArzArgs& a, T* sm) {
     using D = Strict<T>;
-    __shared__ T sm_all[kWarpsPerBlock][32 * K];
+    constexpr int EPW = 32 / LPE;                          // envs per warp
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t env = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib;
-    if (env >= a.buf.n_envs) return;
-    T* sm = sm_all[wib];
+    const int l = lane & (LPE - 1);                        // lane within the env's segment
+    const int64_t env_raw = (static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5)) * EPW + lane / LPE;
+    const bool have = env_raw < a.buf.n_envs;              // odd batch: the last warp's second segment shadows the last env,
+    const int64_t env = have ? env_raw : a.buf.n_envs - 1; // computes along (the shuffles are full-mask) and stores nothing
     const pdecg_arz_cfg& cfg = a.cfg;
     const int M = cfg.M;
-    const int j0 = lane * K;
+    const int j0 = l * K;
     const ArzCtx<T> ctx(cfg);
     ArzCoef<T> co;
     co.c1 = static_cast<T>(cfg.c1); co.c2 = static_cast<T>(cfg.c2); co.c3 = static_cast<T>(cfg.c3); co.c4 = static_cast<T>(cfg.c4);
 
-    // start the row loads first: the scalar load and its broadcast then overlap their latency
+    // start the row loads first: the per-env scalars (one 48-byte row, read as three broadcast 16-byte loads) overlap them
     T* rrow = reinterpret_cast<T*>(a.buf.ry) + env * 2 * M;
     T* yrow = rrow + M;
     T r[K], y[K], r_raw[K], y_raw[K];
-    arz_load_issue<K, T>(r_raw, rrow, M, lane);
-    arz_load_issue<K, T>(y_raw, yrow, M, lane);
+    arz_load_issue<K, T, LPE>(r_raw, rrow, M, l);
+    arz_load_issue<K, T, LPE>(y_raw, yrow, M, l);
     double* frow = a.buf.fenv + env * PDECG_ARZ_NF64;
-    const double fv = (lane < PDECG_ARZ_NF64) ? frow[lane] : 0.0;
-    double time = __shfl_sync(kFull, fv, PDECG_ARZ_F_TIME);
-    const T rs = static_cast<T>(__shfl_sync(kFull, fv, PDECG_ARZ_F_RS));
-    const T vs = static_cast<T>(__shfl_sync(kFull, fv, PDECG_ARZ_F_VS));
-    const T qs = static_cast<T>(__shfl_sync(kFull, fv, PDECG_ARZ_F_QS));
+    static_assert(PDECG_ARZ_F_TIME == 0 && PDECG_ARZ_F_RS == 1 && PDECG_ARZ_F_VS == 2 && PDECG_ARZ_F_QS == 3 &&
+                  PDECG_ARZ_F_ACT_LO == 4 && PDECG_ARZ_F_ACT_HI == 5 && PDECG_ARZ_NF64 == 6, "fenv row layout");
+    const double2 f01 = reinterpret_cast<const double2*>(frow)[0], f23 = reinterpret_cast<const double2*>(frow)[1];
+    const double2 f45 = reinterpret_cast<const double2*>(frow)[2];
+    double time = f01.x;
+    const T rs = static_cast<T>(f01.y), vs = static_cast<T>(f23.x), qs = static_cast<T>(f23.y);
     // action_space.low / .high as built in __init__ (:97-100): NOT refreshed when 'outlet-train' re-draws qs in reset()
-    const double lo = __shfl_sync(kFull, fv, PDECG_ARZ_F_ACT_LO), hi = __shfl_sync(kFull, fv, PDECG_ARZ_F_ACT_HI);
+    const double lo = f45.x, hi = f45.y;
 
-    arz_load_finish<K, T>(r, r_raw, sm, lane);
-    arz_load_finish<K, T>(y, y_raw, sm, lane);
-    // padding slots (never stored, never read by valid points) hold (rho, y) = (1, 1) so that the divisions
-    // evaluated there stay on the fast path instead of div.rn's slow 0/0 path
+    arz_load_finish<K, T, LPE>(r, r_raw, sm, l);
+    arz_load_finish<K, T, LPE>(y, y_raw, sm, l);
+    // padding slots (never stored, never read by valid points) hold (rho, y) = (1, 1): inside every division window
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if (j0 + k >= M) { r[k] = T(1); y[k] = T(1); }
@@ -244,63 +257,103 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
     co.q_in = (st == PDECG_ARZ_INLET || st == PDECG_ARZ_BOTH) ? a0 : qs;
     co.q_out = (st == PDECG_ARZ_OUTLET || st == PDECG_ARZ_OUTLET_TRAIN) ? a0 : ((st == PDECG_ARZ_BOTH) ? a1 : qs);
 
-    const bool fast_cfg = ctx.by_rm.fast_ok();                          // uniform
-    for (int count = 0; count < cfg.control_freq && time < cfg.T; ++count) {          // :173
-        if (fast_cfg) {
-            T r0[K], y0[K];
+    // :173 -- the env's clock only moves once per step, so `time < T` is one decision per env and step
+    const bool live = time < cfg.T;
+    const bool any_live = (EPW == 1) ? live : __any_sync(kFull, live);
+    bool ok = true;
+    for (int count = 0; count < cfg.control_freq && any_live; ++count)
+        ok = ok & arz_substep<K, T, FAST, LPE>(r, y, ctx, co, j0, M);
+    if (EPW > 1 && !live) {                                // the other env of the warp integrated; this one is past T: its
+        arz_load_issue<K, T, LPE>(r_raw, rrow, M, l);      // lanes ran along on a state that is now discarded
+        arz_load_issue<K, T, LPE>(y_raw, yrow, M, l);
 #pragma unroll
-            for (int k = 0; k < K; ++k) { r0[k] = r[k]; y0[k] = y[k]; }
-            const bool ok = arz_substep<K, T, true>(r, y, ctx, co, j0, M);
-            if (__all_sync(kFull, ok)) continue;
-#pragma unroll
-            for (int k = 0; k < K; ++k) { r[k] = r0[k]; y[k] = y0[k]; }               // rare: redo with the exact divisions
+        for (int k = 0; k < K; ++k) {
+            r[k] = (j0 + k < M) ? r_raw[k] : T(1);
+            y[k] = (j0 + k < M) ? y_raw[k] : T(1);
         }
-        arz_substep<K, T, false>(r, y, ctx, co, j0, M);
+        ok = true;
     }
 
     // ---- velocity, reward, flags, observation (:226-233) ----
     T v[K];
-    {
-        bool ok = fast_cfg;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            v[k] = D::add(fast_div(y[k], r[k]), D::mul(ctx.vm, D::sub(T(1), ctx.by_rm.fast(r[k]))));
-            ok = ok & DivWindow<T>::b(r[k]) & DivWindow<T>::a(y[k]);
-        }
-        if (!__all_sync(kFull, ok)) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) v[k] = D::add(D::div(y[k], r[k]), veq(ctx, r[k]));
-        }
-    }
-    double sv = 0.0, sr = 0.0;
-    bool over = false, steady = true;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const bool valid = j0 + k < M;
-        v[k] = valid ? v[k] : T(0);
-        const double dv = static_cast<double>(D::sub(v[k], vs)), dr = static_cast<double>(D::sub(r[k], rs));
-        if (valid) {
-            sv += dv * dv;
-            sr += dr * dr;
-            over = over || (v[k] > static_cast<T>(cfg.vm)) || (r[k] > static_cast<T>(cfg.rm));
-            steady = steady && (dv == 0.0) && (dr == 0.0);
+        if constexpr (FAST) {
+            v[k] = D::add(fast_div(y[k], r[k]), D::mul(ctx.vm, D::sub(T(1), ctx.by_rm.fast(r[k]))));
+            ok = ok & DivWindow<T>::b(r[k]) & DivWindow<T>::a(y[k]);
+        } else {
+            v[k] = D::add(D::div(y[k], r[k]), veq(ctx, r[k]));
         }
     }
-    sv = warp_sum(sv);
-    sr = warp_sum(sr);
-    // traffic_arz_reward.py:22 (float64 mode: numpy's operations on float64 norms; float32 mode: the norms are float32 values)
-    const double reward = (sizeof(T) == 8)
-        ? -__dadd_rn(__ddiv_rn(sqrt(sv), static_cast<double>(vs)), __ddiv_rn(sqrt(sr), static_cast<double>(rs)))
-        : -static_cast<double>(__fadd_rn(__fdiv_rn(static_cast<float>(sqrt(sv)), static_cast<float>(vs)), __fdiv_rn(static_cast<float>(sqrt(sr)), static_cast<float>(rs))));
-    over = __any_sync(kFull, over);
-    steady = __all_sync(kFull, steady);
+    if constexpr (FAST) {
+        if (!__all_sync(kFull, ok)) return false;          // nothing stored yet: the exact instance redoes the step
+    }
+    double sv = 0.0, sr = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double dv = static_cast<double>(D::sub(v[k], vs)), dr = static_cast<double>(D::sub(r[k], rs));
+        if (j0 + k < M) {
+            sv += dv * dv;
+            sr += dr * dr;
+        }
+    }
+    // traffic_arz_reward.py:22: -(||v - vs|| / vs + ||rho - rs|| / rs)   (float64 mode: numpy's operations on float64
+    // norms; float32 mode: the norms are float32 values)
+    double reward;
+    if constexpr (LPE == 32) {
+        // both sums in ONE butterfly: the lower half-warp ends up with sum_v, the upper with sum_r; each half takes its own
+        // square root and quotient, and one more exchange adds the two terms
+        const bool up = (lane & 16) != 0;
+        double mine = up ? sr : sv;
+        mine += __shfl_xor_sync(kFull, up ? sv : sr, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
+        const double den = static_cast<double>(up ? rs : vs);
+        if constexpr (sizeof(T) == 8) {
+            const double term = __ddiv_rn(sqrt(mine), den);
+            reward = -__dadd_rn(term, __shfl_xor_sync(kFull, term, 16));
+            sv = mine;                                     // (only their being zero is looked at below)
+        } else {
+            const float term = __fdiv_rn(static_cast<float>(sqrt(mine)), static_cast<float>(den));
+            reward = -static_cast<double>(__fadd_rn(term, __shfl_xor_sync(kFull, term, 16)));
+        }
+        sv = mine + __shfl_xor_sync(kFull, mine, 16);      // sum_v + sum_r, for the steady-state test
+        sr = 0.0;
+    } else {
+        sv = seg_sum<LPE>(sv);
+        sr = seg_sum<LPE>(sr);
+        reward = (sizeof(T) == 8)
+            ? -__dadd_rn(__ddiv_rn(sqrt(sv), static_cast<double>(vs)), __ddiv_rn(sqrt(sr), static_cast<double>(rs)))
+            : -static_cast<double>(__fadd_rn(__fdiv_rn(static_cast<float>(sqrt(sv)), static_cast<float>(vs)), __fdiv_rn(static_cast<float>(sqrt(sr)), static_cast<float>(rs))));
+    }
+    const unsigned segm = seg_mask<LPE>(lane);
+    // truncate() (:116-127).  "Steady" = every deviation exactly zero: impossible unless both sums of squares are zero
+    // (the converse can fail through underflow), so the per-point test only runs in that case.
+    bool steady = false;
+    if (__any_sync(kFull, sv + sr == 0.0)) {
+        bool st_l = true;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (j0 + k < M) st_l = st_l && (D::sub(v[k], vs) == T(0)) && (D::sub(r[k], rs) == T(0));
+        steady = (__ballot_sync(kFull, !st_l) & segm) == 0u;
+    }
+    bool over = false;
+    if (cfg.limit_pde_state_size) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (j0 + k < M) over = over || (v[k] > static_cast<T>(cfg.vm)) || (r[k] > static_cast<T>(cfg.rm));
+        over = (__ballot_sync(kFull, over) & segm) != 0u;
+    }
     bool term = time >= cfg.t_over_dt;                                                // :109-111
     if (term) time = 0.0;
-    const bool trunc = (cfg.limit_pde_state_size && over) || steady;                  // :122-127
+    const bool trunc = over || steady;
     if (st != PDECG_ARZ_OUTLET_TRAIN) term = term || (reward > -0.00023);             // :233
+    if (!have) return true;                                                           // shadow segment: no stores (no warp-wide op follows)
 
-    arz_store<K, T>(r, rrow, M, sm, lane);
-    arz_store<K, T>(y, yrow, M, sm, lane);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = (j0 + k < M) ? v[k] : T(0);
+    arz_store<K, T, LPE>(r, rrow, M, sm, l);
+    arz_store<K, T, LPE>(y, yrow, M, sm, l);
     const bool restart = a.ar_profile != nullptr && (term || trunc);
     if (st == PDECG_ARZ_OUTLET_TRAIN) {                                               // :231
 #pragma unroll
@@ -310,27 +363,45 @@ __global__ void __launch_bounds__(kThreads, K <= 8 ? PDECG_ARZ_MINBLOCKS : 1) ar
         }
     }
     T* orow = reinterpret_cast<T*>(a.buf.obs) + env * 2 * M;
-    arz_store<K, T>(r, orow, M, sm, lane);
-    arz_store<K, T>(v, orow + M, M, sm, lane);
+    arz_store<K, T, LPE>(r, orow, M, sm, l);
+    arz_store<K, T, LPE>(v, orow + M, M, sm, l);
     if (restart && a.buf.final_obs != nullptr) {                                      // terminal observation for the caller
         T* frow_obs = reinterpret_cast<T*>(a.buf.final_obs) + env * 2 * M;
-        arz_store<K, T>(r, frow_obs, M, sm, lane);
-        arz_store<K, T>(v, frow_obs + M, M, sm, lane);
+        arz_store<K, T, LPE>(r, frow_obs, M, sm, l);
+        arz_store<K, T, LPE>(v, frow_obs + M, M, sm, l);
     }
-    if (lane == 0) {
+    if (l == 0) {
         frow[PDECG_ARZ_F_TIME] = time;
         a.buf.reward[env] = reward;
         a.buf.terminated[env] = term ? 1 : 0;
         a.buf.truncated[env] = trunc ? 1 : 0;
     }
-    if (restart) arz_autoreset_env<T>(a, env, lane);
+    if (restart) arz_autoreset_env<T, LPE>(a, env, l, segm);
+    return true;
+}
+
+template <int K, typename T, int LPE>
+__device__ __noinline__ void arz_step_env_exact(const ArzArgs& a, T* sm) {
+    arz_step_env<K, T, LPE, false>(a, sm);
+}
+
+template <int K, typename T, int LPE>
+__global__ void __launch_bounds__(kThreads, LPE == 16 ? PDECG_ARZ_MINBLOCKS_H : (K <= 8 ? PDECG_ARZ_MINBLOCKS : 1))
+arz_step_kernel(const __grid_constant__ ArzArgs a) {
+    __shared__ T sm_all[kWarpsPerBlock][(K <= 2 || LPE != 32) ? 1 : 32 * K];
+    const int wib = threadIdx.x >> 5;
+    if ((static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + wib) * (32 / LPE) >= a.buf.n_envs) return;      // whole warp
+    const ArzCtx<T> ctx(a.cfg);
+    bool done = false;
+    if (ctx.by_rm.fast_ok()) done = arz_step_env<K, T, LPE, true>(a, sm_all[wib]);     // uniform
+    if (!done) arz_step_env_exact<K, T, LPE>(a, sm_all[wib]);                         // rare: exceptional operands somewhere in the warp
 }
 
 // TrafficPDE1D.reset (:237-267) for one env, executed by its warp.  `keep_outputs`: leave reward / flags alone
 // (fused auto-reset: they keep the step's values).
 template <typename T>
 __device__ __forceinline__ void arz_reset_env(const ArzArgs& a, const double* __restrict__ profile, int64_t env, int lane,
-                                              bool keep_outputs) {
+                                              bool keep_outputs, int nlanes = 32) {
     using D = Strict<T>;
     const pdecg_arz_cfg& cfg = a.cfg;
     const ArzCtx<T> ctx(cfg);
@@ -339,7 +410,7 @@ __device__ __forceinline__ void arz_reset_env(const ArzArgs& a, const double* __
     const T rs = static_cast<T>(frow[PDECG_ARZ_F_RS]), qs = static_cast<T>(frow[PDECG_ARZ_F_QS]);
     T* rrow = reinterpret_cast<T*>(a.buf.ry) + env * 2 * M;
     T* orow = reinterpret_cast<T*>(a.buf.obs) + env * 2 * M;
-    for (int j = lane; j < M; j += 32) {
+    for (int j = lane; j < M; j += nlanes) {
         // :259-261  r = rs*profile ; y = qs*1 - vm*r + (vm/rm)*r**2 ; v = y/r + Veq(r)
         const T r = D::mul(rs, static_cast<T>(profile[j]));
         const T y = D::add(D::sub(D::mul(qs, T(1)), D::mul(static_cast<T>(cfg.vm), r)), D::mul(static_cast<T>(cfg.vm_over_rm), D::mul(r, r)));
@@ -357,10 +428,10 @@ __device__ __forceinline__ void arz_reset_env(const ArzArgs& a, const double* __
 }
 
 // fused same-step auto-reset: out of line so the (rare) restart does not weigh on the step kernel's registers
-template <typename T>
-__device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int lane) {
-    __syncwarp();                                  // the step's own row / observation stores come first
-    arz_reset_env<T>(a, a.ar_profile, env, lane, true);
+template <typename T, int LPE>
+__device__ __noinline__ void arz_autoreset_env(const ArzArgs& a, int64_t env, int l, unsigned segm) {
+    __syncwarp(segm);                              // the step's own row / observation stores come first
+    arz_reset_env<T>(a, a.ar_profile, env, l, true, LPE);
 }
 
 template <typename T>
@@ -385,6 +456,7 @@ static int arz_validate(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf) 
     if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (buf->n_envs > 0 && (!buf->ry || !buf->obs || !buf->fenv || !buf->reward || !buf->terminated || !buf->truncated))
         return fail(PDECG_ERR_INVALID, "null device buffer");
+    if (reinterpret_cast<uintptr_t>(buf->fenv) % 16 != 0) return fail(PDECG_ERR_INVALID, "fenv must be 16-byte aligned");
     return PDECG_OK;
 }
 
@@ -414,13 +486,30 @@ static int arz_launch_step(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* bu
     ArzArgs a{*cfg, *buf, ar_profile};
     const unsigned grid = static_cast<unsigned>((buf->n_envs + kWarpsPerBlock - 1) / kWarpsPerBlock);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Two envs per warp (16 lanes each): 29 % fewer instructions per env-step, but 118 registers at 4 points per lane
+    // leave 16 warps per SM and the kernel turns latency-bound (0.230 vs 0.199 ms per 262k-env step) -- opt-in only.
+    if (cfg->M <= 64 && getenv("PDECG_ARZ_LPE16")) {
+        const int64_t warps = (buf->n_envs + 1) / 2;
+        const unsigned grid2 = static_cast<unsigned>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        switch ((cfg->M + 15) / 16) {
+#define PDECG_CASE(KK)                                                                              \
+    case KK:                                                                                        \
+        if (cfg->precision == PDECG_PREC_FP32) arz_step_kernel<KK, float, 16><<<grid2, kThreads, 0, st>>>(a); \
+        else arz_step_kernel<KK, double, 16><<<grid2, kThreads, 0, st>>>(a);                         \
+        break;
+            PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4)
+#undef PDECG_CASE
+        }
+        count_launch();
+        return check_launch("arz_step_kernel");
+    }
     int K = (cfg->M + 31) / 32;
     if (K > 8) K = (K + 1) / 2 * 2;                    // 257..512 points: even K in {10, 12, 14, 16}
     switch (K) {
 #define PDECG_CASE(KK)                                                                          \
     case KK:                                                                                    \
-        if (cfg->precision == PDECG_PREC_FP32) arz_step_kernel<KK, float><<<grid, kThreads, 0, st>>>(a); \
-        else arz_step_kernel<KK, double><<<grid, kThreads, 0, st>>>(a);                          \
+        if (cfg->precision == PDECG_PREC_FP32) arz_step_kernel<KK, float, 32><<<grid, kThreads, 0, st>>>(a); \
+        else arz_step_kernel<KK, double, 32><<<grid, kThreads, 0, st>>>(a);                          \
         break;
         PDECG_CASE(1) PDECG_CASE(2) PDECG_CASE(3) PDECG_CASE(4) PDECG_CASE(5) PDECG_CASE(6) PDECG_CASE(7) PDECG_CASE(8)
         PDECG_CASE(10) PDECG_CASE(12) PDECG_CASE(14) PDECG_CASE(16)

@@ -191,3 +191,39 @@ def test_exceptional_operands_take_the_exact_division(cuda_device, dx):
             assert np.array_equal(g[fin].view(np.uint64), o_r[fin].view(np.uint64)), f"step {k}: obs not bit-identical"
             assert np.array_equal(env._ry.cpu().numpy()[:, 0, :][~np.isnan(orc.r)].view(np.uint64), orc.r[~np.isnan(orc.r)].view(np.uint64))
             assert np.array_equal(te_g.cpu().numpy(), te_r) and np.array_equal(tr_g.cpu().numpy(), tr_r), f"step {k}: flags"
+
+
+@pytest.mark.parametrize("mapping", ["two_envs_per_warp", "one_env_per_warp"])
+@pytest.mark.parametrize("B", [7, 2, 1])
+def test_staggered_clocks_and_both_lane_mappings(cuda_device, monkeypatch, mapping, B):
+    """Grids up to 64 points can run two envs per warp (16 lanes each, csrc/traffic_arz.cu; opt-in with PDECG_ARZ_LPE16,
+    measured slower).  Both must match the oracle, also when the two envs of a warp disagree on `time < T`
+    (the integration stops at time_index >= T while the episode runs until T/dt, traffic_arz_env.py:109-111,173) and with
+    an odd batch (the last warp's second half shadows the last env)."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    from pdecontrolgym_b200.envs_traffic_arz import F_TIME
+    if mapping == "two_envs_per_warp":
+        monkeypatch.setenv("PDECG_ARZ_LPE16", "1")
+    else:
+        monkeypatch.delenv("PDECG_ARZ_LPE16", raising=False)
+    kw = dict(T=5, dt=0.25, X=500, dx=10, simulation_type="outlet", control_freq=2)
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, reward_class=pcg.TrafficARZReward(), **kw)
+    orc = O.TrafficARZOracle(B, **kw)
+    env.reset()
+    orc.reset()
+    clocks = np.array([0.0, 4.0, 1.5, 4.5, 3.25, 0.25, 4.75])[:B]      # integration stops at 5.0: envs cross it on different steps
+    orc.time_index = clocks.copy()
+    env._fenv[:, F_TIME] = torch.from_numpy(clocks).to(cuda_device)
+    rng = np.random.default_rng(9)
+    mixed = False
+    for k in range(30):
+        a = rng.uniform(0.9, 1.5, size=(B, 1))
+        o_r, r_r, te_r, tr_r = orc.step(a)
+        o_g, r_g, te_g, tr_g, _ = env.step(torch.from_numpy(a))
+        assert np.array_equal(o_g.cpu().numpy(), o_r), f"step {k}: obs not bit-identical"
+        np.testing.assert_allclose(r_g.cpu().numpy(), r_r, rtol=1e-12)
+        assert np.array_equal(te_g.cpu().numpy(), te_r) and np.array_equal(tr_g.cpu().numpy(), tr_r)
+        assert np.array_equal(env.time_index.cpu().numpy(), orc.time_index)
+        mixed |= bool((orc.time_index >= 5.0).any() and (orc.time_index < 5.0).any())
+    assert mixed or B == 1
