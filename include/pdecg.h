@@ -232,8 +232,8 @@ typedef struct {
                                where the observation is the state itself)                              */
     const double* x_scale;  /* [nx] np.linspace(0, X, nx)   (:57)                                        */
     const double* action;   /* [n_envs] proportion of total_dosage (unused by WRAP_RESET / RUN_TO_END)   */
-    int32_t* ienv;          /* [n_envs, PDECG_BT_NINT]                                                  */
-    double* fenv;           /* [n_envs, PDECG_BT_NF64]                                                  */
+    int32_t* ienv;          /* [n_envs, PDECG_BT_NINT], 16-byte aligned                                 */
+    double* fenv;           /* [n_envs, PDECG_BT_NF64], 16-byte aligned                                 */
     double* reward;         /* [n_envs]                                                                 */
     uint8_t* terminated;    /* [n_envs]                                                                 */
     uint8_t* truncated;     /* [n_envs]                                                                 */

@@ -55,14 +55,16 @@ struct BtDivs {      // the two loop-invariant divisors of _update_fd (:236-237)
     unsigned om_limit;  // |u_c| with a high word below this takes the 3-instruction quotient (0: never)
     unsigned k_hi;      // high word of k: 0 <= v < k for sure when hiword(v) < k_hi (as unsigned)
     bool dx2_one;       // dx**2 == 1 (the reference's grid): the division by it is the identity
-    __device__ __forceinline__ explicit BtDivs(const pdecg_bt_cfg& cfg) : by_dx2(cfg.dx * cfg.dx), by_k(cfg.k) {   // self.dx ** 2 (one rounded multiply)
+    __device__ __forceinline__ explicit BtDivs(const pdecg_bt_cfg& cfg) : by_k(cfg.k) {
+        const double dx2 = cfg.dx * cfg.dx;                     // self.dx ** 2 (one rounded multiply)
+        dx2_one = (dx2 == 1.0);                                 // the reference's grid: no reciprocal to set up (uniform branch)
+        if (!dx2_one) by_dx2 = ConstDiv<double>(dx2);
         const unsigned khi = static_cast<unsigned>(__double2hiint(cfg.k)) & 0x7ff00000u;    // 2^floor(log2 k)
         tiny_hi = (khi > (61u << 20)) ? khi - (60u << 20) : 0u;
         // ConstDiv<double>::in_range is 0x07b00000 <= hi < 0x78300000; everything below tiny_hi is fine too (see
         // bt_fd), so one unsigned compare covers both whenever the two windows overlap
         om_limit = (by_k.d_ok && tiny_hi >= 0x07b00000u) ? 0x78300000u : 0u;
         k_hi = static_cast<unsigned>(__double2hiint(cfg.k));
-        dx2_one = (by_dx2.d == 1.0);
     }
 };
 
@@ -382,30 +384,25 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
     // start the row load first: the scalar loads and their broadcast then overlap its latency
     T* urow = reinterpret_cast<T*>(a.buf.u) + env * nx;
     T u[K], u_raw[K];
-    load_row_issue<T, T, K>(u_raw, urow, nx, lane);
-    // per-env scalars: one coalesced read, broadcast by shuffle
+    constexpr int SURE = (K <= 8) ? K - 1 : K - 2;      // rows of a coalesced pass (j = lane + 32 i) that lie inside the row for every lane
+    load_row_issue<T, T, K, 32, SURE>(u_raw, urow, nx, lane);
+    // per-env scalars: the 64-byte integer row and the 32-byte float row, read by every lane as broadcast 16-byte loads
     int* irow = a.buf.ienv + env * PDECG_BT_NINT;
     double* frow = a.buf.fenv + env * PDECG_BT_NF64;
-    const int iv = (lane < PDECG_BT_NINT) ? irow[lane] : 0;
-    const double fv = (lane < PDECG_BT_NF64) ? frow[lane] : 0.0;
+    static_assert(PDECG_BT_I_T == 0 && PDECG_BT_I_STAGE == 1 && PDECG_BT_I_GROWTH_DAYS == 2 && PDECG_BT_I_THERAPY_DAYS == 3 &&
+                  PDECG_BT_I_POST_DAYS == 4 && PDECG_BT_I_SIM_DAYS == 5 && PDECG_BT_I_FIRST_THERAPY == 6 && PDECG_BT_I_FIRST_POST == 7 &&
+                  PDECG_BT_I_DEATH_DAY == 8 && PDECG_BT_I_T_BENCHMARK == 9 && PDECG_BT_I_CONSECUTIVE == 10 &&
+                  PDECG_BT_I_TREATMENT_CALLS == 11 && PDECG_BT_I_VIOLATIONS == 12 && PDECG_BT_NINT == 16, "ienv row layout");
+    static_assert(PDECG_BT_F_REMAINING == 0 && PDECG_BT_F_D == 1 && PDECG_BT_F_RHO == 2 && PDECG_BT_F_LAST_DOSE == 3 && PDECG_BT_NF64 == 4, "fenv row layout");
+    const int4 i0 = reinterpret_cast<const int4*>(irow)[0], i1 = reinterpret_cast<const int4*>(irow)[1];
+    const int4 i2 = reinterpret_cast<const int4*>(irow)[2], i3 = reinterpret_cast<const int4*>(irow)[3];
+    const double2 f0 = reinterpret_cast<const double2*>(frow)[0], f1 = reinterpret_cast<const double2*>(frow)[1];
     BtEnv e;
-    e.t = __shfl_sync(kFull, iv, PDECG_BT_I_T);
-    e.stage = __shfl_sync(kFull, iv, PDECG_BT_I_STAGE);
-    e.growthDays = __shfl_sync(kFull, iv, PDECG_BT_I_GROWTH_DAYS);
-    e.therapyDays = __shfl_sync(kFull, iv, PDECG_BT_I_THERAPY_DAYS);
-    e.postTherapyDays = __shfl_sync(kFull, iv, PDECG_BT_I_POST_DAYS);
-    e.simulationDays = __shfl_sync(kFull, iv, PDECG_BT_I_SIM_DAYS);
-    e.firstTherapyDay = __shfl_sync(kFull, iv, PDECG_BT_I_FIRST_THERAPY);
-    e.firstPostTherapyDay = __shfl_sync(kFull, iv, PDECG_BT_I_FIRST_POST);
-    e.cDeathDay = __shfl_sync(kFull, iv, PDECG_BT_I_DEATH_DAY);
-    e.t_benchmark = __shfl_sync(kFull, iv, PDECG_BT_I_T_BENCHMARK);
-    e.consecutive = __shfl_sync(kFull, iv, PDECG_BT_I_CONSECUTIVE);
-    e.treatment_calls = __shfl_sync(kFull, iv, PDECG_BT_I_TREATMENT_CALLS);
-    e.violations = __shfl_sync(kFull, iv, PDECG_BT_I_VIOLATIONS);
-    e.remaining = __shfl_sync(kFull, fv, PDECG_BT_F_REMAINING);
-    e.D = __shfl_sync(kFull, fv, PDECG_BT_F_D);
-    e.rho = __shfl_sync(kFull, fv, PDECG_BT_F_RHO);
-    e.last_dose = __shfl_sync(kFull, fv, PDECG_BT_F_LAST_DOSE);
+    e.t = i0.x; e.stage = i0.y; e.growthDays = i0.z; e.therapyDays = i0.w;
+    e.postTherapyDays = i1.x; e.simulationDays = i1.y; e.firstTherapyDay = i1.z; e.firstPostTherapyDay = i1.w;
+    e.cDeathDay = i2.x; e.t_benchmark = i2.y; e.consecutive = i2.z; e.treatment_calls = i2.w;
+    e.violations = i3.x;
+    e.remaining = f0.x; e.D = f0.y; e.rho = f1.x; e.last_dose = f1.y;
 
     load_row_finish<T, K>(u, u_raw, sm, lane);
 
@@ -430,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
         // TherapyWrapper.reset (:408-427); with a mask only the selected envs take part (the others keep their
         // consecutive-treatment-day counter and everything else: they are mid-therapy patients of the same batch)
         if (a.buf.mask != nullptr && a.buf.mask[env] == 0) {
-            if (obs_all != nullptr) store_row_chunk<T, K>(u, obs_all + env * nx, nx, sm, lane);
+            if (obs_all != nullptr) store_row_chunk<T, K, 32, SURE>(u, obs_all + env * nx, nx, sm, lane);
             return;
         }
         e.consecutive = 0;
@@ -459,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
                     // the observation returned is the therapy day's row; the two rest days' results are
                     // discarded and the loop tests the STALE flags (:470-473)
                     if (obs_all != nullptr) {
-                        store_row_chunk<T, K>(u, obs_all + env * nx, nx, sm, lane);
+                        store_row_chunk<T, K, 32, SURE>(u, obs_all + env * nx, nx, sm, lane);
                         wrote_obs = true;
                     }
                     for (int i = 0; i < 2; ++i) {
@@ -478,29 +475,20 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
         }
     }
 
-    store_row_chunk<T, K>(u, urow, nx, sm, lane);
-    if (obs_all != nullptr && !wrote_obs) store_row_chunk<T, K>(u, obs_all + env * nx, nx, sm, lane);
+    store_row_chunk<T, K, 32, SURE>(u, urow, nx, sm, lane);
+    if (obs_all != nullptr && !wrote_obs) store_row_chunk<T, K, 32, SURE>(u, obs_all + env * nx, nx, sm, lane);
 
-    // write back scalars (coalesced)
-    int ov = iv;
-    ov = (lane == PDECG_BT_I_T) ? e.t : ov;
-    ov = (lane == PDECG_BT_I_STAGE) ? e.stage : ov;
-    ov = (lane == PDECG_BT_I_GROWTH_DAYS) ? e.growthDays : ov;
-    ov = (lane == PDECG_BT_I_THERAPY_DAYS) ? e.therapyDays : ov;
-    ov = (lane == PDECG_BT_I_POST_DAYS) ? e.postTherapyDays : ov;
-    ov = (lane == PDECG_BT_I_SIM_DAYS) ? e.simulationDays : ov;
-    ov = (lane == PDECG_BT_I_FIRST_THERAPY) ? e.firstTherapyDay : ov;
-    ov = (lane == PDECG_BT_I_FIRST_POST) ? e.firstPostTherapyDay : ov;
-    ov = (lane == PDECG_BT_I_DEATH_DAY) ? e.cDeathDay : ov;
-    ov = (lane == PDECG_BT_I_T_BENCHMARK) ? e.t_benchmark : ov;
-    ov = (lane == PDECG_BT_I_CONSECUTIVE) ? e.consecutive : ov;
-    ov = (lane == PDECG_BT_I_TREATMENT_CALLS) ? e.treatment_calls : ov;
-    ov = (lane == PDECG_BT_I_VIOLATIONS) ? e.violations : ov;
-    if (lane < PDECG_BT_NINT) irow[lane] = ov;
-    double of = fv;
-    of = (lane == PDECG_BT_F_REMAINING) ? e.remaining : of;
-    of = (lane == PDECG_BT_F_LAST_DOSE) ? e.last_dose : of;
-    if (lane < PDECG_BT_NF64) frow[lane] = of;
+    // write back the scalars (lane 0: four + two 16-byte stores; the unused tail of the integer row keeps its contents)
+    if (lane == 0) {
+        int4* io = reinterpret_cast<int4*>(irow);
+        io[0] = make_int4(e.t, e.stage, e.growthDays, e.therapyDays);
+        io[1] = make_int4(e.postTherapyDays, e.simulationDays, e.firstTherapyDay, e.firstPostTherapyDay);
+        io[2] = make_int4(e.cDeathDay, e.t_benchmark, e.consecutive, e.treatment_calls);
+        io[3] = make_int4(e.violations, i3.y, i3.z, i3.w);
+        double2* fo = reinterpret_cast<double2*>(frow);
+        fo[0] = make_double2(e.remaining, f0.y);
+        fo[1] = make_double2(f1.x, e.last_dose);
+    }
     if (lane == 0) {
         a.buf.reward[env] = reward;
         a.buf.terminated[env] = term ? 1 : 0;
@@ -510,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
     if constexpr (!MULTI) {
         if (a.ar_init != nullptr && (term || trunc)) {
             if (a.buf.final_obs != nullptr)          // terminal observation for the caller, before the row is re-initialised
-                store_row_chunk<T, K>(u, reinterpret_cast<T*>(a.buf.final_obs) + env * nx, nx, sm, lane);
+                store_row_chunk<T, K, 32, SURE>(u, reinterpret_cast<T*>(a.buf.final_obs) + env * nx, nx, sm, lane);
             bt_autoreset_env_t<T>(a, env, lane);
         }
     }
@@ -577,6 +565,8 @@ static int bt_validate(const pdecg_bt_cfg* cfg, const pdecg_bt_buffers* buf) {
     if (buf->n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (buf->n_envs > 0 && (!buf->u || !buf->ienv || !buf->fenv || !buf->reward || !buf->terminated || !buf->truncated || !buf->x_scale))
         return fail(PDECG_ERR_INVALID, "null device buffer");
+    if (reinterpret_cast<uintptr_t>(buf->ienv) % 16 != 0 || reinterpret_cast<uintptr_t>(buf->fenv) % 16 != 0)
+        return fail(PDECG_ERR_INVALID, "ienv / fenv must be 16-byte aligned");
     return PDECG_OK;
 }
 

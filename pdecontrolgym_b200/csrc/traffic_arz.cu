@@ -13,7 +13,7 @@
 #define PDECG_BT_MINBLOCKS 1
 #endif
 #ifndef PDECG_ARZ_MINBLOCKS
-#define PDECG_ARZ_MINBLOCKS 8    // 64 registers, 32 warps/SM (measured at 262k envs: 12 -> 0.285, 10 -> 0.262, 8 -> 0.254, 6 -> 0.297 ms)
+#define PDECG_ARZ_MINBLOCKS 8    // 64 registers, 32 warps/SM (measured at 262k envs: 10 -> 0.187, 9 -> 0.185, 8 -> 0.178, 7 -> 0.180, 6 -> 0.189 ms)
 #endif
 #ifndef PDECG_ARZ_MINBLOCKS_H
 #define PDECG_ARZ_MINBLOCKS_H 4  // two envs per warp, up to 4 points per lane
