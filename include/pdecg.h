@@ -335,7 +335,8 @@ int pdecg_arz_step_host(const pdecg_arz_cfg* cfg, const pdecg_arz_buffers* buf, 
                         const double* autoreset_profile, pdecg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Family 4: NavierStokes2D (Chorin projection, Jacobi pressure solve) + NSReward   -- all float64
+ * Family 4: NavierStokes2D (Chorin projection, Jacobi pressure solve) + NSReward
+ *           float64 (bit-identical fields), or opt-in float32 fields / arithmetic (precision = PDECG_PREC_FP32)
  * ------------------------------------------------------------------------------------------ */
 typedef enum { PDECG_NS_DIRICHLET = 0, PDECG_NS_NEUMANN = 1, PDECG_NS_CONTROLLABLE = 2 } pdecg_ns_bc;
 /* side order = the order apply_boundary visits them (navier_stokes2D.py:76): lower (row 0),
@@ -353,10 +354,17 @@ typedef struct {
     double dt, dx, dy;
     double viscosity, density;
     double gamma;                 /* NSReward(gamma)                              ns_reward.py:15       */
+    int32_t precision;            /* PDECG_PREC_REF / PDECG_PREC_FP64: float64 everywhere, as the reference (bit-identical
+                                     fields).  PDECG_PREC_FP32: opt-in fast mode -- u, v, p, obs, final_obs are FLOAT32
+                                     buffers and the step runs in float32 (same operation order); actions, u_ref, action_ref,
+                                     the reward and the initial fields handed to reset stay float64.  On-chip grids only
+                                     (nx * ny <= 4,096).                                                              */
+    int32_t reserved;
 } pdecg_ns_cfg;
 
 typedef struct {
     int64_t n_envs;
+    /* u, v, p, obs, final_obs: float64, or float32 storage behind the same pointers when cfg.precision == PDECG_PREC_FP32 */
     double* u;               /* [n_envs, ny, nx]  x-velocity (row = y index, col = x index, as the reference) */
     double* v;               /* [n_envs, ny, nx]                                                            */
     double* p;               /* [n_envs, ny, nx]  pressure, warm start of the next solve (:115,129)          */

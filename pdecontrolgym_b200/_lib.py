@@ -98,6 +98,7 @@ class NsCfg(C.Structure):
         ("n_pressure_iters", C.c_int32), ("bc", (C.c_int32 * 2) * 4), ("n_action_ref", C.c_int32),
         ("n_uref", C.c_int32), ("dt", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
         ("viscosity", C.c_double), ("density", C.c_double), ("gamma", C.c_double),
+        ("precision", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -14,6 +14,7 @@
 // Jacobi formula at the clamped index of its own point -- boundary points recompute their neighbour's
 // value (same inputs, same operation order => same bits) instead of waiting for a second barrier.
 #include <cstdlib>
+#include <type_traits>
 
 #include "pdecg_internal.h"
 
@@ -36,17 +37,25 @@ struct NsArgs {
 
 // NavierStokes2D.reset (:171-194) for one env, executed by `nth` cooperating threads (a CTA or a warp).
 // `keep_outputs`: leave reward / flags / valid alone (fused auto-reset: they keep the step's values).
+// T = double: the reference's arithmetic (bit-identical fields).  T = float: the opt-in fast mode (PDECG_PREC_FP32):
+// float32 fields, observation and arithmetic in the same operation order; actions, the reference trajectory, the reward
+// and the initial conditions handed to reset stay float64.
+template <typename T>
 __device__ __forceinline__ void ns_reset_env(const NsArgs& a, const double* __restrict__ iu, const double* __restrict__ iv,
                                              const double* __restrict__ ip, int64_t stride, int64_t env, int tid, int nth,
                                              bool keep_outputs) {
     const int npt = a.cfg.nx * a.cfg.ny;
+    T* const bu = reinterpret_cast<T*>(a.buf.u);
+    T* const bv = reinterpret_cast<T*>(a.buf.v);
+    T* const bp = reinterpret_cast<T*>(a.buf.p);
+    T* const bo = reinterpret_cast<T*>(a.buf.obs);
     for (int q = tid; q < npt; q += nth) {
-        const double un = iu[env * stride + q], vn = iv[env * stride + q];
-        a.buf.u[env * npt + q] = un;
-        a.buf.v[env * npt + q] = vn;
-        a.buf.p[env * npt + q] = ip[env * stride + q];
-        a.buf.obs[(env * npt + q) * 2] = un;
-        a.buf.obs[(env * npt + q) * 2 + 1] = vn;
+        const T un = static_cast<T>(iu[env * stride + q]), vn = static_cast<T>(iv[env * stride + q]);
+        bu[env * npt + q] = un;
+        bv[env * npt + q] = vn;
+        bp[env * npt + q] = static_cast<T>(ip[env * stride + q]);
+        bo[(env * npt + q) * 2] = un;
+        bo[(env * npt + q) * 2 + 1] = vn;
     }
     if (tid == 0) {
         a.buf.time_index[env] = 0;
@@ -72,29 +81,34 @@ constexpr int kNsMaxPoints = 4096;   // 7 fields x 4096 x 8 B = 224 KB of the 22
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // central_difference (:9-15) and laplace (:17-22) at an INTERIOR point of a smem field with row pitch nx
-__device__ __forceinline__ double cd_x(const double* f, int i, int j, int nx, double two_dx) {
-    return D::div(D::sub(f[i * nx + j + 1], f[i * nx + j - 1]), two_dx);
+template <typename T>
+__device__ __forceinline__ T cd_x(const T* f, int i, int j, int nx, T two_dx) {
+    return Strict<T>::div(Strict<T>::sub(f[i * nx + j + 1], f[i * nx + j - 1]), two_dx);
 }
-__device__ __forceinline__ double cd_y(const double* f, int i, int j, int nx, double two_dy) {
-    return D::div(D::sub(f[(i + 1) * nx + j], f[(i - 1) * nx + j]), two_dy);
+template <typename T>
+__device__ __forceinline__ T cd_y(const T* f, int i, int j, int nx, T two_dy) {
+    return Strict<T>::div(Strict<T>::sub(f[(i + 1) * nx + j], f[(i - 1) * nx + j]), two_dy);
 }
-__device__ __forceinline__ double lap5(const double* f, int i, int j, int nx, double dxdy) {
-    const double c = f[i * nx + j];
-    double s = D::add(f[i * nx + j - 1], f[(i - 1) * nx + j]);
-    s = D::sub(s, D::mul(4.0, c));
-    s = D::add(s, f[i * nx + j + 1]);
-    s = D::add(s, f[(i + 1) * nx + j]);
-    return D::div(s, dxdy);
+template <typename T>
+__device__ __forceinline__ T lap5(const T* f, int i, int j, int nx, T dxdy) {
+    using S = Strict<T>;
+    const T c = f[i * nx + j];
+    T s = S::add(f[i * nx + j - 1], f[(i - 1) * nx + j]);
+    s = S::sub(s, S::mul(T(4), c));
+    s = S::add(s, f[i * nx + j + 1]);
+    s = S::add(s, f[(i + 1) * nx + j]);
+    return S::div(s, dxdy);
 }
 
 // apply_boundary (:68-91): sides in the reference's order, u before v; a barrier between sides keeps the
 // corner values order-dependent exactly like the sequential numpy assignments.
-__device__ void apply_boundary(const pdecg_ns_cfg& cfg, double* fu, double* fv, double action, int tid, int nthreads) {
+template <typename T>
+__device__ void apply_boundary(const pdecg_ns_cfg& cfg, T* fu, T* fv, T action, int tid, int nthreads) {
     const int nx = cfg.nx, ny = cfg.ny;
     for (int side = 0; side < 4; ++side) {
         const int len = (side < 2) ? nx : ny;
         for (int comp = 0; comp < 2; ++comp) {
-            double* f = comp == 0 ? fu : fv;
+            T* f = comp == 0 ? fu : fv;
             const int cond = cfg.bc[side][comp];
             for (int q = tid; q < len; q += nthreads) {
                 int dst, src;
@@ -103,7 +117,7 @@ __device__ void apply_boundary(const pdecg_ns_cfg& cfg, double* fu, double* fv, 
                 else if (side == PDECG_NS_LEFT) { dst = q * nx; src = q * nx + 1; }
                 else { dst = q * nx + nx - 1; src = q * nx + nx - 2; }
                 if (cond == PDECG_NS_NEUMANN) f[dst] = f[src];
-                else if (cond == PDECG_NS_DIRICHLET) f[dst] = 0.0;
+                else if (cond == PDECG_NS_DIRICHLET) f[dst] = T(0);
                 else f[dst] = action;
             }
         }
@@ -113,12 +127,13 @@ __device__ void apply_boundary(const pdecg_ns_cfg& cfg, double* fu, double* fv, 
 
 // N Jacobi sweeps (:104-114) on smem ping-pong buffers pa (current) / pb; returns the buffer holding the result.
 // `b` = (dx*dy) * rhs, per point (only interior entries are read).
-template <int PT>
-__device__ __forceinline__ double* jacobi(const pdecg_ns_cfg& cfg, double* pa, double* pb, const double* b, int tid, int nthreads) {
+template <int PT, typename T>
+__device__ __forceinline__ T* jacobi(const pdecg_ns_cfg& cfg, T* pa, T* pb, const T* b, int tid, int nthreads) {
+    using S = Strict<T>;
     const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny;
     // each thread owns up to PT points (npt <= PT*nthreads is enforced on the host)
     int idx[PT], ci[PT];
-    double bb[PT];
+    T bb[PT];
 #pragma unroll
     for (int s = 0; s < PT; ++s) {
         const int q = tid + s * nthreads;
@@ -132,58 +147,66 @@ __device__ __forceinline__ double* jacobi(const pdecg_ns_cfg& cfg, double* pa, d
         for (int s = 0; s < PT; ++s) {
             if (idx[s] >= 0) {
                 const int c = ci[s];
-                double acc = D::add(pa[c - 1], pa[c - nx]);     // ((left + up) + right) + down
-                acc = D::add(acc, pa[c + 1]);
-                acc = D::add(acc, pa[c + nx]);
-                pb[idx[s]] = D::mul(0.25, D::sub(acc, bb[s]));
+                T acc = S::add(pa[c - 1], pa[c - nx]);     // ((left + up) + right) + down
+                acc = S::add(acc, pa[c + 1]);
+                acc = S::add(acc, pa[c + nx]);
+                pb[idx[s]] = S::mul(T(0.25), S::sub(acc, bb[s]));
             }
         }
         __syncthreads();
-        double* t = pa; pa = pb; pb = t;
+        T* t = pa; pa = pb; pb = t;
     }
     return pa;
 }
 
 // THREADS x PT >= nx*ny: (256, 2) up to 512 points, (512, 4) up to 2,048, (1024, 4) up to 4,096 (64 x 64; the seven
 // float64 fields of one env then fill the SM's 227 KB of shared memory)
-template <int THREADS, int PT>
+template <int THREADS, int PT, typename T>
 __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
-    extern __shared__ double smem[];
+    using S = Strict<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
     const pdecg_ns_cfg& cfg = a.cfg;
     const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny;
     const int tid = threadIdx.x, nth = blockDim.x;
     const int64_t env = blockIdx.x;
-    double* su = smem;                 // u  -> u_next
-    double* sv = su + npt;             // v  -> v_next
-    double* sus = sv + npt;            // u* (predictor)
-    double* svs = sus + npt;           // v*
-    double* sp0 = svs + npt;           // pressure ping
-    double* sp1 = sp0 + npt;           // pressure pong
-    double* sb = sp1 + npt;            // (dx*dy) * rhs
+    T* su = smem;                 // u  -> u_next
+    T* sv = su + npt;             // v  -> v_next
+    T* sus = sv + npt;            // u* (predictor)
+    T* svs = sus + npt;           // v*
+    T* sp0 = svs + npt;           // pressure ping
+    T* sp1 = sp0 + npt;           // pressure pong
+    T* sb = sp1 + npt;            // (dx*dy) * rhs
     __shared__ double red[THREADS / 32];
 
-    const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
-    const double dxdy = D::mul(cfg.dx, cfg.dy);
+    const T dx = static_cast<T>(cfg.dx), dy = static_cast<T>(cfg.dy), dt = static_cast<T>(cfg.dt);
+    const T nu = static_cast<T>(cfg.viscosity), rho = static_cast<T>(cfg.density);
+    const T two_dx = S::mul(T(2), dx), two_dy = S::mul(T(2), dy);
+    const T dxdy = S::mul(dx, dy);
 
     if (a.solve_only) {
-        const double* gu = a.su + env * npt;
-        const double* gv = a.sv + env * npt;
-        double* gp = a.sp + env * npt;
-        for (int q = tid; q < npt; q += nth) { sus[q] = gu[q]; svs[q] = gv[q]; sp0[q] = gp[q]; sb[q] = 0.0; }
-        __syncthreads();
-        const double rho_dt = D::div(cfg.density, cfg.dt);
-        for (int q = tid; q < npt; q += nth) {
-            const int i = q / nx, j = q % nx;
-            if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2)
-                sb[q] = D::mul(dxdy, D::mul(rho_dt, D::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
+        if constexpr (sizeof(T) == 8) {          // NavierStokes2D.solve_pressure alone (float64 callers only)
+            const double* gu = a.su + env * npt;
+            const double* gv = a.sv + env * npt;
+            double* gp = a.sp + env * npt;
+            for (int q = tid; q < npt; q += nth) { sus[q] = gu[q]; svs[q] = gv[q]; sp0[q] = gp[q]; sb[q] = 0.0; }
+            __syncthreads();
+            const double rho_dt = D::div(cfg.density, cfg.dt);
+            for (int q = tid; q < npt; q += nth) {
+                const int i = q / nx, j = q % nx;
+                if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2)
+                    sb[q] = D::mul(dxdy, D::mul(rho_dt, D::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
+            }
+            __syncthreads();
+            double* pf = jacobi<PT, double>(cfg, sp0, sp1, sb, tid, nth);
+            for (int q = tid; q < npt; q += nth) gp[q] = pf[q];
         }
-        __syncthreads();
-        double* pf = jacobi<PT>(cfg, sp0, sp1, sb, tid, nth);
-        for (int q = tid; q < npt; q += nth) gp[q] = pf[q];
         return;
     }
 
     const int t0 = a.buf.time_index[env];
+    T* const obs_all = reinterpret_cast<T*>(a.buf.obs);
+    T* const fobs_all = reinterpret_cast<T*>(a.buf.final_obs);
     if (t0 + 1 >= cfg.nt || t0 + 1 >= cfg.n_uref || t0 + 1 >= cfg.n_action_ref) {
         // the reference raises IndexError here (U[time_index] / U_ref / action_ref out of range)
         if (tid == 0) {
@@ -193,79 +216,80 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
             a.buf.reward[env] = 0.0;
         }
         if (a.ar_u != nullptr) {
-            if (a.buf.final_obs != nullptr) {        // terminal observation = the (unchanged) current U[t]
-                for (int q = tid; q < 2 * npt; q += nth) a.buf.final_obs[env * npt * 2 + q] = a.buf.obs[env * npt * 2 + q];
+            if (fobs_all != nullptr) {        // terminal observation = the (unchanged) current U[t]
+                for (int q = tid; q < 2 * npt; q += nth) fobs_all[env * npt * 2 + q] = obs_all[env * npt * 2 + q];
                 __syncthreads();
             }
-            ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
+            ns_reset_env<T>(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
         }
         return;
     }
-    double* gu = a.buf.u + env * npt;
-    double* gv = a.buf.v + env * npt;
-    double* gp = a.buf.p + env * npt;
-    const double action = a.buf.action[env];
+    T* gu = reinterpret_cast<T*>(a.buf.u) + env * npt;
+    T* gv = reinterpret_cast<T*>(a.buf.v) + env * npt;
+    T* gp = reinterpret_cast<T*>(a.buf.p) + env * npt;
+    const double action_d = a.buf.action[env];
+    const T action = static_cast<T>(action_d);
     for (int q = tid; q < npt; q += nth) { su[q] = gu[q]; sv[q] = gv[q]; sp0[q] = gp[q]; }
     __syncthreads();
 
     // ---- predictor (:130-138) ----
     for (int q = tid; q < npt; q += nth) {
         const int i = q / nx, j = q % nx;
-        double us = su[q], vs = sv[q];
+        T us = su[q], vs = sv[q];
         if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2) {
-            const double u0 = su[q], v0 = sv[q];
+            const T u0 = su[q], v0 = sv[q];
             // u + dt * (((-u)*dudx - v*dudy) + nu*lap(u))
-            double adv = D::sub(D::mul(-u0, cd_x(su, i, j, nx, two_dx)), D::mul(v0, cd_y(su, i, j, nx, two_dy)));
-            us = D::add(u0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap5(su, i, j, nx, dxdy)))));
-            adv = D::sub(D::mul(-u0, cd_x(sv, i, j, nx, two_dx)), D::mul(v0, cd_y(sv, i, j, nx, two_dy)));
-            vs = D::add(v0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap5(sv, i, j, nx, dxdy)))));
+            T adv = S::sub(S::mul(-u0, cd_x(su, i, j, nx, two_dx)), S::mul(v0, cd_y(su, i, j, nx, two_dy)));
+            us = S::add(u0, S::mul(dt, S::add(adv, S::mul(nu, lap5(su, i, j, nx, dxdy)))));
+            adv = S::sub(S::mul(-u0, cd_x(sv, i, j, nx, two_dx)), S::mul(v0, cd_y(sv, i, j, nx, two_dy)));
+            vs = S::add(v0, S::mul(dt, S::add(adv, S::mul(nu, lap5(sv, i, j, nx, dxdy)))));
         }
         sus[q] = us;
         svs[q] = vs;
     }
     __syncthreads();
-    apply_boundary(cfg, sus, svs, action, tid, nth);
+    apply_boundary<T>(cfg, sus, svs, action, tid, nth);
 
     // ---- pressure Poisson (:94-116) ----
-    const double rho_dt = D::div(cfg.density, cfg.dt);
+    const T rho_dt = S::div(rho, dt);
     for (int q = tid; q < npt; q += nth) {
         const int i = q / nx, j = q % nx;
-        double bv = 0.0;
+        T bv = T(0);
         if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2)
-            bv = D::mul(dxdy, D::mul(rho_dt, D::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
+            bv = S::mul(dxdy, S::mul(rho_dt, S::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
         sb[q] = bv;
     }
     __syncthreads();
-    double* pf = jacobi<PT>(cfg, sp0, sp1, sb, tid, nth);
+    T* pf = jacobi<PT, T>(cfg, sp0, sp1, sb, tid, nth);
 
     // ---- corrector (:143-146) ----
-    const double dt_rho = D::div(cfg.dt, cfg.density);
+    const T dt_rho = S::div(dt, rho);
     for (int q = tid; q < npt; q += nth) {
         const int i = q / nx, j = q % nx;
-        double un = sus[q], vn = svs[q];
+        T un = sus[q], vn = svs[q];
         if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2) {
-            un = D::sub(un, D::mul(dt_rho, cd_x(pf, i, j, nx, two_dx)));
-            vn = D::sub(vn, D::mul(dt_rho, cd_y(pf, i, j, nx, two_dy)));
+            un = S::sub(un, S::mul(dt_rho, cd_x(pf, i, j, nx, two_dx)));
+            vn = S::sub(vn, S::mul(dt_rho, cd_y(pf, i, j, nx, two_dy)));
         }
         su[q] = un;
         sv[q] = vn;
     }
     __syncthreads();
-    apply_boundary(cfg, su, sv, action, tid, nth);
+    apply_boundary<T>(cfg, su, sv, action, tid, nth);
 
     // ---- store, observation U[t], reward (:147-157, ns_reward.py:28) ----
     const int t1 = t0 + 1;
     const double* uref = a.buf.u_ref + static_cast<int64_t>(t1) * npt * 2;
-    double* gobs = a.buf.obs + env * npt * 2;
+    T* gobs = obs_all + env * npt * 2;
     double ss = 0.0;
     for (int q = tid; q < npt; q += nth) {
-        const double un = su[q], vn = sv[q];
+        const T un = su[q], vn = sv[q];
         gu[q] = un;
         gv[q] = vn;
         gp[q] = pf[q];
         gobs[2 * q] = un;
         gobs[2 * q + 1] = vn;
-        const double du = D::sub(un, uref[2 * q]), dv = D::sub(vn, uref[2 * q + 1]);
+        const double du = D::sub(static_cast<double>(un), uref[2 * q]), dv = D::sub(static_cast<double>(vn), uref[2 * q + 1]);
         ss += du * du;
         ss += dv * dv;
     }
@@ -278,7 +302,7 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
         const double nrm = sqrt(tot);
         // -1/2 * norm**2 / shape[1] / shape[2] - gamma/2 * norm(a - a_ref[t])**2
         double r1 = D::div(D::div(D::mul(-0.5, D::mul(nrm, nrm)), static_cast<double>(nx)), static_cast<double>(ny));   // / shape[1] / shape[2]
-        const double da = fabs(D::sub(action, a.buf.action_ref[t1]));
+        const double da = fabs(D::sub(action_d, a.buf.action_ref[t1]));
         const double r2 = D::mul(D::div(cfg.gamma, 2.0), D::mul(da, da));
         a.buf.reward[env] = D::sub(r1, r2);
         a.buf.time_index[env] = t1;
@@ -287,20 +311,21 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
         if (a.buf.valid) a.buf.valid[env] = 1;
     }
     if (a.ar_u != nullptr && t1 >= cfg.nt - 1) {          // same-step auto-reset (block-uniform condition)
-        if (a.buf.final_obs != nullptr) {                 // terminal observation U[nt-1] for the caller
-            double* fobs = a.buf.final_obs + env * npt * 2;
+        if (fobs_all != nullptr) {                        // terminal observation U[nt-1] for the caller
+            T* fobs = fobs_all + env * npt * 2;
             for (int q = tid; q < npt; q += nth) { fobs[2 * q] = su[q]; fobs[2 * q + 1] = sv[q]; }
         }
         __syncthreads();                                  // the step's own field / observation stores come first
-        ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
+        ns_reset_env<T>(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, const double* __restrict__ iu, const double* __restrict__ iv,
                                                               const double* __restrict__ ip, int64_t stride, const uint8_t* __restrict__ mask) {
     const int64_t env = blockIdx.x;
     if (mask != nullptr && mask[env] == 0) return;
-    ns_reset_env(a, iu, iv, ip, stride, env, threadIdx.x, blockDim.x, false);
+    ns_reset_env<T>(a, iu, iv, ip, stride, env, threadIdx.x, blockDim.x, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -323,12 +348,14 @@ __global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, co
 // shared memory, so an arbitrary initial pressure field is handled exactly.
 // All 32 lanes run the whole kernel in lock step whatever their env's state: a segment whose env does not exist or
 // is past its last step computes on zeros and stores nothing, so every shuffle / barrier names the full warp.
-template <int N, int BR, int BC, int RG, int CG, int WPB, int LPE>
+template <int N, int BR, int BC, int RG, int CG, int WPB, int LPE, typename T>
 __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) {
     static_assert(LPE == 32 || LPE == 16, "32 or 16 lanes per env");
     static_assert(RG * CG <= LPE && RG * BR >= N && CG * BC >= N, "bad tiling");
     constexpr int NX = N + 2, NPT = NX * NX, EPW = 32 / LPE;
-    extern __shared__ double smem[];
+    using S = Strict<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
     const pdecg_ns_cfg& cfg = a.cfg;
     const int lane = threadIdx.x & (LPE - 1), wib = threadIdx.x >> 5;
     const int seg = (threadIdx.x & 31) / LPE;
@@ -337,10 +364,10 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
     if (env0 >= a.buf.n_envs) return;                          // warp-uniform
     const int64_t env = env0 + seg;
     const bool exists = env < a.buf.n_envs;
-    double* f0 = smem + static_cast<size_t>(wib * EPW + seg) * 4 * NPT;   // u   -> (dx*dy)*rhs
-    double* f1 = f0 + NPT;                                     // v   -> pressure
-    double* f2 = f1 + NPT;                                     // u*  -> u_next
-    double* f3 = f2 + NPT;                                     // v*  -> v_next
+    T* f0 = smem + static_cast<size_t>(wib * EPW + seg) * 4 * NPT;   // u   -> (dx*dy)*rhs
+    T* f1 = f0 + NPT;                                     // v   -> pressure
+    T* f2 = f1 + NPT;                                     // u*  -> u_next
+    T* f3 = f2 + NPT;                                     // v*  -> v_next
 
     const int t0 = exists ? a.buf.time_index[env] : 0;
     const bool stale = exists && (t0 + 1 >= cfg.nt || t0 + 1 >= cfg.n_uref || t0 + 1 >= cfg.n_action_ref);
@@ -354,54 +381,58 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
         }
         if (a.ar_u != nullptr) {
             if (a.buf.final_obs != nullptr) {        // terminal observation = the (unchanged) current U[t]
-                for (int q = lane; q < 2 * NPT; q += LPE) a.buf.final_obs[env * NPT * 2 + q] = a.buf.obs[env * NPT * 2 + q];
+                for (int q = lane; q < 2 * NPT; q += LPE)
+                    reinterpret_cast<T*>(a.buf.final_obs)[env * NPT * 2 + q] = reinterpret_cast<T*>(a.buf.obs)[env * NPT * 2 + q];
                 __syncwarp(segmask);
             }
-            ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, LPE, true);
+            ns_reset_env<T>(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, LPE, true);
         }
     }
     __syncwarp();
     if (!__any_sync(kFull, live)) return;                      // warp-uniform
-    const double two_dx = D::mul(2.0, cfg.dx), two_dy = D::mul(2.0, cfg.dy);
-    const double dxdy = D::mul(cfg.dx, cfg.dy);
-    const ConstDiv<double> by_2dx(two_dx), by_2dy(two_dy), by_dxdy(dxdy);
+    const T dx = static_cast<T>(cfg.dx), dy = static_cast<T>(cfg.dy), dt = static_cast<T>(cfg.dt);
+    const T nu = static_cast<T>(cfg.viscosity), rho = static_cast<T>(cfg.density);
+    const T two_dx = S::mul(T(2), dx), two_dy = S::mul(T(2), dy);
+    const T dxdy = S::mul(dx, dy);
+    const ConstDiv<T> by_2dx(two_dx), by_2dy(two_dy), by_dxdy(dxdy);
     const int64_t envc = live ? env : 0;                       // pointers of a non-live segment are never dereferenced
-    double* gu = a.buf.u + envc * NPT;
-    double* gv = a.buf.v + envc * NPT;
-    double* gp = a.buf.p + envc * NPT;
-    const double action = live ? a.buf.action[env] : 0.0;
+    T* gu = reinterpret_cast<T*>(a.buf.u) + envc * NPT;
+    T* gv = reinterpret_cast<T*>(a.buf.v) + envc * NPT;
+    T* gp = reinterpret_cast<T*>(a.buf.p) + envc * NPT;
+    const double action_d = live ? a.buf.action[env] : 0.0;
+    const T action = static_cast<T>(action_d);
 
-    for (int q = lane; q < NPT; q += LPE) { f0[q] = live ? gu[q] : 0.0; f1[q] = live ? gv[q] : 0.0; }
+    for (int q = lane; q < NPT; q += LPE) { f0[q] = live ? gu[q] : T(0); f1[q] = live ? gv[q] : T(0); }
     __syncwarp();
     auto interior = [](int q) { const int i = q / NX, j = q - i * NX; return i >= 1 && i <= N && j >= 1 && j <= N; };
-    auto cdx = [&](const double* f, int q) { return by_2dx(D::sub(f[q + 1], f[q - 1])); };
-    auto cdy = [&](const double* f, int q) { return by_2dy(D::sub(f[q + NX], f[q - NX])); };
-    auto lap = [&](const double* f, int q) {
-        double s = D::add(f[q - 1], f[q - NX]);
-        s = D::sub(s, D::mul(4.0, f[q]));
-        s = D::add(s, f[q + 1]);
-        s = D::add(s, f[q + NX]);
+    auto cdx = [&](const T* f, int q) { return by_2dx(S::sub(f[q + 1], f[q - 1])); };
+    auto cdy = [&](const T* f, int q) { return by_2dy(S::sub(f[q + NX], f[q - NX])); };
+    auto lap = [&](const T* f, int q) {
+        T s = S::add(f[q - 1], f[q - NX]);
+        s = S::sub(s, S::mul(T(4), f[q]));
+        s = S::add(s, f[q + 1]);
+        s = S::add(s, f[q + NX]);
         return by_dxdy(s);
     };
     // ---- predictor (:130-138) ----
     for (int q = lane; q < NPT; q += LPE) {
-        double us = f0[q], vs = f1[q];
+        T us = f0[q], vs = f1[q];
         if (interior(q)) {
-            const double u0 = us, v0 = vs;
-            double adv = D::sub(D::mul(-u0, cdx(f0, q)), D::mul(v0, cdy(f0, q)));
-            us = D::add(u0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap(f0, q)))));
-            adv = D::sub(D::mul(-u0, cdx(f1, q)), D::mul(v0, cdy(f1, q)));
-            vs = D::add(v0, D::mul(cfg.dt, D::add(adv, D::mul(cfg.viscosity, lap(f1, q)))));
+            const T u0 = us, v0 = vs;
+            T adv = S::sub(S::mul(-u0, cdx(f0, q)), S::mul(v0, cdy(f0, q)));
+            us = S::add(u0, S::mul(dt, S::add(adv, S::mul(nu, lap(f0, q)))));
+            adv = S::sub(S::mul(-u0, cdx(f1, q)), S::mul(v0, cdy(f1, q)));
+            vs = S::add(v0, S::mul(dt, S::add(adv, S::mul(nu, lap(f1, q)))));
         }
         f2[q] = us;
         f3[q] = vs;
     }
     __syncwarp();
     // apply_boundary (:68-91): sides in the reference's order, u before v
-    auto apply_bc = [&](double* fu, double* fv) {
+    auto apply_bc = [&](T* fu, T* fv) {
         for (int side = 0; side < 4; ++side) {
             for (int comp = 0; comp < 2; ++comp) {
-                double* f = comp == 0 ? fu : fv;
+                T* f = comp == 0 ? fu : fv;
                 const int cond = cfg.bc[side][comp];
                 for (int q = lane; q < NX; q += LPE) {
                     int dst, src;
@@ -410,7 +441,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
                     else if (side == PDECG_NS_LEFT) { dst = q * NX; src = q * NX + 1; }
                     else { dst = q * NX + NX - 1; src = q * NX + NX - 2; }
                     if (cond == PDECG_NS_NEUMANN) f[dst] = f[src];
-                    else if (cond == PDECG_NS_DIRICHLET) f[dst] = 0.0;
+                    else if (cond == PDECG_NS_DIRICHLET) f[dst] = T(0);
                     else f[dst] = action;
                 }
             }
@@ -419,10 +450,10 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
     };
     apply_bc(f2, f3);
     // ---- (dx*dy)*rhs into f0, warm-start pressure into f1 ----
-    const double rho_dt = D::div(cfg.density, cfg.dt);
+    const T rho_dt = S::div(rho, dt);
     for (int q = lane; q < NPT; q += LPE) {
-        f0[q] = interior(q) ? D::mul(dxdy, D::mul(rho_dt, D::add(cdx(f2, q), cdy(f3, q)))) : 0.0;
-        f1[q] = live ? gp[q] : 0.0;
+        f0[q] = interior(q) ? S::mul(dxdy, S::mul(rho_dt, S::add(cdx(f2, q), cdy(f3, q)))) : T(0);
+        f1[q] = live ? gp[q] : T(0);
     }
     __syncwarp();
 
@@ -430,7 +461,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
     const int rg = lane / CG, cg = lane - rg * CG;
     const int i0 = rg * BR, j0 = cg * BC;                    // interior coordinates of this lane's block
     if (cfg.n_pressure_iters >= 1) {
-        double p[BR][BC], b[BR][BC];
+        T p[BR][BC], b[BR][BC];
 #pragma unroll
         for (int rr = 0; rr < BR; ++rr)
 #pragma unroll
@@ -438,20 +469,20 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
                 const int i = i0 + rr, j = j0 + cc;
                 const bool ok = (lane < RG * CG) && i < N && j < N;
                 const int q = ok ? (i + 1) * NX + (j + 1) : NX + 1;
-                b[rr][cc] = ok ? f0[q] : 0.0;
+                b[rr][cc] = ok ? f0[q] : T(0);
                 // sweep 1: true neighbours (incl. stored boundary values) from shared memory
-                double acc = D::add(f1[q - 1], f1[q - NX]);
-                acc = D::add(acc, f1[q + 1]);
-                acc = D::add(acc, f1[q + NX]);
-                p[rr][cc] = ok ? D::mul(0.25, D::sub(acc, b[rr][cc])) : 0.0;
+                T acc = S::add(f1[q - 1], f1[q - NX]);
+                acc = S::add(acc, f1[q + 1]);
+                acc = S::add(acc, f1[q + NX]);
+                p[rr][cc] = ok ? S::mul(T(0.25), S::sub(acc, b[rr][cc])) : T(0);
             }
         constexpr int RLAST = (N - 1) / BR, RSLOT = (N - 1) % BR;     // block / slot holding interior row N-1
         constexpr int CLAST = (N - 1) / BC, CSLOT = (N - 1) % BC;
         const bool top = rg == 0, bottom = rg == RLAST, leftmost = cg == 0, rightmost = cg == CLAST;
         // Halo values of a block (the neighbouring blocks' edge rows / columns); the clamp at the domain edge is a select
         // on the halo: the neighbour beyond the edge is the point itself.
-        struct Halo { double up[BC], dn[BC], lf[BR], rt[BR]; };
-        auto exchange_rows = [&](const double (&src)[BR][BC], Halo& h) {
+        struct Halo { T up[BC], dn[BC], lf[BR], rt[BR]; };
+        auto exchange_rows = [&](const T (&src)[BR][BC], Halo& h) {
 #pragma unroll
             for (int cc = 0; cc < BC; ++cc) {
                 h.up[cc] = __shfl_up_sync(kFull, src[BR - 1][cc], CG, LPE);
@@ -460,7 +491,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
                 if constexpr (RSLOT == BR - 1) h.dn[cc] = bottom ? src[BR - 1][cc] : h.dn[cc];
             }
         };
-        auto exchange_cols = [&](const double (&src)[BR][BC], Halo& h) {
+        auto exchange_cols = [&](const T (&src)[BR][BC], Halo& h) {
 #pragma unroll
             for (int rr = 0; rr < BR; ++rr) {
                 h.lf[rr] = __shfl_up_sync(kFull, src[rr][BC - 1], 1, LPE);
@@ -469,24 +500,24 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
                 if constexpr (CSLOT == BC - 1) h.rt[rr] = rightmost ? src[rr][BC - 1] : h.rt[rr];
             }
         };
-        auto exchange = [&](const double (&src)[BR][BC], Halo& h) { exchange_rows(src, h); exchange_cols(src, h); };
-        auto point = [&](const double (&src)[BR][BC], const Halo& h, int rr, int cc) {
-            const double self = src[rr][cc];
-            const double up = (rr > 0) ? src[rr > 0 ? rr - 1 : 0][cc] : h.up[cc];
-            double dn = (rr < BR - 1) ? src[rr < BR - 1 ? rr + 1 : 0][cc] : h.dn[cc];
+        auto exchange = [&](const T (&src)[BR][BC], Halo& h) { exchange_rows(src, h); exchange_cols(src, h); };
+        auto point = [&](const T (&src)[BR][BC], const Halo& h, int rr, int cc) {
+            const T self = src[rr][cc];
+            const T up = (rr > 0) ? src[rr > 0 ? rr - 1 : 0][cc] : h.up[cc];
+            T dn = (rr < BR - 1) ? src[rr < BR - 1 ? rr + 1 : 0][cc] : h.dn[cc];
             if constexpr (RSLOT < BR - 1) { if (rr == RSLOT) dn = bottom ? self : dn; }
-            const double lf = (cc > 0) ? src[rr][cc > 0 ? cc - 1 : 0] : h.lf[rr];
-            double rt = (cc < BC - 1) ? src[rr][cc < BC - 1 ? cc + 1 : 0] : h.rt[rr];
+            const T lf = (cc > 0) ? src[rr][cc > 0 ? cc - 1 : 0] : h.lf[rr];
+            T rt = (cc < BC - 1) ? src[rr][cc < BC - 1 ? cc + 1 : 0] : h.rt[rr];
             if constexpr (CSLOT < BC - 1) { if (cc == CSLOT) rt = rightmost ? self : rt; }
-            double acc = D::add(lf, up);             // ((left + up) + right) + down
-            acc = D::add(acc, rt);
-            acc = D::add(acc, dn);
-            return D::mul(0.25, D::sub(acc, b[rr][cc]));
+            T acc = S::add(lf, up);             // ((left + up) + right) + down
+            acc = S::add(acc, rt);
+            acc = S::add(acc, dn);
+            return S::mul(T(0.25), S::sub(acc, b[rr][cc]));
         };
         // One sweep `src` (with its halo `hs`) -> `dst` (and its halo `hd`).  The block's EDGE points come first and
         // their shuffles are issued at once; the interior points, which need no halo, are computed while the shuffles
         // are in flight: the sweep-to-sweep recurrence (edge values -> shuffle -> edge values) overlaps with them.
-        auto sweep = [&](const double (&src)[BR][BC], const Halo& hs, double (&dst)[BR][BC], Halo& hd) {
+        auto sweep = [&](const T (&src)[BR][BC], const Halo& hs, T (&dst)[BR][BC], Halo& hd) {
 #pragma unroll
             for (int rr = 0; rr < BR; ++rr)
 #pragma unroll
@@ -498,7 +529,7 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
 #pragma unroll
                 for (int cc = 1; cc < BC - 1; ++cc) dst[rr][cc] = point(src, hs, rr, cc);
         };
-        double n[BR][BC];
+        T n[BR][BC];
         Halo hp, hn;
         if (cfg.n_pressure_iters > 1) exchange(p, hp);
         int it = 1;
@@ -533,11 +564,11 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
     }
 
     // ---- corrector (:143-146) ----
-    const double dt_rho = D::div(cfg.dt, cfg.density);
+    const T dt_rho = S::div(dt, rho);
     for (int q = lane; q < NPT; q += LPE) {
         if (interior(q)) {
-            f2[q] = D::sub(f2[q], D::mul(dt_rho, cdx(f1, q)));
-            f3[q] = D::sub(f3[q], D::mul(dt_rho, cdy(f1, q)));
+            f2[q] = S::sub(f2[q], S::mul(dt_rho, cdx(f1, q)));
+            f3[q] = S::sub(f3[q], S::mul(dt_rho, cdy(f1, q)));
         }
     }
     __syncwarp();
@@ -546,28 +577,32 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
     // ---- store, observation U[t], reward ----
     const int t1 = t0 + 1;
     const double* uref = a.buf.u_ref + static_cast<int64_t>(live ? t1 : 0) * NPT * 2;
-    double* gobs = a.buf.obs + envc * NPT * 2;
+    T* gobs = reinterpret_cast<T*>(a.buf.obs) + envc * NPT * 2;
+    using V2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
     double ss = 0.0;
     if (live) {
         for (int q = lane; q < NPT; q += LPE) {
-            const double un = f2[q], vn = f3[q];
+            const T un = f2[q], vn = f3[q];
             gu[q] = un;
             gv[q] = vn;
             gp[q] = f1[q];
-            const double du = D::sub(un, uref[2 * q]), dv = D::sub(vn, uref[2 * q + 1]);
+            const double du = D::sub(static_cast<double>(un), uref[2 * q]), dv = D::sub(static_cast<double>(vn), uref[2 * q + 1]);
             ss += du * du;
             ss += dv * dv;
         }
-        // interleaved (u, v) observation: coalesced 16-byte pairs
+        // interleaved (u, v) observation: coalesced pairs
         for (int q = lane; q < NPT; q += LPE) {
-            reinterpret_cast<double2*>(gobs)[q] = make_double2(f2[q], f3[q]);
+            V2 pr;
+            pr.x = f2[q];
+            pr.y = f3[q];
+            reinterpret_cast<V2*>(gobs)[q] = pr;
         }
     }
     ss = seg_sum<LPE>(ss);                                     // full-warp mask: every lane is here
     if (live && lane == 0) {
         const double nrm = sqrt(ss);
         double r1 = D::div(D::div(D::mul(-0.5, D::mul(nrm, nrm)), static_cast<double>(NX)), static_cast<double>(NX));
-        const double da = fabs(D::sub(action, a.buf.action_ref[t1]));
+        const double da = fabs(D::sub(action_d, a.buf.action_ref[t1]));
         const double r2 = D::mul(D::div(cfg.gamma, 2.0), D::mul(da, da));
         a.buf.reward[env] = D::sub(r1, r2);
         a.buf.time_index[env] = t1;
@@ -577,11 +612,16 @@ __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) 
     }
     if (live && a.ar_u != nullptr && t1 >= cfg.nt - 1) {  // same-step auto-reset (segment-uniform condition)
         if (a.buf.final_obs != nullptr) {                 // terminal observation U[nt-1] for the caller
-            double2* fobs = reinterpret_cast<double2*>(a.buf.final_obs + env * NPT * 2);
-            for (int q = lane; q < NPT; q += LPE) fobs[q] = make_double2(f2[q], f3[q]);
+            V2* fobs = reinterpret_cast<V2*>(reinterpret_cast<T*>(a.buf.final_obs) + env * NPT * 2);
+            for (int q = lane; q < NPT; q += LPE) {
+                V2 pr;
+                pr.x = f2[q];
+                pr.y = f3[q];
+                fobs[q] = pr;
+            }
         }
         __syncwarp(segmask);                              // the step's own field / observation stores come first
-        ns_reset_env(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, LPE, true);
+        ns_reset_env<T>(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, lane, LPE, true);
     }
 }
 
@@ -595,6 +635,9 @@ static int ns_validate_cfg(const pdecg_ns_cfg* cfg) {
     for (int s = 0; s < 4; ++s)
         for (int c = 0; c < 2; ++c)
             if (cfg->bc[s][c] < PDECG_NS_DIRICHLET || cfg->bc[s][c] > PDECG_NS_CONTROLLABLE) return fail(PDECG_ERR_INVALID, "bad boundary condition code");
+    if (cfg->precision < PDECG_PREC_REF || cfg->precision > PDECG_PREC_FP32) return fail(PDECG_ERR_INVALID, "bad precision %d", cfg->precision);
+    if (cfg->precision == PDECG_PREC_FP32 && (cfg->nx * cfg->ny > kNsMaxPoints || getenv("PDECG_NS_TILED") != nullptr))
+        return fail(PDECG_ERR_UNSUPPORTED, "the float32 mode covers the on-chip grids only (nx * ny <= %d)", kNsMaxPoints);
     return PDECG_OK;
 }
 
@@ -604,12 +647,15 @@ static bool ns_use_large(const pdecg_ns_cfg* cfg) {
     return cfg->nx * cfg->ny > kNsMaxPoints || getenv("PDECG_NS_TILED") != nullptr;
 }
 
-static size_t ns_smem_bytes(const pdecg_ns_cfg* cfg) { return static_cast<size_t>(7) * cfg->nx * cfg->ny * sizeof(double); }
+static bool ns_f32(const pdecg_ns_cfg* cfg) { return cfg->precision == PDECG_PREC_FP32; }
+static size_t ns_smem_bytes(const pdecg_ns_cfg* cfg) {
+    return static_cast<size_t>(7) * cfg->nx * cfg->ny * (ns_f32(cfg) ? sizeof(float) : sizeof(double));
+}
 
 // generic (CTA-per-env) kernel: pick the instantiation for this grid, opt in to its shared memory, launch
 template <int THREADS, int PT>
 static int ns_launch_generic_t(const NsArgs& a, int64_t n_envs, size_t smem, cudaStream_t st) {
-    auto kern = ns_step_kernel<THREADS, PT>;
+    void (*kern)(const NsArgs) = ns_f32(&a.cfg) ? ns_step_kernel<THREADS, PT, float> : ns_step_kernel<THREADS, PT, double>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     kern<<<static_cast<unsigned>(n_envs), THREADS, smem, st>>>(a);
@@ -637,7 +683,8 @@ extern "C" int pdecg_ns_reset(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* b
     if (!init_u || !init_v || !init_p || !buf->u || !buf->v || !buf->p || !buf->obs || !buf->time_index || !buf->reward || !buf->terminated || !buf->truncated)
         return fail(PDECG_ERR_INVALID, "null device buffer");
     NsArgs a{*cfg, *buf, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0};
-    ns_reset_kernel<<<static_cast<unsigned>(buf->n_envs), kNsThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init_u, init_v, init_p, init_env_stride, mask);
+    if (ns_f32(cfg)) ns_reset_kernel<float><<<static_cast<unsigned>(buf->n_envs), kNsThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init_u, init_v, init_p, init_env_stride, mask);
+    else ns_reset_kernel<double><<<static_cast<unsigned>(buf->n_envs), kNsThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, init_u, init_v, init_p, init_env_stride, mask);
     count_launch();
     return check_launch("ns_reset_kernel");
 }
@@ -663,10 +710,14 @@ static int ns_launch_step(const pdecg_ns_cfg* cfg, const pdecg_ns_buffers* buf, 
         const int64_t warps = (buf->n_envs + epw - 1) / epw;
         const bool small = (warps < 148 * 16 || getenv("PDECG_NS_WPB1")) && !getenv("PDECG_NS_WPB4");
         const int wpb = small ? 1 : kWarpsPerBlock;
-        const size_t smem_w = static_cast<size_t>(wpb) * epw * 4 * (kN + 2) * (kN + 2) * sizeof(double);
+        const bool f32 = ns_f32(cfg);
+        const size_t smem_w = static_cast<size_t>(wpb) * epw * 4 * (kN + 2) * (kN + 2) * (f32 ? sizeof(float) : sizeof(double));
         void (*kern)(const NsArgs);
-        if (lpe32) kern = small ? ns_step_warp_kernel<kN, 2, 7, 10, 3, 1, 32> : ns_step_warp_kernel<kN, 2, 7, 10, 3, kWarpsPerBlock, 32>;
-        else kern = small ? ns_step_warp_kernel<kN, 5, 5, 4, 4, 1, 16> : ns_step_warp_kernel<kN, 5, 5, 4, 4, kWarpsPerBlock, 16>;
+        if (f32) {
+            if (lpe32) kern = small ? ns_step_warp_kernel<kN, 2, 7, 10, 3, 1, 32, float> : ns_step_warp_kernel<kN, 2, 7, 10, 3, kWarpsPerBlock, 32, float>;
+            else kern = small ? ns_step_warp_kernel<kN, 5, 5, 4, 4, 1, 16, float> : ns_step_warp_kernel<kN, 5, 5, 4, 4, kWarpsPerBlock, 16, float>;
+        } else if (lpe32) kern = small ? ns_step_warp_kernel<kN, 2, 7, 10, 3, 1, 32, double> : ns_step_warp_kernel<kN, 2, 7, 10, 3, kWarpsPerBlock, 32, double>;
+        else kern = small ? ns_step_warp_kernel<kN, 5, 5, 4, 4, 1, 16, double> : ns_step_warp_kernel<kN, 5, 5, 4, 4, kWarpsPerBlock, 16, double>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_w));
         if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         const unsigned grid = static_cast<unsigned>((warps + wpb - 1) / wpb);
@@ -699,6 +750,7 @@ extern "C" int pdecg_ns_solve_pressure(const pdecg_ns_cfg* cfg, int64_t n_envs, 
     if (n_envs < 0) return fail(PDECG_ERR_INVALID, "n_envs < 0");
     if (n_envs == 0) return PDECG_OK;
     if (!u || !v || !p) return fail(PDECG_ERR_INVALID, "null device buffer");
+    if (ns_f32(cfg)) return fail(PDECG_ERR_UNSUPPORTED, "pdecg_ns_solve_pressure is float64 only");
     if (ns_use_large(cfg)) return ns_large_solve_pressure(cfg, n_envs, u, v, p, work, static_cast<cudaStream_t>(stream));
     NsArgs a{};
     a.cfg = *cfg;
@@ -724,7 +776,8 @@ extern "C" int pdecg_ns_step_host(const pdecg_ns_cfg* cfg, const pdecg_ns_buffer
     cudaError_t e = cudaMemcpyAsync(const_cast<double*>(buf->action), action_host, n * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
     if ((rc = ns_launch_step(cfg, buf, autoreset_u, autoreset_v, autoreset_p, autoreset_env_stride, stream)) != PDECG_OK) return rc;
-    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->obs, n * npt * 2 * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
+    const size_t esz = ns_f32(cfg) ? sizeof(float) : sizeof(double);
+    if (obs_host && (e = cudaMemcpyAsync(obs_host, buf->obs, n * npt * 2 * esz, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
     if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
     if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
     if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));

@@ -46,8 +46,13 @@ class NavierStokes2D(StateDictMixin):
                  *, T, dt, X, dx, Y, dy, action_dim: int = 1, reward_class=None, normalize: bool = False,
                  num_envs: int = 1, device="cuda", precision: str = "ref", copy_obs: bool = True, autoreset: bool = False,
                  final_obs: bool = False):
-        if precision not in ("ref", "fp64"):
-            raise ValueError("NavierStokes2D is float64 in the reference; precision must be 'ref' or 'fp64'")
+        if precision not in ("ref", "fp64", "fp32"):
+            raise ValueError("NavierStokes2D: precision must be 'ref' / 'fp64' (float64 as the reference, bit-identical fields) "
+                             "or 'fp32' (opt-in fast mode: float32 fields and arithmetic)")
+        self.precision = precision
+        # 'fp32': float32 u / v / p / observation and float32 arithmetic in the same operation order; actions, U_ref,
+        # action_ref, the reward and the initial fields stay float64 (tests/test_gpu_navier_stokes.py states the tolerance)
+        self.state_dtype = torch.float32 if precision == "fp32" else torch.float64
         if not isinstance(reward_class, NSReward):
             raise TypeError("reward_class must be a pdecontrolgym_b200.NSReward (evaluated inside the kernel)")
         if action_dim != 1:
@@ -91,6 +96,7 @@ class NavierStokes2D(StateDictMixin):
                 cfg.bc[s][c] = _BC[cond]
         cfg.dt, cfg.dx, cfg.dy = float(dt), float(dx), float(dy)
         cfg.viscosity, cfg.density, cfg.gamma = float(viscosity), float(density), float(reward_class.gamma)
+        cfg.precision = _lib.PREC[precision]
         dev = self.device
         uref = np.ascontiguousarray(np.asarray(U_ref, dtype=np.float64))
         if uref.ndim != 4 or uref.shape[1:] != (self.nx, self.ny, 2):
@@ -103,10 +109,10 @@ class NavierStokes2D(StateDictMixin):
             self.U_ref = torch.from_numpy(uref).to(dev)
             self.action_ref = torch.from_numpy(aref).to(dev)
             shp = (N, self.ny, self.nx)
-            self.u = torch.zeros(shp, dtype=torch.float64, device=dev)
-            self.v = torch.zeros(shp, dtype=torch.float64, device=dev)
-            self.p = torch.zeros(shp, dtype=torch.float64, device=dev)
-            self._obs = torch.zeros(shp + (2,), dtype=torch.float64, device=dev)
+            self.u = torch.zeros(shp, dtype=self.state_dtype, device=dev)
+            self.v = torch.zeros(shp, dtype=self.state_dtype, device=dev)
+            self.p = torch.zeros(shp, dtype=self.state_dtype, device=dev)
+            self._obs = torch.zeros(shp + (2,), dtype=self.state_dtype, device=dev)
             self.time_index = torch.zeros((N,), dtype=torch.int32, device=dev)
             self._reward = torch.zeros((N,), dtype=torch.float64, device=dev)
             self._terminated = torch.zeros((N,), dtype=torch.uint8, device=dev)
@@ -219,7 +225,8 @@ class NavierStokes2D(StateDictMixin):
     def step_host(self, action_host, obs_host=None, reward_host=None, terminated_host=None, truncated_host=None, valid_host=None):
         """End-to-end step over HOST buffers (pdecg_ns_step_host): H2D(actions) -> kernel -> D2H(U[t], reward, flags) on
         the current stream, synchronised on return.  CPU tensors (pin them): `action_host` float64 [num_envs];
-        `obs_host` float64 [num_envs, ny, nx, 2]; `reward_host` float64 [num_envs]; flags / valid uint8 [num_envs]."""
+        `obs_host` [num_envs, ny, nx, 2] in the state dtype (float64; float32 with precision="fp32"); `reward_host` float64
+        [num_envs]; flags / valid uint8 [num_envs]."""
         if not self._reset_done:
             raise RuntimeError("call reset() before step_host()")
         N = self.num_envs
@@ -234,7 +241,7 @@ class NavierStokes2D(StateDictMixin):
         with torch.cuda.device(self.device):
             _lib.check(self._L.pdecg_ns_step_host(
                 C.byref(self._cfg), C.byref(buf), a_ptr,
-                _lib.host_ptr(obs_host, torch.float64, N * self.nx * self.ny * 2, "obs_host"),
+                _lib.host_ptr(obs_host, self.state_dtype, N * self.nx * self.ny * 2, "obs_host"),
                 _lib.host_ptr(reward_host, torch.float64, N, "reward_host"),
                 _lib.host_ptr(terminated_host, torch.uint8, N, "terminated_host"),
                 _lib.host_ptr(truncated_host, torch.uint8, N, "truncated_host"),
@@ -244,7 +251,9 @@ class NavierStokes2D(StateDictMixin):
         return obs_host, reward_host, terminated_host, truncated_host, {}
 
     def solve_pressure(self, u, v, p_prev):
-        """Batched `solve_pressure` (navier_stokes2D.py:94-116) for external callers; returns the new p."""
+        """Batched `solve_pressure` (navier_stokes2D.py:94-116) for external callers; returns the new p (float64 only)."""
+        if self.precision == "fp32":
+            raise NotImplementedError("solve_pressure is float64 only; build the env with precision='ref'")
         u, v = self._field(u, "u"), self._field(v, "v")
         p = self._field(p_prev, "p_prev").clone()
         wbytes = int(self._L.pdecg_ns_workspace_bytes(C.byref(self._cfg), u.shape[0]))

@@ -145,15 +145,15 @@ def bench_bt():
 def bench_ns():
     # ---- NavierStokes2D x1,024 (config 4) ----
     bc = {"upper": ["Controllable", "Dirchilet"], "lower": ["Dirchilet", "Dirchilet"], "left": ["Dirchilet", "Dirchilet"], "right": ["Dirchilet", "Dirchilet"]}
-    for N in ([1024] if QUICK else [1024, 8192]):
+    for N, prec in ([(1024, "ref")] if QUICK else [(1024, "ref"), (8192, "ref"), (1024, "fp32"), (8192, "fp32")]):
         uref = np.zeros((200, 21, 21, 2))
         env = pcg.make("PDEControlGym-NavierStokes2D", num_envs=N, device=dev, boundary_condition=bc, U_ref=uref, action_ref=2.0 * np.ones(1000),
-                       reward_class=pcg.NSReward(0.1), action_dim=1, T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05, copy_obs=False)
+                       reward_class=pcg.NSReward(0.1), action_dim=1, T=0.2, dt=1e-3, X=1, dx=0.05, Y=1, dy=0.05, copy_obs=False, precision=prec)
         c = torch.empty(3, N, 1, 1, dtype=torch.float64, device=dev).uniform_(-5, 5) * torch.ones(1, 21, 21, dtype=torch.float64, device=dev)
         env.reset(options={"init": (c[0], c[1], c[2])})
         acts = torch.empty(32, N, dtype=torch.float64, device=dev).uniform_(2, 4)
         ms = timed(lambda i: env.step(acts[i % 32]), 20, warmup=3)
-        report(f"NavierStokes2D 21x21, 2000 Jacobi sweeps x{N}", N, ms, 361 * 2000)
+        report(f"NavierStokes2D 21x21, 2000 Jacobi sweeps x{N}" + (" (opt-in float32 mode)" if prec == "fp32" else ""), N, ms, 361 * 2000)
         del env
 
 

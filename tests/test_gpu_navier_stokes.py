@@ -17,7 +17,7 @@ BC_MIX = {"upper": ["Controllable", "Neumann"], "lower": ["Neumann", "Dirchilet"
           "left": ["Dirchilet", "Controllable"], "right": ["Neumann", "Neumann"]}
 
 
-def make_pair(cuda_device, B, bc, iters, n=21, T=0.2, uref=None, gamma=0.1):
+def make_pair(cuda_device, B, bc, iters, n=21, T=0.2, uref=None, gamma=0.1, **env_kw):
     import pdecontrolgym_b200 as pcg
     h = 1.0 / (n - 1)
     kw = dict(T=T, dt=1e-3 * (h / 0.05) ** 2, X=1, dx=h, Y=1, dy=h)
@@ -26,7 +26,7 @@ def make_pair(cuda_device, B, bc, iters, n=21, T=0.2, uref=None, gamma=0.1):
         uref = np.random.default_rng(11).uniform(-1, 1, (nt + 1, n, n, 2))
     aref = 2.0 * np.ones(1000)
     env = pcg.make("PDEControlGym-NavierStokes2D", num_envs=B, device=cuda_device, boundary_condition=bc, U_ref=uref,
-                   action_ref=aref, maximum_pressure_iteration=iters, reward_class=pcg.NSReward(gamma), action_dim=1, **kw)
+                   action_ref=aref, maximum_pressure_iteration=iters, reward_class=pcg.NSReward(gamma), action_dim=1, **kw, **env_kw)
     orc = O.NavierStokesOracle(B, boundary_condition=bc, U_ref=uref, action_ref=aref, maximum_pressure_iteration=iters,
                                gamma=gamma, **kw)
     return env, orc, nt
@@ -224,3 +224,55 @@ def test_warp_kernel_mappings_odd_batches_and_stale_partners(cuda_device, monkey
                 assert np.array_equal(og[late], o_l[late]) and np.array_equal(env.p.cpu().numpy()[late], orc_late.p[late]), f"iters {iters} step {k} (late)"
                 np.testing.assert_allclose(r_g.cpu().numpy()[late], r_l[late], rtol=1e-12)
                 assert valid[late].all() and np.array_equal(te_g.cpu().numpy()[late], te_l[late])
+
+
+@pytest.mark.parametrize("n,iters,mapping", [(21, 2000, "two_envs_per_warp"), (21, 300, "one_env_per_warp"), (33, 400, "cta"), (64, 120, "cta")])
+def test_fp32_fast_mode_tolerance(cuda_device, monkeypatch, n, iters, mapping):
+    """precision="fp32" (opt-in): float32 fields / observation / arithmetic in the reference's operation order; actions,
+    U_ref, the reward and the initial fields stay float64.  Stated tolerance against the float64 oracle over a whole
+    episode from a smooth initial state with the reference's boundary set: fields <= 2e-4 of the field scale per step
+    (Jacobi is a contraction: rounding errors of earlier sweeps are damped, not accumulated), pressure <= 2e-3 of its
+    scale, reward <= 1e-4 relative; termination flags identical.  The float32 state is returned as float32."""
+    import torch
+    if mapping == "one_env_per_warp":
+        monkeypatch.setenv("PDECG_NS_LPE32", "1")
+    B = 3
+    T = 0.03 * (20 / (n - 1)) ** 2
+    env, orc, nt = make_pair(cuda_device, B, BC_REF, iters, n=n, T=T, precision="fp32")
+    xs = np.linspace(0, 1, n)
+    X, Y = np.meshgrid(xs, xs)
+    u0 = np.stack([0.3 * (b + 1) * np.sin(np.pi * X) * np.cos(np.pi * Y) for b in range(B)])
+    v0 = np.stack([-0.2 * (b + 1) * np.cos(np.pi * X) * np.sin(np.pi * Y) for b in range(B)])
+    p0 = np.zeros_like(u0)
+    o_g, _ = env.reset(options={"init": (u0, v0, p0)})
+    o_r = orc.reset(u0, v0, p0)
+    assert o_g.dtype == torch.float32 and env.u.dtype == torch.float32 and env.p.dtype == torch.float32
+    assert np.array_equal(o_g.cpu().numpy(), o_r.astype(np.float32))
+    rng = np.random.default_rng(3)
+    steps = 0
+    while True:
+        a = rng.uniform(1, 3, B)
+        o_r, r_r, te_r, tr_r = orc.step(a)
+        o_g, r_g, te_g, tr_g, info = env.step(torch.from_numpy(a))
+        steps += 1
+        scale = np.abs(o_r).max()
+        assert np.abs(o_g.cpu().numpy() - o_r).max() <= 2e-4 * scale, f"step {steps}: fields off by {np.abs(o_g.cpu().numpy() - o_r).max() / scale:.2e} of scale"
+        assert np.abs(env.p.cpu().numpy() - orc.p).max() <= 2e-3 * max(np.abs(orc.p).max(), 1e-12), f"step {steps}: pressure"
+        np.testing.assert_allclose(r_g.cpu().numpy(), r_r, rtol=1e-4)
+        assert r_g.dtype == torch.float64
+        assert np.array_equal(te_g.cpu().numpy(), te_r) and not tr_g.any()
+        if te_r.all():
+            break
+    assert steps == nt - 1
+
+
+def test_fp32_rejects_what_it_does_not_cover(cuda_device):
+    import pdecontrolgym_b200 as pcg
+    env, _, _ = make_pair(cuda_device, 1, BC_REF, 5, precision="fp32")
+    z = np.zeros((21, 21))
+    env.reset(options={"init": (z, z, z)})
+    with pytest.raises(NotImplementedError):
+        env.solve_pressure(z[None], z[None], z[None])
+    with pytest.raises(Exception, match="on-chip"):
+        e2, _, _ = make_pair(cuda_device, 1, BC_REF, 5, n=81, T=0.002, precision="fp32")
+        e2.reset(options={"init": (np.zeros((81, 81)),) * 3})
