@@ -1,5 +1,5 @@
 """NavierStokes2D as a batched environment (environments2d/navier_stokes2D.py:9-194 and
-base_env_2d.py:24-63 of the reference).  float64 throughout, arrays indexed [env, row(y), col(x)].
+base_env_2d.py:24-63 of the reference).  float64 like the reference (or the opt-in float32 mode, precision='fp32'), arrays indexed [env, row(y), col(x)].
 
 One scalar action per env drives every "Controllable" boundary (the reference's `action_dim=1` use).
 """

@@ -1,5 +1,5 @@
 """TrafficPDE1D (Aw-Rascle-Zhang traffic model) as a batched environment
-(traffic_arz_env.py:23-280 of the reference).  float64 throughout, like the reference.
+(traffic_arz_env.py:23-280 of the reference).  float64 like the reference (or the opt-in float32 mode, precision='fp32').
 
 The reference's time bookkeeping is kept as is: `time_index` is a float time that
 advances by dt per *step*, the PDE integrates only while it is < T, `terminated` fires when it reaches
