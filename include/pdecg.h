@@ -242,6 +242,8 @@ typedef struct {
                                the day that ended the episode) of the envs that restart; other rows are left alone  */
     const uint8_t* mask;    /* optional, PDECG_BT_WRAP_RESET only: [n_envs], run the wrapper reset (Growth stage, consecutive
                                <- 0) only for envs whose byte is non-zero -- TherapyWrapper.reset of a subset of a batch */
+    int32_t* stage_out;     /* optional [n_envs]: each env's stage after the launch (after the fused restart, if any) -- a
+                               private copy for the caller's info dict, so that no copy kernel follows the step         */
 } pdecg_bt_buffers;
 
 /* BrainTumor1D.reset (:347-384): u <- init ([n_envs or 1, nx] float64), stage <- Growth, counters <- 0;

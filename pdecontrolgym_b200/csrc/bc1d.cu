@@ -172,7 +172,8 @@ namespace {
 constexpr int kPipeStreams = 4;
 struct HostPipe {
     cudaStream_t s[kPipeStreams] = {};
-    cudaEvent_t start = nullptr, done[kPipeStreams] = {};
+    cudaStream_t small = nullptr;                    // reward / flag copies: one transfer each for the whole batch
+    cudaEvent_t start = nullptr, done[kPipeStreams] = {}, kernels[kPipeStreams] = {}, small_done = nullptr;
     bool ready = false;
 };
 constexpr int kMaxDevices = 64;
@@ -188,7 +189,10 @@ int ensure_pipe(HostPipe** out) {
         for (int i = 0; i < kPipeStreams; ++i) {
             if ((e = cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
             if ((e = cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+            if ((e = cudaEventCreateWithFlags(&p.kernels[i], cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
         }
+        if ((e = cudaStreamCreateWithFlags(&p.small, cudaStreamNonBlocking)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        if ((e = cudaEventCreateWithFlags(&p.small_done, cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
         if ((e = cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
         p.ready = true;
     }
@@ -224,13 +228,20 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
     int nchunk = static_cast<int>(n / 4096);
     nchunk = nchunk < 1 ? 1 : (nchunk > max_chunks ? max_chunks : nchunk);
     const int64_t per = ((n + nchunk - 1) / nchunk + 3) / 4 * 4;
-    cudaError_t e = cudaEventRecord(g_pipe.start, user);      // order after whatever the caller queued
-    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+    // a short first chunk (a quarter of the others) gets the device->host queue going early: nothing can be copied out
+    // before the first kernel has finished
+    const int64_t first = (nchunk > 1) ? (per / 4 + 3) / 4 * 4 : per;
+    // all actions in ONE transfer on the caller's stream (ordered after whatever the caller queued); the chunks fan out behind it
+    cudaError_t e = cudaMemcpyAsync(const_cast<void*>(buf->action), action_host, n * asz, cudaMemcpyHostToDevice, user);
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
+    if ((e = cudaEventRecord(g_pipe.start, user)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
     for (int i = 0; i < kPipeStreams; ++i) cudaStreamWaitEvent(g_pipe.s[i], g_pipe.start, 0);
     MapEnvsScope map_scope(n);                                // every chunk uses the lane mapping of the whole batch
     auto off = [](const void* p, size_t bytes) { return p ? static_cast<const char*>(p) + bytes : nullptr; };
-    for (int c = 0; c * per < n; ++c) {
-        const int64_t lo = c * per, cnt = (lo + per <= n) ? per : n - lo;
+    int c = 0;
+    for (int64_t lo = 0; lo < n; ++c) {
+        const int64_t want = (c == 0) ? first : per, cnt = (lo + want <= n) ? want : n - lo;
+        const bool last_on_stream = lo + cnt + (kPipeStreams - 1) * per >= n;      // no later chunk lands on this stream
         cudaStream_t st = g_pipe.s[c % kPipeStreams];
         pdecg_bc1d_buffers b = *buf;
         b.n_envs = cnt;
@@ -244,8 +255,6 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
         b.time_index = buf->time_index + lo;
         b.carry = buf->carry + lo * a.carry_len;
         b.obs_copy = via_copy ? const_cast<char*>(off(buf->obs_copy, lo * obs_row)) : nullptr;
-        if ((e = cudaMemcpyAsync(const_cast<void*>(b.action), off(action_host, lo * asz), cnt * asz, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-            return fail(PDECG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
         if (autoreset) {
             pdecg_bc1d_autoreset ar = *autoreset;
             const size_t isz = ar.init_dtype == PDECG_F64 ? 8 : 4;
@@ -258,14 +267,25 @@ extern "C" int pdecg_bc1d_step_host(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_
             rc = pdecg_bc1d_step(cfg, &b, st);
         }
         if (rc != PDECG_OK) return rc;
+        // the stream's last kernel: from here on only this chunk's observation copy follows on it
+        if (last_on_stream) cudaEventRecord(g_pipe.kernels[c % kPipeStreams], st);
         if (obs_host) {
             const void* src = via_copy ? static_cast<const void*>(b.obs_copy) : (full ? static_cast<const void*>(b.u) : static_cast<const void*>(b.obs));
             if ((e = cudaMemcpyAsync(static_cast<char*>(obs_host) + lo * obs_row, src, cnt * obs_row, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
                 return fail(PDECG_ERR_CUDA, "D2H obs: %s", cudaGetErrorString(e));
         }
-        if (reward_host && (e = cudaMemcpyAsync(reward_host + lo, b.reward, cnt * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
-        if (terminated_host && (e = cudaMemcpyAsync(terminated_host + lo, b.terminated, cnt, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
-        if (truncated_host && (e = cudaMemcpyAsync(truncated_host + lo, b.truncated, cnt, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
+        lo += cnt;
+    }
+    // reward / flags: one transfer each for the whole batch, once every chunk's kernel has run -- on their own stream, so
+    // they overlap the last observation copies instead of fragmenting the D2H queue chunk by chunk
+    const int used = c < kPipeStreams ? c : kPipeStreams;
+    if (reward_host || terminated_host || truncated_host) {
+        for (int i = 0; i < used; ++i) cudaStreamWaitEvent(g_pipe.small, g_pipe.kernels[i], 0);
+        if (reward_host && (e = cudaMemcpyAsync(reward_host, buf->reward, n * 8, cudaMemcpyDeviceToHost, g_pipe.small)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H reward: %s", cudaGetErrorString(e));
+        if (terminated_host && (e = cudaMemcpyAsync(terminated_host, buf->terminated, n, cudaMemcpyDeviceToHost, g_pipe.small)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H terminated: %s", cudaGetErrorString(e));
+        if (truncated_host && (e = cudaMemcpyAsync(truncated_host, buf->truncated, n, cudaMemcpyDeviceToHost, g_pipe.small)) != cudaSuccess) return fail(PDECG_ERR_CUDA, "D2H truncated: %s", cudaGetErrorString(e));
+        cudaEventRecord(g_pipe.small_done, g_pipe.small);
+        cudaStreamWaitEvent(user, g_pipe.small_done, 0);
     }
     for (int i = 0; i < kPipeStreams; ++i) {                   // the caller's stream continues after every pipe
         cudaEventRecord(g_pipe.done[i], g_pipe.s[i]);

@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(kThreads, K > 8 ? 1 : (MULTI ? PDECG_BT_MINBLO
         a.buf.terminated[env] = term ? 1 : 0;
         a.buf.truncated[env] = trunc ? 1 : 0;
         if (a.buf.valid) a.buf.valid[env] = valid ? 1 : 0;
+        if (a.buf.stage_out) a.buf.stage_out[env] = (!MULTI && a.ar_init != nullptr && (term || trunc)) ? PDECG_BT_GROWTH : e.stage;
     }
     if constexpr (!MULTI) {
         if (a.ar_init != nullptr && (term || trunc)) {

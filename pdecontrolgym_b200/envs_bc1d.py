@@ -308,14 +308,14 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
     def _reset_kernel(self, mask_t):
         if self._random_ic is not None:
             r = self._random_ic
-            with torch.cuda.device(self.device):
+            with _lib.device_guard(self.device):
                 _lib.check(self._L.pdecg_bc1d_reset_random(
                     C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
                     _lib.F64 if self._ic.dtype == torch.float64 else _lib.F32, r.lo, r.hi,
                     self._seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset, self._episode.data_ptr(),
                     None if mask_t is None else mask_t.data_ptr(), self._stream()))
             return
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_bc1d_reset(
                 C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
                 _lib.F64 if self._ic.dtype == torch.float64 else _lib.F32, self._ic_stride,
@@ -380,7 +380,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         self._buf.nonfinite = flags[2].data_ptr() if self.report_nonfinite else None
         ke = self._kernel_events          # optional (start, stop) CUDA events bracketing only the step kernel
         try:
-            with torch.cuda.device(self.device):
+            with _lib.device_guard(self.device):
                 if ke is not None:
                     ke[0].record()
                 if self.autoreset:          # same-step auto-reset inside the step launch: finished envs restart from their IC
@@ -444,7 +444,7 @@ class _BoundaryControlVecEnv(PDEVecEnv1D):
         return obs_host, reward_host, terminated_host, truncated_host, {}
 
     def _step_host_call(self, a, obs_ptr, ptr, reward_host, terminated_host, truncated_host):
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_bc1d_step_host(
                 C.byref(self._cfg), C.byref(self._buf), a.data_ptr(),
                 obs_ptr,

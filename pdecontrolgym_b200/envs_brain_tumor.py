@@ -127,10 +127,13 @@ class BrainTumor1D(StateDictMixin):
         buf.obs = (None if obs_out is None else obs_out.data_ptr()) if mode == RAW_STEP else self._obs.data_ptr()
         outs = tuple(torch.empty_like(t) for t in (self._reward, self._terminated, self._truncated, self._valid))
         buf.reward, buf.terminated, buf.truncated, buf.valid = (t.data_ptr() for t in outs)
+        # info["stage"] as a private copy: written by the launch itself instead of a clone kernel after it
+        self._stage_out = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device) if self.copy_obs else None
+        buf.stage_out = None if self._stage_out is None else self._stage_out.data_ptr()
         buf.final_obs = self._final_obs.data_ptr() if (autoreset and self._final_obs is not None) else None
         buf.mask = None if mask_t is None else mask_t.data_ptr()
         try:
-            with torch.cuda.device(self.device):
+            with _lib.device_guard(self.device):
                 if autoreset:
                     _lib.check(self._L.pdecg_bt_step_autoreset(C.byref(self._cfg), C.byref(buf), self._ic.data_ptr(),
                                                                0 if self._ic.shape[0] == 1 else self.nx, self._stream()))
@@ -139,11 +142,14 @@ class BrainTumor1D(StateDictMixin):
         finally:
             buf.reward, buf.terminated, buf.truncated, buf.valid = (
                 self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(), self._valid.data_ptr())
-            buf.final_obs = buf.mask = None
+            buf.final_obs = buf.mask = buf.stage_out = None
         return outs
 
     def _prep_action(self, action):
         if isinstance(action, torch.Tensor):
+            if (action.dtype == torch.float64 and action.dim() == 1 and action.shape[0] == self.num_envs
+                    and action.device == self.device and action.is_contiguous()):
+                return action                  # already in the kernel's layout: nothing to do
             a = action.to(self.device, torch.float64)
         else:
             a = torch.from_numpy(np.ascontiguousarray(np.asarray(action, dtype=np.float64))).to(self.device)
@@ -160,8 +166,9 @@ class BrainTumor1D(StateDictMixin):
     def _out_rest(self, outs):
         """(reward, terminated, truncated, info) from the fresh tensors a launch wrote."""
         reward, term_u8, trunc_u8, valid_u8 = outs
-        stage = self._ienv[:, I_STAGE]              # copy_obs=False: a live zero-copy view, like the observation
-        info = {"stage": stage.clone() if self.copy_obs else stage, "valid": valid_u8.view(torch.bool)}
+        # copy_obs=False: a live zero-copy view, like the observation; else the private copy the launch wrote
+        stage = self._stage_out if self.copy_obs else self._ienv[:, I_STAGE]
+        info = {"stage": stage, "valid": valid_u8.view(torch.bool)}
         if self.autoreset and self._final_obs is not None:
             info["final_obs"] = self._final_obs      # rows of the envs with terminated | truncated this step are fresh
         return (reward, term_u8.view(torch.bool), trunc_u8.view(torch.bool), info)
@@ -195,7 +202,7 @@ class BrainTumor1D(StateDictMixin):
             self._ic = t
         mask = options.get("mask")
         mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_bt_reset(C.byref(self._cfg), C.byref(self._buf), self._ic.data_ptr(),
                                               0 if self._ic.shape[0] == 1 else self.nx,
                                               None if mask_t is None else mask_t.data_ptr(), self._stream()))
@@ -226,7 +233,7 @@ class BrainTumor1D(StateDictMixin):
             self._act_dev = torch.empty((N,), dtype=torch.float64, device=self.device)
         buf = self._buf
         buf.action, buf.obs = self._act_dev.data_ptr(), None
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_bt_step_host(
                 C.byref(self._cfg), C.byref(buf), a_ptr,
                 _lib.host_ptr(obs_host, self.state_dtype, N * self.nx, "obs_host"),

@@ -172,7 +172,7 @@ class NavierStokes2D(StateDictMixin):
         self._init = (iu, iv, ip)
         mask = options.get("mask")
         mask_t = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_ns_reset(C.byref(self._cfg), C.byref(self._buf), iu.data_ptr(), iv.data_ptr(), ip.data_ptr(),
                                               self.nx * self.ny, None if mask_t is None else mask_t.data_ptr(), self._stream()))
         self._reset_done = True
@@ -205,7 +205,7 @@ class NavierStokes2D(StateDictMixin):
             fin = self._final_obs
         buf.final_obs = None if fin is None else fin.data_ptr()
         try:
-            with torch.cuda.device(self.device):
+            with _lib.device_guard(self.device):
                 if self.autoreset:       # same-step auto-reset to the last initial fields, inside the step launch
                     iu, iv, ip = self._init
                     _lib.check(self._L.pdecg_ns_step_autoreset(C.byref(self._cfg), C.byref(buf), iu.data_ptr(), iv.data_ptr(),
@@ -238,7 +238,7 @@ class NavierStokes2D(StateDictMixin):
         buf = self._buf
         buf.action = self._act_dev.data_ptr()
         iu, iv, ip = self._init if self.autoreset else (None, None, None)
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_ns_step_host(
                 C.byref(self._cfg), C.byref(buf), a_ptr,
                 _lib.host_ptr(obs_host, self.state_dtype, N * self.nx * self.ny * 2, "obs_host"),
@@ -258,7 +258,7 @@ class NavierStokes2D(StateDictMixin):
         p = self._field(p_prev, "p_prev").clone()
         wbytes = int(self._L.pdecg_ns_workspace_bytes(C.byref(self._cfg), u.shape[0]))
         work = torch.empty((wbytes + 7) // 8, dtype=torch.float64, device=self.device) if wbytes else None
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_ns_solve_pressure(C.byref(self._cfg), u.shape[0], u.data_ptr(), v.data_ptr(), p.data_ptr(),
                                                        None if work is None else work.data_ptr(), self._stream()))
         return p

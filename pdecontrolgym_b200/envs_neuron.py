@@ -125,7 +125,7 @@ class NeuronPDE1D(StateDictMixin):
     def step(self, action=None, n_steps: int = 1):
         """`n_steps` explicit steps of every env in one launch (neuron_env.py:263-339; `action` is ignored like the reference's
         step() takes none).  Returns (u [N, M], reward [N], terminated [N], truncated [N], info)."""
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_neuron_step(C.byref(self._cfg), C.byref(self._buf), int(n_steps), _lib.current_raw_stream(self.device.index)))
         obs = self.u.clone()
         mask = torch.arange(self.M, device=self.device)[None, :] < self.L[:, None]           # new_u = u[:L]  (:324)

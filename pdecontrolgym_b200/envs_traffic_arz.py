@@ -96,6 +96,7 @@ class TrafficPDE1D(StateDictMixin):
         cfg.c4 = 0.5 * dt / tau                                            # :221
         cfg.vm_over_rm = v_max / ro_max                                    # :84
         cfg.precision = _lib.PREC[precision]
+        self._nact = int(cfg.action_dim)
         self._cfg = cfg
         self._L = _lib.lib()
         dev = self.device
@@ -157,7 +158,7 @@ class TrafficPDE1D(StateDictMixin):
         return _lib.current_raw_stream(self.device.index)
 
     def _reset_kernel(self, mask_t):
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_arz_reset(C.byref(self._cfg), C.byref(self._buf), self._profile.data_ptr(),
                                                None if mask_t is None else mask_t.data_ptr(), self._stream()))
 
@@ -190,16 +191,20 @@ class TrafficPDE1D(StateDictMixin):
     def step(self, action):
         """traffic_arz_env.py:131-233: clip the flow-rate action(s), `control_freq` Lax-Wendroff substeps,
         reward, terminate / truncate -- one kernel launch for all envs."""
-        nact = self._cfg.action_dim
-        if isinstance(action, torch.Tensor):
-            a = action.to(self.device, torch.float64)
+        nact = self._nact
+        if (isinstance(action, torch.Tensor) and action.dtype == torch.float64 and action.dim() == 2 and action.shape[0] == self.num_envs
+                and action.shape[1] == nact and action.device == self.device and action.is_contiguous()):
+            a = action                         # already in the kernel's layout: nothing to do
         else:
-            a = torch.from_numpy(np.ascontiguousarray(np.asarray(action, dtype=np.float64))).to(self.device)
-        if a.numel() == nact and self.num_envs != 1:
-            a = a.reshape(1, nact).expand(self.num_envs, nact)
-        if a.numel() != self.num_envs * nact:
-            raise ValueError(f"action must have shape ({self.num_envs}, {nact})")
-        a = a.reshape(self.num_envs, nact).contiguous()
+            if isinstance(action, torch.Tensor):
+                a = action.to(self.device, torch.float64)
+            else:
+                a = torch.from_numpy(np.ascontiguousarray(np.asarray(action, dtype=np.float64))).to(self.device)
+            if a.numel() == nact and self.num_envs != 1:
+                a = a.reshape(1, nact).expand(self.num_envs, nact)
+            if a.numel() != self.num_envs * nact:
+                raise ValueError(f"action must have shape ({self.num_envs}, {nact})")
+            a = a.reshape(self.num_envs, nact).contiguous()
         buf = self._buf
         buf.action = a.data_ptr()
         # the kernels write reward / flags (and, with copy_obs, the observation) straight into fresh tensors handed to
@@ -214,7 +219,7 @@ class TrafficPDE1D(StateDictMixin):
         buf.final_obs = self._final_obs.data_ptr() if (fused and self._final_obs is not None) else None
         info = self.info
         try:
-            with torch.cuda.device(self.device):
+            with _lib.device_guard(self.device):
                 if fused:
                     _lib.check(self._L.pdecg_arz_step_autoreset(C.byref(self._cfg), C.byref(buf), self._profile.data_ptr(), self._stream()))
                 else:
@@ -255,7 +260,7 @@ class TrafficPDE1D(StateDictMixin):
         fused = self.autoreset and self.simulation_type != "outlet-train"
         if self.autoreset and not fused:
             raise NotImplementedError("step_host with autoreset is not available for 'outlet-train' (rs is re-drawn on the host)")
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(self._L.pdecg_arz_step_host(
                 C.byref(self._cfg), C.byref(buf), a_ptr,
                 _lib.host_ptr(obs_host, self.state_dtype, N * 2 * self.M, "obs_host"),
