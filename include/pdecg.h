@@ -167,9 +167,11 @@ int pdecg_bc1d_step_autoreset(const pdecg_bc1d_cfg* cfg, const pdecg_bc1d_buffer
                               const pdecg_bc1d_autoreset* autoreset, pdecg_stream_t stream);
 
 /* Same step, but `action_host` ([n_envs], cfg.action_dtype) and the outputs are HOST buffers:
- * H2D(actions) -> kernel -> D2H(obs, reward, flags), then synchronised.  The batch is cut into chunks that
- * rotate over four library-owned streams ordered after `stream`, so the copy-out of one chunk overlaps the
- * kernels of the next ones.  obs_host is [n_envs, npts] for FULL sensing, [n_envs] S otherwise; any output
+ * H2D(actions) -> kernel -> D2H(obs, reward, flags), then synchronised.  All actions go up in one transfer on
+ * `stream`; the batch is then cut into chunks (a short first one, so that the copy-out starts early) that rotate
+ * over four library-owned streams ordered after it, so the observation copy of one chunk overlaps the kernels of
+ * the next ones; reward and flags leave in one transfer each on a fifth stream once the last kernels have run.
+ * obs_host is [n_envs, npts] for FULL sensing, [n_envs] S otherwise; any output
  * pointer may be NULL to skip that copy.  For FULL sensing the observation is copied out of buf->obs_copy when the
  * caller provides that device buffer (dtype S, or float32 with obs_copy_f32 -- half the PCIe bytes of a float64
  * state), else straight out of the state.  Device buffers in `buf` are still the caller's (buf->action is the
