@@ -227,3 +227,37 @@ def test_staggered_clocks_and_both_lane_mappings(cuda_device, monkeypatch, mappi
         assert np.array_equal(env.time_index.cpu().numpy(), orc.time_index)
         mixed |= bool((orc.time_index >= 5.0).any() and (orc.time_index < 5.0).any())
     assert mixed or B == 1
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_physical_parameters(cuda_device, seed):
+    """The deferred-check division path must stay bit-identical for any physical parameter set, not only the tutorial's:
+    random (vm, rm, tau, steady state, grid, control_freq, simulation type) per case, random in-range actions, 150 steps."""
+    import torch
+    import pdecontrolgym_b200 as pcg
+    rng = np.random.default_rng(100 + seed)
+    st = ["inlet", "outlet", "both"][seed % 3]
+    dx = float(rng.choice([5.0, 8.0, 10.0, 12.5, 20.0]))
+    X = float(rng.choice([300.0, 500.0, 640.0]))
+    vm, rm = float(rng.uniform(25, 60)), float(rng.uniform(0.1, 0.3))
+    kw = dict(T=30, dt=0.2 * dx / vm * float(rng.uniform(0.6, 1.0)) * 4, X=X, dx=dx, simulation_type=st, control_freq=int(rng.integers(1, 4)),
+              v_max=vm, ro_max=rm, tau=float(rng.uniform(20, 120)), ro_steady=float(rng.uniform(0.3, 0.8)) * rm,
+              limit_pde_state_size=bool(seed & 1))
+    kw["v_steady"] = vm * (1 - kw["ro_steady"] / rm)
+    B = 5
+    env = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, reward_class=pcg.TrafficARZReward(), **kw)
+    orc = O.TrafficARZOracle(B, **kw)
+    assert np.array_equal(env.reset()[0].cpu().numpy(), orc.reset())
+    qs = kw["ro_steady"] * kw["v_steady"]
+    nact = 2 if st == "both" else 1
+    with np.errstate(all="ignore"):
+        for k in range(150):
+            a = rng.uniform(0.75 * qs, 1.25 * qs, size=(B, nact))
+            o_r, r_r, te_r, tr_r = orc.step(a)
+            o_g, r_g, te_g, tr_g, _ = env.step(torch.from_numpy(a))
+            g = o_g.cpu().numpy()
+            fin = np.isfinite(o_r)
+            assert np.array_equal(np.isnan(g), np.isnan(o_r)) and np.array_equal(g[fin].view(np.uint64), o_r[fin].view(np.uint64)), f"step {k}: obs"
+            ok = np.isfinite(r_r)
+            np.testing.assert_allclose(r_g.cpu().numpy()[ok], r_r[ok], rtol=1e-12)
+            assert np.array_equal(te_g.cpu().numpy(), te_r) and np.array_equal(tr_g.cpu().numpy(), tr_r), f"step {k}: flags"
