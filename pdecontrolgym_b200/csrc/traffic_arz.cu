@@ -1,4 +1,4 @@
-// traffic_arz.cu -- TrafficPDE1D (Aw-Rascle-Zhang) step / reset kernels + C ABI (sm_100a, float64).
+// traffic_arz.cu -- TrafficPDE1D (Aw-Rascle-Zhang) step / reset kernels + C ABI (sm_100a; float64, opt-in float32).
 //
 // Reference behaviour restated here (no code shared): traffic_arz_env.py:23-280 and
 // rewards/traffic_arz_reward.py:12-22 of lukebhan/PDEControlGym.
@@ -9,9 +9,6 @@
 // between the two cells that use them -- bit-identical to the reference, which evaluates them twice.
 #include "pdecg_internal.h"
 
-#ifndef PDECG_BT_MINBLOCKS
-#define PDECG_BT_MINBLOCKS 1
-#endif
 #ifndef PDECG_ARZ_MINBLOCKS
 #define PDECG_ARZ_MINBLOCKS 8    // 64 registers, 32 warps/SM (measured at 262k envs: 10 -> 0.187, 9 -> 0.185, 8 -> 0.178, 7 -> 0.180, 6 -> 0.189 ms)
 #endif
