@@ -159,9 +159,130 @@ __device__ __forceinline__ T* jacobi(const pdecg_ns_cfg& cfg, T* pa, T* pb, cons
     return pa;
 }
 
+// 0.25 * (acc - b) in the reference's two roundings (float64); the float32 fast mode folds it into one FMA on b' = -b/4
+__device__ __forceinline__ double jacobi_update(double acc, double b) { return D::mul(0.25, D::sub(acc, b)); }
+__device__ __forceinline__ float jacobi_update(float acc, float bq) { return __fmaf_rn(acc, 0.25f, bq); }
+__device__ __forceinline__ double jacobi_rhs(double b) { return b; }
+__device__ __forceinline__ float jacobi_rhs(float b) { return __fmul_rn(-0.25f, b); }
+
+// The same N sweeps with the pressure in REGISTERS (grids up to 82 x 82): the interior is tiled over the CTA as 16 thread
+// columns x (2 per warp) thread rows of 5 x BC points.  By the sweep identity above only the interior is iterated, with
+// clamped neighbours at the domain edge; inside a block neighbours are registers, left / right come from 16-lane
+// shuffles, up / down from the partner half-warp by shuffle and from the adjacent warps through a double-buffered edge
+// array in shared memory -- one block barrier and no other shared-memory traffic per sweep (the generic form above reads
+// four neighbours and writes one value per point per sweep through shared memory: 2.5 Jacobi points per clock per SM at
+// 41 x 41, against the FP64 pipe's 6.4).  The first sweep reads the true boundary values of the warm-start pressure from
+// shared memory; the result goes back to `sp` (interior, then the boundary copies).  blockDim.x = 32 * ceil(ceil((ny-2)/5)/2).
+constexpr int kBlkRows = 5;
+template <int BC, typename T>
+__device__ __forceinline__ void jacobi_blk(const pdecg_ns_cfg& cfg, T* sp, const T* sb, T* edges, int tid, int nthreads) {
+    using S = Strict<T>;
+    constexpr int BR = kBlkRows, EW = 16 * BC;
+    const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny, NXI = nx - 2, NYI = ny - 2;
+    if (cfg.n_pressure_iters < 1) return;
+    const int warp = tid >> 5, nwarps = nthreads >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    const bool odd = (ty & 1) != 0;
+    const int i0 = ty * BR, j0 = tx * BC;
+    T p[BR][BC], n[BR][BC], b[BR][BC];
+#pragma unroll
+    for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < BC; ++cc) {
+            const int i = i0 + rr, j = j0 + cc;
+            const bool ok = i < NYI && j < NXI;
+            const int q = ok ? (i + 1) * nx + (j + 1) : nx + 1;
+            b[rr][cc] = ok ? jacobi_rhs(sb[q]) : T(0);
+            T acc = S::add(sp[q - 1], sp[q - nx]);          // sweep 1: true neighbours, incl. the stored boundary values
+            acc = S::add(acc, sp[q + 1]);
+            acc = S::add(acc, sp[q + nx]);
+            p[rr][cc] = ok ? jacobi_update(acc, b[rr][cc]) : T(0);
+        }
+    // clamps at the domain edge: the neighbour beyond it is the point itself.  Top / left sit on a block boundary (select
+    // on the halo); the last interior row / column may sit at any slot of one thread row / column.
+    const int lb = NYI - 1, lr = NXI - 1;
+    const bool is_top = ty == 0, is_left = tx == 0;
+    const int sb_slot = (lb / BR == ty) ? lb - ty * BR : -1, sr_slot = (lr / BC == tx) ? lr - tx * BC : -1;
+    auto sweep = [&](const T (&src)[BR][BC], T (&dst)[BR][BC], int par) {
+        T up_h[BC], dn_h[BC], lf_h[BR], rt_h[BR];
+        T* e_mine = edges + ((par * nwarps + warp) * 2) * EW;                  // [top | bottom] rows of this warp
+#pragma unroll
+        for (int cc = 0; cc < BC; ++cc) {
+            const T pub = odd ? src[0][cc] : src[BR - 1][cc];                 // what the partner thread row needs from me
+            const T got = __shfl_xor_sync(kFull, pub, 16);
+            if (odd) e_mine[EW + tx * BC + cc] = src[BR - 1][cc];              // my bottom row -> warp + 1's up halo
+            else e_mine[tx * BC + cc] = src[0][cc];                            // my top row    -> warp - 1's down halo
+            up_h[cc] = got;
+            dn_h[cc] = got;
+        }
+        __syncthreads();
+        {
+            const T* e_up = edges + ((par * nwarps + (warp > 0 ? warp - 1 : 0)) * 2 + 1) * EW + tx * BC;              // bottom row of the warp above
+            const T* e_dn = edges + ((par * nwarps + (warp < nwarps - 1 ? warp + 1 : nwarps - 1)) * 2) * EW + tx * BC;   // top row of the warp below
+#pragma unroll
+            for (int cc = 0; cc < BC; ++cc) {
+                const T far = odd ? e_dn[cc] : e_up[cc];
+                if (odd) dn_h[cc] = far; else up_h[cc] = far;
+                if (is_top) up_h[cc] = src[0][cc];
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < BR; ++rr) {
+            lf_h[rr] = __shfl_up_sync(kFull, src[rr][BC - 1], 1, 16);
+            rt_h[rr] = __shfl_down_sync(kFull, src[rr][0], 1, 16);
+            if (is_left) lf_h[rr] = src[rr][0];
+        }
+#pragma unroll
+        for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < BC; ++cc) {
+                const T self = src[rr][cc];
+                const T up = (rr > 0) ? src[rr > 0 ? rr - 1 : 0][cc] : up_h[cc];
+                T dn = (rr < BR - 1) ? src[rr < BR - 1 ? rr + 1 : 0][cc] : dn_h[cc];
+                const T lf = (cc > 0) ? src[rr][cc > 0 ? cc - 1 : 0] : lf_h[rr];
+                T rt = (cc < BC - 1) ? src[rr][cc < BC - 1 ? cc + 1 : 0] : rt_h[rr];
+                dn = (sb_slot == rr) ? self : dn;
+                rt = (sr_slot == cc) ? self : rt;
+                T acc = S::add(lf, up);                      // ((left + up) + right) + down
+                acc = S::add(acc, rt);
+                acc = S::add(acc, dn);
+                dst[rr][cc] = jacobi_update(acc, b[rr][cc]);
+            }
+    };
+    int it = 1;
+    for (; it + 2 <= cfg.n_pressure_iters; it += 2) {       // register ping-pong
+        sweep(p, n, 0);
+        sweep(n, p, 1);
+    }
+    if (it < cfg.n_pressure_iters) {
+        sweep(p, n, 0);
+#pragma unroll
+        for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < BC; ++cc) p[rr][cc] = n[rr][cc];
+    }
+    __syncthreads();                                         // every thread has read what it needs of the old sp
+#pragma unroll
+    for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < BC; ++cc) {
+            const int i = i0 + rr, j = j0 + cc;
+            if (i < NYI && j < NXI) sp[(i + 1) * nx + (j + 1)] = p[rr][cc];
+        }
+    __syncthreads();
+    // boundary values = nearest interior value (the four Neumann copies of :110-113, in their order)
+    for (int q = tid; q < npt; q += nthreads) {
+        const int i = q / nx, j = q - i * nx;
+        if (i < 1 || i > ny - 2 || j < 1 || j > nx - 2) sp[q] = sp[clampi(i, 1, ny - 2) * nx + clampi(j, 1, nx - 2)];
+    }
+    __syncthreads();
+}
+
 // THREADS x PT >= nx*ny: (256, 2) up to 512 points, (512, 4) up to 2,048, (1024, 4) up to 4,096 (64 x 64; the seven
 // float64 fields of one env then fill the SM's 227 KB of shared memory)
-template <int THREADS, int PT, typename T>
+// BC = 0: the shared-memory Jacobi above (any thread count).  BC = 1..5: the register-blocked Jacobi (jacobi_blk) with BC
+// points per thread per row; the launch then uses 32 * ceil(ceil((ny-2)/5)/2) <= THREADS threads and no pong buffer.
+template <int THREADS, int PT, typename T, int BC = 0>
 __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
     using S = Strict<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -170,13 +291,19 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
     const int nx = cfg.nx, ny = cfg.ny, npt = nx * ny;
     const int tid = threadIdx.x, nth = blockDim.x;
     const int64_t env = blockIdx.x;
-    T* su = smem;                 // u  -> u_next
-    T* sv = su + npt;             // v  -> v_next
-    T* sus = sv + npt;            // u* (predictor)
-    T* svs = sus + npt;           // v*
-    T* sp0 = svs + npt;           // pressure ping
-    T* sp1 = sp0 + npt;           // pressure pong
-    T* sb = sp1 + npt;            // (dx*dy) * rhs
+    // BC = 0: seven fields.  BC > 0: four -- u / v are dead after the predictor, so the right-hand side and the pressure
+    // take their place, and the corrector updates u* / v* in place (more CTAs per SM: 54 KB instead of 94 KB at 41 x 41).
+    T* su = smem;                 // u  -> u_next                      | BC > 0: u, then (dx*dy) * rhs
+    T* sv = su + npt;             // v  -> v_next                      | BC > 0: v, then the pressure
+    T* sus = sv + npt;            // u* (predictor)                    | BC > 0: ... -> u_next
+    T* svs = sus + npt;           // v*                                | BC > 0: ... -> v_next
+    T* sp0 = (BC > 0) ? sv : svs + npt;           // pressure (ping)
+    T* sp1 = sp0 + npt;                           // pressure pong (BC = 0 only)
+    T* sb = (BC > 0) ? su : sp1 + npt;            // (dx*dy) * rhs
+    T* edges = svs + npt;         // BC > 0: [2][warps][2][16 * BC] rows exchanged between adjacent warps
+    T* fu = (BC > 0) ? sus : su;  // where u_next / v_next end up
+    T* fv = (BC > 0) ? svs : sv;
+    (void)sp1; (void)edges;
     __shared__ double red[THREADS / 32];
 
     const T dx = static_cast<T>(cfg.dx), dy = static_cast<T>(cfg.dy), dt = static_cast<T>(cfg.dt);
@@ -198,7 +325,9 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
                     sb[q] = D::mul(dxdy, D::mul(rho_dt, D::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
             }
             __syncthreads();
-            double* pf = jacobi<PT, double>(cfg, sp0, sp1, sb, tid, nth);
+            double* pf;
+            if constexpr (BC > 0) { jacobi_blk<BC, double>(cfg, sp0, sb, edges, tid, nth); pf = sp0; }
+            else pf = jacobi<PT, double>(cfg, sp0, sp1, sb, tid, nth);
             for (int q = tid; q < npt; q += nth) gp[q] = pf[q];
         }
         return;
@@ -229,7 +358,11 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
     T* gp = reinterpret_cast<T*>(a.buf.p) + env * npt;
     const double action_d = a.buf.action[env];
     const T action = static_cast<T>(action_d);
-    for (int q = tid; q < npt; q += nth) { su[q] = gu[q]; sv[q] = gv[q]; sp0[q] = gp[q]; }
+    for (int q = tid; q < npt; q += nth) {
+        su[q] = gu[q];
+        sv[q] = gv[q];
+        if constexpr (BC == 0) sp0[q] = gp[q];
+    }
     __syncthreads();
 
     // ---- predictor (:130-138) ----
@@ -258,9 +391,12 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
         if (i >= 1 && i <= ny - 2 && j >= 1 && j <= nx - 2)
             bv = S::mul(dxdy, S::mul(rho_dt, S::add(cd_x(sus, i, j, nx, two_dx), cd_y(svs, i, j, nx, two_dy))));
         sb[q] = bv;
+        if constexpr (BC > 0) sp0[q] = gp[q];            // the warm-start pressure takes v's place
     }
     __syncthreads();
-    T* pf = jacobi<PT, T>(cfg, sp0, sp1, sb, tid, nth);
+    T* pf;
+    if constexpr (BC > 0) { jacobi_blk<BC, T>(cfg, sp0, sb, edges, tid, nth); pf = sp0; }
+    else pf = jacobi<PT, T>(cfg, sp0, sp1, sb, tid, nth);
 
     // ---- corrector (:143-146) ----
     const T dt_rho = S::div(dt, rho);
@@ -271,11 +407,11 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
             un = S::sub(un, S::mul(dt_rho, cd_x(pf, i, j, nx, two_dx)));
             vn = S::sub(vn, S::mul(dt_rho, cd_y(pf, i, j, nx, two_dy)));
         }
-        su[q] = un;
-        sv[q] = vn;
+        fu[q] = un;
+        fv[q] = vn;
     }
     __syncthreads();
-    apply_boundary<T>(cfg, su, sv, action, tid, nth);
+    apply_boundary<T>(cfg, fu, fv, action, tid, nth);
 
     // ---- store, observation U[t], reward (:147-157, ns_reward.py:28) ----
     const int t1 = t0 + 1;
@@ -283,7 +419,7 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
     T* gobs = obs_all + env * npt * 2;
     double ss = 0.0;
     for (int q = tid; q < npt; q += nth) {
-        const T un = su[q], vn = sv[q];
+        const T un = fu[q], vn = fv[q];
         gu[q] = un;
         gv[q] = vn;
         gp[q] = pf[q];
@@ -313,7 +449,7 @@ __global__ void __launch_bounds__(THREADS) ns_step_kernel(const NsArgs a) {
     if (a.ar_u != nullptr && t1 >= cfg.nt - 1) {          // same-step auto-reset (block-uniform condition)
         if (fobs_all != nullptr) {                        // terminal observation U[nt-1] for the caller
             T* fobs = fobs_all + env * npt * 2;
-            for (int q = tid; q < npt; q += nth) { fobs[2 * q] = su[q]; fobs[2 * q + 1] = sv[q]; }
+            for (int q = tid; q < npt; q += nth) { fobs[2 * q] = fu[q]; fobs[2 * q + 1] = fv[q]; }
         }
         __syncthreads();                                  // the step's own field / observation stores come first
         ns_reset_env<T>(a, a.ar_u, a.ar_v, a.ar_p, a.ar_stride, env, tid, nth, true);
@@ -348,10 +484,6 @@ __global__ void __launch_bounds__(kNsThreads) ns_reset_kernel(const NsArgs a, co
 // shared memory, so an arbitrary initial pressure field is handled exactly.
 // All 32 lanes run the whole kernel in lock step whatever their env's state: a segment whose env does not exist or
 // is past its last step computes on zeros and stores nothing, so every shuffle / barrier names the full warp.
-// 0.25 * (acc - b) in the reference's two roundings (float64); the float32 fast mode folds it into one FMA on b' = -b/4
-__device__ __forceinline__ double jacobi_update(double acc, double b) { return D::mul(0.25, D::sub(acc, b)); }
-__device__ __forceinline__ float jacobi_update(float acc, float bq) { return __fmaf_rn(acc, 0.25f, bq); }
-
 template <int N, int BR, int BC, int RG, int CG, int WPB, int LPE, typename T>
 __global__ void __launch_bounds__(WPB * 32) ns_step_warp_kernel(const NsArgs a) {
     static_assert(LPE == 32 || LPE == 16, "32 or 16 lanes per env");
@@ -667,8 +799,36 @@ static int ns_launch_generic_t(const NsArgs& a, int64_t n_envs, size_t smem, cud
     count_launch();
     return check_launch("ns_step_kernel");
 }
+// register-blocked Jacobi: 16 thread columns x BC points cover the interior width, 5-point thread rows the height
+template <int BC>
+static int ns_launch_blk_t(const NsArgs& a, int64_t n_envs, cudaStream_t st) {
+    const int rows = (a.cfg.ny - 2 + kBlkRows - 1) / kBlkRows, warps = (rows + 1) / 2;
+    const size_t esz = ns_f32(&a.cfg) ? sizeof(float) : sizeof(double);
+    const size_t smem = (static_cast<size_t>(4) * a.cfg.nx * a.cfg.ny + static_cast<size_t>(2) * warps * 2 * 16 * BC) * esz;
+    void (*kern)(const NsArgs) = ns_f32(&a.cfg) ? ns_step_kernel<256, 1, float, BC> : ns_step_kernel<256, 1, double, BC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(PDECG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<static_cast<unsigned>(n_envs), warps * 32, smem, st>>>(a);
+    count_launch();
+    return check_launch("ns_step_kernel (register-blocked Jacobi)");
+}
 static int ns_launch_generic(const NsArgs& a, int64_t n_envs, cudaStream_t st) {
     const int npt = a.cfg.nx * a.cfg.ny;
+    // Register-blocked Jacobi up to 50 x 50 (1..3 points per thread per row): 3.29 vs 4.32 ms per 1,024-env step at
+    // 41 x 41.  Wider blocks lose to the shared-memory form (7.02 vs 5.86 ms per 592-env step at 64 x 64): with a runtime
+    // grid size the clamp at the last interior row / column is a select on every point, ~19 instructions per point-sweep
+    // of which 5 are FP64, and the launch turns issue-bound; PDECG_NS_BLK_JACOBI forces it for any on-chip grid (tests).
+    const int bc = (a.cfg.nx - 2 + 15) / 16;
+    const bool force = getenv("PDECG_NS_BLK_JACOBI") != nullptr;
+    if (a.cfg.nx - 2 <= 16 * 5 && a.cfg.ny - 2 <= 16 * kBlkRows && (bc <= 3 || force) && !getenv("PDECG_NS_SMEM_JACOBI")) {
+        switch (bc) {
+            case 0: case 1: return ns_launch_blk_t<1>(a, n_envs, st);
+            case 2: return ns_launch_blk_t<2>(a, n_envs, st);
+            case 3: return ns_launch_blk_t<3>(a, n_envs, st);
+            case 4: return ns_launch_blk_t<4>(a, n_envs, st);
+            default: return ns_launch_blk_t<5>(a, n_envs, st);
+        }
+    }
     const size_t smem = ns_smem_bytes(&a.cfg);
     if (npt <= 2 * 256) return ns_launch_generic_t<256, 2>(a, n_envs, smem, st);
     if (npt <= 4 * 512) return ns_launch_generic_t<512, 4>(a, n_envs, smem, st);

@@ -53,9 +53,19 @@ def test_vs_oracle(cuda_device, bc, iters):
         assert np.array_equal(te_g.cpu().numpy(), te_r) and not tr_g.any()
 
 
-@pytest.mark.parametrize("n", [5, 8, 11, 16, 22, 23, 41, 45, 46, 64])      # 23..45: 512 threads x 4 points, 46..64: 1024 x 4
-def test_grid_sizes(cuda_device, n):
+@pytest.mark.parametrize("jacobi", ["registers", "shared_memory"])
+@pytest.mark.parametrize("n", [5, 7, 8, 11, 12, 16, 18, 22, 23, 34, 41, 45, 46, 50, 63, 64])
+def test_grid_sizes(cuda_device, monkeypatch, n, jacobi):
+    """On-chip grids other than 21 x 21: the CTA kernel with the register-blocked Jacobi (16 thread columns x 1..5 points,
+    5-point thread rows; the sizes straddle its block / warp boundaries) and, behind PDECG_NS_SMEM_JACOBI, the
+    shared-memory Jacobi (256 x 2, 512 x 4, 1024 x 4 threads x points)."""
     import torch
+    if jacobi == "shared_memory":
+        if n in (7, 12, 18, 34, 50, 63):
+            pytest.skip("one size per instantiation is enough for the fallback form")
+        monkeypatch.setenv("PDECG_NS_SMEM_JACOBI", "1")
+    else:
+        monkeypatch.setenv("PDECG_NS_BLK_JACOBI", "1")          # also beyond 50 x 50, where it is not the default
     env, orc, nt = make_pair(cuda_device, 2, BC_MIX, 25, n=n, T=0.02 * (20 / (n - 1)) ** 2)
     rng = np.random.default_rng(n)
     u0, v0, p0 = (rng.uniform(-1, 1, (2, n, n)) for _ in range(3))
@@ -276,3 +286,24 @@ def test_fp32_rejects_what_it_does_not_cover(cuda_device):
     with pytest.raises(Exception, match="on-chip"):
         e2, _, _ = make_pair(cuda_device, 1, BC_REF, 5, n=81, T=0.002, precision="fp32")
         e2.reset(options={"init": (np.zeros((81, 81)),) * 3})
+
+
+@pytest.mark.parametrize("iters", [0, 1, 2, 3, 38])
+@pytest.mark.parametrize("n", [30, 52])
+def test_register_blocked_jacobi_sweep_counts(cuda_device, monkeypatch, n, iters):
+    """Odd / even / degenerate sweep counts of the register-blocked Jacobi (first sweep from shared memory, register
+    ping-pong, tail sweep), warm-started from a random pressure field with non-trivial boundary values."""
+    import torch
+    monkeypatch.setenv("PDECG_NS_BLK_JACOBI", "1")
+    env, orc, nt = make_pair(cuda_device, 3, BC_MIX, iters, n=n, T=0.02 * (20 / (n - 1)) ** 2)
+    rng = np.random.default_rng(100 * n + iters)
+    u0, v0, p0 = (rng.uniform(-1, 1, (3, n, n)) for _ in range(3))
+    env.reset(options={"init": (u0, v0, p0)})
+    orc.reset(u0, v0, p0)
+    for k in range(min(4, nt - 1)):
+        a = rng.uniform(-2, 2, 3)
+        o_r, r_r, te_r, _ = orc.step(a)
+        o_g, r_g, te_g, _, _ = env.step(torch.from_numpy(a))
+        assert np.array_equal(o_g.cpu().numpy(), o_r), f"step {k}: fields"
+        assert np.array_equal(env.p.cpu().numpy(), orc.p), f"step {k}: pressure"
+        np.testing.assert_allclose(r_g.cpu().numpy(), r_r, rtol=1e-12)
