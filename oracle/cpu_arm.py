@@ -211,6 +211,9 @@ def lockstep_rate(workload, cores=None, k_envs=1, rounds=None, seconds=None, war
         c.send(None)
     for p in procs:
         p.join(timeout=5)
+        if p.is_alive():            # never leave a worker behind: the GPU legs that follow are timed on the same host
+            p.terminate()
+            p.join(timeout=5)
     what = ("the reference's own classes (unmodified files staged in oracle/_ref, numpy)" if impl == "reference"
             else "numpy oracle (port of the reference's numpy path; no reference tree found)")
     return {"value": n * cores * k_envs / wall, "rounds": n, "wall_s": wall, "cores": cores, "kind": impl, "envs": cores * k_envs,
