@@ -152,10 +152,10 @@ def test_empty_batch_and_errors(cuda_device):
 
 
 @pytest.mark.parametrize("autoreset", [False, True])
-@pytest.mark.parametrize("N", [3, 4099, 20001])
+@pytest.mark.parametrize("N", [3, 4099, 20001, 40003])      # 1 / 2 / 5 / 9 chunks (a short first one) over four streams
 def test_step_host_matches_device_step(cuda_device, N, autoreset):
-    """pdecg_bc1d_step_host (H2D -> chunked, two-stream pipelined kernels -> D2H) == pdecg_bc1d_step, with and
-    without the fused same-step auto-reset (per-env initial rows: the chunk offsets matter)."""
+    """pdecg_bc1d_step_host (one H2D -> chunked kernels pipelined over four streams -> D2H per chunk, reward / flags once)
+    == pdecg_bc1d_step, with and without the fused same-step auto-reset (per-env initial rows: the chunk offsets matter)."""
     import torch
     import pdecontrolgym_b200 as pcg
     kw, npts, beta, nt = bc1d_case("rd", None, 3)
