@@ -696,7 +696,7 @@ def run_ours(args):
     bytes_per_launch = E * bytes_per_env + NX_PTS * 8
     traffic = None                # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_rd_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_rd_traffic.json")) as f:
             traffic = float(json.load(f)["dram_bytes_per_launch"]) if E == 65536 else None
     except Exception:  # noqa: BLE001
         pass
@@ -756,7 +756,7 @@ def run_ours(args):
         "config": headline_config(E, world),
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / fp64_peak_tflops, "traffic": traffic,
-                     "traffic_source": "profiles/r1_rd_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full launch)",
+                     "traffic_source": "profiles/r2_rd_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full launch)",
                      "kernel": "bc1d_step_kernel<RD, ModeFp64, K=13, fast, 16 lanes/env>", "kernel_ms": k_ms,
                      "kernel_share_of_step": k_ms * K / ms_total,
                      "flops_per_launch": flops_per_launch,
