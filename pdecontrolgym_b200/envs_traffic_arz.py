@@ -172,7 +172,10 @@ class TrafficPDE1D(StateDictMixin):
         if self.simulation_type == "outlet-train":
             rs = options.get("rs")
             if rs is None:
-                rs = np.array([_RS_VALUES[random.randint(0, 2)] for _ in range(self.num_envs)], dtype=np.float64)
+                # one draw per env that actually resets, in env order (the reference draws once per reset() call, :251)
+                which = np.arange(self.num_envs) if mask_t is None else np.flatnonzero(mask_t.cpu().numpy())
+                rs = np.full(self.num_envs, _RS_VALUES[1], dtype=np.float64)
+                rs[which] = [_RS_VALUES[random.randint(0, 2)] for _ in range(which.size)]
             rs = np.broadcast_to(np.asarray(rs, dtype=np.float64), (self.num_envs,)).copy()
             vs = self.Veq(self.vm, self.rm, rs)
             self._set_steady(rs, vs, rs * vs, None if mask_t is None else mask_t.bool())
@@ -225,7 +228,9 @@ class TrafficPDE1D(StateDictMixin):
                 else:
                     _lib.check(self._L.pdecg_arz_step(C.byref(self._cfg), C.byref(buf), self._stream()))
             terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
-            if self.autoreset and not fused:
+            if self.autoreset and not fused and bool(torch.bitwise_or(term_u8, trunc_u8).any()):
+                # ('outlet-train' re-draws the steady state on the host: one sync per step to see whether any env finished,
+                # then the masked reset only on the steps that need it)
                 done = torch.bitwise_or(term_u8, trunc_u8)
                 if self._final_obs is not None:
                     self._final_obs.copy_(torch.where(done.bool().unsqueeze(1), obs, self._final_obs))

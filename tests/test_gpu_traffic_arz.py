@@ -261,3 +261,40 @@ def test_random_physical_parameters(cuda_device, seed):
             ok = np.isfinite(r_r)
             np.testing.assert_allclose(r_g.cpu().numpy()[ok], r_r[ok], rtol=1e-12)
             assert np.array_equal(te_g.cpu().numpy(), te_r) and np.array_equal(tr_g.cpu().numpy(), tr_r), f"step {k}: flags"
+
+
+def test_outlet_train_autoreset_redraws_only_finished_envs(cuda_device):
+    """'outlet-train' with autoreset=True: the steady state of an env that finishes is re-drawn on the host with Python's
+    `random` (one draw per finishing env, in env order, like the reference's reset(), traffic_arz_env.py:251-256); envs
+    that go on are untouched, and steps on which nobody finishes do not reset anything.  Compared with a manual
+    step + masked reset driven by the same `random` stream."""
+    import random
+    import torch
+    import pdecontrolgym_b200 as pcg
+    from pdecontrolgym_b200.envs_traffic_arz import F_TIME, _RS_VALUES
+    B, kw = 6, dict(T=2, dt=0.25, X=500, dx=10, simulation_type="outlet-train", control_freq=2, reward_class=pcg.TrafficARZReward(),
+                    rs_init=np.array([0.12, 0.115, 0.125, 0.12, 0.115, 0.125]))
+    auto = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, autoreset=True, **kw)
+    manual = pcg.make("PDEControlGym-TrafficPDE1D", num_envs=B, device=cuda_device, autoreset=False, **kw)
+    rs0 = np.array([0.125, 0.12, 0.115, 0.115, 0.12, 0.125])
+    clocks = torch.tensor([0.0, 6.0, 3.0, 7.5, 1.25, 6.0], dtype=torch.float64, device=cuda_device)   # episodes end at time >= T/dt = 8
+    for e in (auto, manual):
+        e.reset(options={"rs": rs0})
+        e._fenv[:, F_TIME] = clocks
+    rng = np.random.default_rng(2)
+    acts = rng.uniform(0.9, 1.5, size=(40, B, 1))
+    random.seed(11)
+    outs = [tuple(t.clone() for t in auto.step(torch.from_numpy(acts[k]))[:4]) for k in range(40)]
+    random.seed(11)
+    resets = 0
+    for k in range(40):
+        o, r, te, tr, _ = manual.step(torch.from_numpy(acts[k]))
+        done = (te | tr).cpu().numpy()
+        if done.any():
+            resets += 1
+            rs = np.full(B, 0.12)
+            rs[np.flatnonzero(done)] = [_RS_VALUES[random.randint(0, 2)] for _ in range(int(done.sum()))]
+            o, _ = manual.reset(options={"mask": done, "rs": rs})
+        assert torch.equal(outs[k][0], o), f"step {k}: observation"
+        assert torch.equal(outs[k][1], r) and torch.equal(outs[k][2], te) and torch.equal(outs[k][3], tr), f"step {k}"
+    assert 3 <= resets < 40 and torch.equal(auto._fenv, manual._fenv)
