@@ -1,5 +1,10 @@
-import ctypes as C, sys
-sys.path.insert(0, '/root/repo')
+"""Does an FP64 (FP32) warp instruction with 16 active lanes occupy its pipe for less time than one with 32?  (No: the
+warp-instruction rate per SM is the same, so a half-empty warp wastes half of its pipe time.)  python scripts/probe_half_warp.py"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pdecontrolgym_b200 import _lib
 L = _lib.lib()
