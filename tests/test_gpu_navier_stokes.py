@@ -307,3 +307,22 @@ def test_register_blocked_jacobi_sweep_counts(cuda_device, monkeypatch, n, iters
         assert np.array_equal(o_g.cpu().numpy(), o_r), f"step {k}: fields"
         assert np.array_equal(env.p.cpu().numpy(), orc.p), f"step {k}: pressure"
         np.testing.assert_allclose(r_g.cpu().numpy(), r_r, rtol=1e-12)
+
+
+def test_tiled_solve_equals_sweep_by_sweep_at_512(cuda_device):
+    """512 x 512 (81 tiles per env): 40 sweeps through the tiled kernel (4 launches of 10 after the first sweep) equal 40
+    applications of the one-sweep path, bit for bit, for two envs with different fields."""
+    import torch
+    n, B = 512, 2
+    rng = np.random.default_rng(512)
+    kw = dict(n=n, T=0.2 * (20 / (n - 1)) ** 2)
+    env40, _, _ = make_pair(cuda_device, B, BC_REF, 40, **kw)
+    env1, _, _ = make_pair(cuda_device, B, BC_REF, 1, **kw)
+    us, vs, p0 = (rng.uniform(-1, 1, (B, n, n)) for _ in range(3))
+    want = torch.from_numpy(p0.copy()).to(cuda_device)
+    for _ in range(40):
+        want = env1.solve_pressure(us, vs, want)
+    got = env40.solve_pressure(us, vs, p0)
+    assert torch.equal(got, want)
+    p = got.cpu().numpy()
+    assert np.array_equal(p[:, 0, :], p[:, 1, :]) and np.array_equal(p[:, 1:-1, -1], p[:, 1:-1, -2])
